@@ -1,0 +1,250 @@
+/*
+ * vgb.h -- C ABI of libvgb200: B200-native batched path flattening + stroke / convex-fill
+ * mesh generation (hand-written sm_100a CUDA underneath).
+ *
+ * This is the drop-in boundary for the ONE hot path of jdryg/vg-renderer:
+ *
+ *   reference interface                                   replaced by
+ *   ---------------------------------------------------   -----------------------------------
+ *   include/vg/path.h:19-38    vg::createPath ...          vgb_path_*      (per-object, 1:1)
+ *   include/vg/stroker.h:11-70 vg::createStroker ...       vgb_stroker_*   (per-object, 1:1)
+ *   src/vg.cpp:2969-3059 ctxBeginPath/ctxMoveTo/...        vgb_batch_begin_path / vgb_batch_*_to
+ *   src/vg.cpp:3401-3492 ctxStrokePathColor                vgb_batch_stroke
+ *   src/vg.cpp:3061-3179 ctxFillPathColor (convex)         vgb_batch_convex_fill
+ *   src/vg.cpp:4957-4975 transformPath                     xform6 argument of begin_path
+ *   src/vg.cpp:5207-5244 createDrawCommand_VertexColor     VGB_RUN_INDEX_U32 merged buffers /
+ *                                                          vgb_batch_download_bgfx_streams
+ *
+ * Plain C types only: pointers, sizes, PODs.  No torch / CUDA types in any signature
+ * (device pointers are returned as void*).  All functions return 0 on success, a negative
+ * VGB_ERR_* otherwise; vgb_last_error() gives the message for the calling thread.
+ * A vgb_batch is not re-entrant; distinct batches are independent (one CUDA stream each).
+ *
+ * The C++ namespace-vg wrappers that let src/vg.cpp link unchanged are in
+ * include/vgb_dropin.hpp; the reference-side binding is shown in INTEGRATION.md.
+ */
+#ifndef VGB_H
+#define VGB_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VGB_API __attribute__((visibility("default")))
+
+/* ---- error codes -------------------------------------------------------------------- */
+enum {
+	VGB_OK = 0,
+	VGB_ERR_INVALID = -1,   /* bad argument / command sequence (e.g. lineTo before moveTo) */
+	VGB_ERR_NONFINITE = -2, /* NaN/Inf coordinate: the reference never terminates on these */
+	VGB_ERR_CUDA = -3,      /* CUDA runtime failure (message has the cudaError string)      */
+	VGB_ERR_NOGPU = -4,     /* no usable CUDA device: there is NO CPU fallback              */
+	VGB_ERR_CAPACITY = -5,  /* caller buffer too small                                      */
+	VGB_ERR_STATE = -6      /* call out of order (e.g. download before run)                 */
+};
+
+/* ---- enums: numeric values identical to the reference (include/vg/vg.h:156-259) ------ */
+enum { VGB_CAP_BUTT = 0, VGB_CAP_ROUND = 1, VGB_CAP_SQUARE = 2 };  /* vg::LineCap  */
+enum { VGB_JOIN_MITER = 0, VGB_JOIN_ROUND = 1, VGB_JOIN_BEVEL = 2 }; /* vg::LineJoin */
+enum { VGB_WINDING_CCW = 0, VGB_WINDING_CW = 1 };                  /* vg::Winding  */
+
+/* path commands (one per vg::pathXXX builder, include/vg/path.h:23-36); floats consumed */
+enum {
+	VGB_CMD_MOVE_TO = 0,              /* x y                         */
+	VGB_CMD_LINE_TO = 1,              /* x y                         */
+	VGB_CMD_CUBIC_TO = 2,             /* c1x c1y c2x c2y x y         */
+	VGB_CMD_QUAD_TO = 3,              /* cx cy x y                   */
+	VGB_CMD_ARC_TO = 4,               /* x1 y1 x2 y2 r               */
+	VGB_CMD_RECT = 5,                 /* x y w h                     */
+	VGB_CMD_ROUNDED_RECT = 6,         /* x y w h r                   */
+	VGB_CMD_ROUNDED_RECT_VARYING = 7, /* x y w h rtl rtr rbr rbl     */
+	VGB_CMD_CIRCLE = 8,               /* cx cy r                     */
+	VGB_CMD_ELLIPSE = 9,              /* cx cy rx ry                 */
+	VGB_CMD_ARC = 10,                 /* cx cy r a0 a1 dir(0|1)      */
+	VGB_CMD_POLYLINE = 11,            /* n(as uint32 bits) then 2n   */
+	VGB_CMD_CLOSE = 12,               /* -                           */
+	VGB_CMD__COUNT = 13
+};
+
+/* mesh operations (one per vg::strokerXXX entry point, include/vg/stroker.h:29-70) */
+enum {
+	VGB_OP_STROKE_AA = 0,      /* strokerPolylineStrokeAA     pos + color + index */
+	VGB_OP_CONVEX_FILL_AA = 1, /* strokerConvexFillAA         pos + color + index */
+	VGB_OP_STROKE = 2,         /* strokerPolylineStroke       pos + index (color = draw color) */
+	VGB_OP_STROKE_AA_THIN = 3, /* strokerPolylineStrokeAAThin pos + color + index */
+	VGB_OP_CONVEX_FILL = 4     /* strokerConvexFill           pos(copy) + index   */
+};
+
+/* vgb_batch_run flags */
+enum {
+	VGB_RUN_INDEX_U16 = 0, /* per-mesh local uint16 indices: exactly vg::Mesh::m_IndexBuffer */
+	VGB_RUN_INDEX_U32 = 1  /* merged uint32 indices: local + mesh first vertex + vertex_base  */
+};
+
+typedef struct vgb_batch vgb_batch;
+
+/* vg::Mesh (include/vg/vg.h:353-360), C layout */
+typedef struct vgb_mesh {
+	const float* pos;      /* x,y interleaved                        */
+	const uint32_t* color; /* NULL when the op has no per-vertex colour */
+	const uint16_t* index;
+	uint32_t num_vertices;
+	uint32_t num_indices;
+} vgb_mesh;
+
+/* vg::SubPath (include/vg/path.h:11-16) */
+typedef struct vgb_subpath {
+	uint32_t first_vertex;
+	uint32_t num_vertices;
+	uint8_t is_closed;
+} vgb_subpath;
+
+/* result sizes of one run */
+typedef struct vgb_sizes {
+	uint64_t num_vertices;   /* emitted mesh vertices (the metric's unit)  */
+	uint64_t num_indices;
+	uint64_t num_points;     /* flattened polyline points                   */
+	uint32_t num_subpaths;
+	uint32_t num_meshes;     /* = jobs: (draw, sub-path) pairs, some empty  */
+	uint32_t kernel_launches;/* kernels launched by the last run            */
+	uint32_t reserved;
+} vgb_sizes;
+
+/* ---- library ------------------------------------------------------------------------- */
+VGB_API const char* vgb_last_error(void);
+VGB_API int vgb_device_count(void);
+VGB_API const char* vgb_version(void);
+
+/* ---- batched path: record -> run -> read ------------------------------------------------ */
+VGB_API vgb_batch* vgb_batch_create(int device_ordinal);
+VGB_API void vgb_batch_destroy(vgb_batch* b);
+
+/* forget everything recorded; fringe_width = Context::m_FringeWidth (src/vg.cpp:1041) */
+VGB_API int vgb_batch_reset(vgb_batch* b, float fringe_width);
+
+/* ctxBeginPath (src/vg.cpp:2969-2981): pathReset(scale, tol) + strokerReset(scale, tol, fringe).
+ * xform6 = state transform applied between flatten and stroke (transformPath), NULL = identity */
+VGB_API int vgb_batch_begin_path(vgb_batch* b, float scale, float tess_tol, const float* xform6);
+VGB_API int vgb_batch_move_to(vgb_batch* b, float x, float y);
+VGB_API int vgb_batch_line_to(vgb_batch* b, float x, float y);
+VGB_API int vgb_batch_cubic_to(vgb_batch* b, float c1x, float c1y, float c2x, float c2y, float x, float y);
+VGB_API int vgb_batch_quadratic_to(vgb_batch* b, float cx, float cy, float x, float y);
+VGB_API int vgb_batch_arc_to(vgb_batch* b, float x1, float y1, float x2, float y2, float r);
+VGB_API int vgb_batch_rect(vgb_batch* b, float x, float y, float w, float h);
+VGB_API int vgb_batch_rounded_rect(vgb_batch* b, float x, float y, float w, float h, float r);
+VGB_API int vgb_batch_rounded_rect_varying(vgb_batch* b, float x, float y, float w, float h, float rtl, float rtr, float rbr, float rbl);
+VGB_API int vgb_batch_circle(vgb_batch* b, float x, float y, float r);
+VGB_API int vgb_batch_ellipse(vgb_batch* b, float x, float y, float rx, float ry);
+VGB_API int vgb_batch_arc(vgb_batch* b, float x, float y, float r, float a0, float a1, uint32_t dir);
+VGB_API int vgb_batch_polyline(vgb_batch* b, const float* coords, uint32_t num_points);
+VGB_API int vgb_batch_close(vgb_batch* b);
+
+/* draw the current path: one mesh per sub-path, in sub-path order (vg.cpp:3448-3485, 3099-3132).
+ * stroke: op in {VGB_OP_STROKE_AA, VGB_OP_STROKE, VGB_OP_STROKE_AA_THIN}; width is the final
+ * (already scaled/clamped) strokerXXX width.  fill: aa != 0 -> strokerConvexFillAA. */
+VGB_API int vgb_batch_stroke(vgb_batch* b, uint32_t op, uint32_t color, float width, uint32_t cap, uint32_t join);
+VGB_API int vgb_batch_convex_fill(vgb_batch* b, uint32_t color, int aa);
+
+/* bulk recorders for regular workloads (same result as the per-call sequence, one memcpy):
+ * n paths of  moveTo(p[0..1]) cubicTo(p[2..7])  + stroke(op, ...)                              */
+VGB_API int vgb_batch_add_cubic_strokes(vgb_batch* b, const float* p8, uint32_t n, float scale, float tess_tol,
+                                        uint32_t op, uint32_t color, float width, uint32_t cap, uint32_t join);
+/* n paths of  roundedRect(x,y,w,h,r) + convex fill                                             */
+VGB_API int vgb_batch_add_rounded_rect_fills(vgb_batch* b, const float* xywhr, uint32_t n, float scale, float tess_tol,
+                                             uint32_t color, int aa);
+
+/* stroker-only entry (strokerXXX called on caller polylines, no Path object involved):
+ * replaces the flatten stage's output by these polylines; draws then refer to "paths" that are
+ * single sub-paths.  pts = x,y interleaved; sub-path s = pts[first[s] .. first[s]+num[s]).      */
+VGB_API int vgb_batch_set_polylines(vgb_batch* b, const float* pts, uint32_t num_points,
+                                    const uint32_t* first, const uint32_t* num, const uint8_t* closed,
+                                    uint32_t num_subpaths, float scale, float tess_tol);
+/* one draw per polyline sub-path s (after vgb_batch_set_polylines) */
+VGB_API int vgb_batch_draw_polyline(vgb_batch* b, uint32_t subpath, uint32_t op, uint32_t color, float width, uint32_t cap, uint32_t join);
+/* the same draw for every polyline sub-path / every recorded path */
+VGB_API int vgb_batch_draw_all(vgb_batch* b, uint32_t op, uint32_t color, float width, uint32_t cap, uint32_t join);
+
+/* ---- execution ----------------------------------------------------------------------------
+ * upload: host tables -> device (async on the batch stream).  run: all kernels; results stay in
+ * HBM.  vertex_base / index_base are added to merged uint32 indices / reported offsets (multi-GPU
+ * merged buffer: the exclusive scan of per-rank totals).  */
+VGB_API int vgb_batch_upload(vgb_batch* b);
+VGB_API int vgb_batch_run(vgb_batch* b, uint32_t flags, uint64_t vertex_base);
+VGB_API int vgb_batch_sync(vgb_batch* b);
+VGB_API int vgb_batch_get_sizes(vgb_batch* b, vgb_sizes* out);
+
+/* device-resident results (valid until the next run/reset/destroy) */
+VGB_API int vgb_batch_device_ptrs(vgb_batch* b, void** pos, void** color, void** index,
+                                  void** mesh_vtx_off_u64, void** mesh_idx_off_u64,
+                                  void** points, void** subpaths);
+
+/* copy results to host buffers (any may be NULL to skip).  Capacities in elements.
+ * mesh_vtx_off / mesh_idx_off get num_meshes+1 exclusive offsets. */
+VGB_API int vgb_batch_download(vgb_batch* b, float* pos, uint32_t* color, void* index,
+                               uint64_t vtx_capacity, uint64_t idx_capacity,
+                               uint64_t* mesh_vtx_off, uint64_t* mesh_idx_off);
+/* flattened polylines: points (x,y), sub-path table (vg::SubPath layout) */
+VGB_API int vgb_batch_download_paths(vgb_batch* b, float* pts, uint64_t pts_capacity,
+                                     vgb_subpath* subpaths, uint32_t subpath_capacity);
+
+/* one call: upload + run + download into caller (ideally pinned) host buffers, D2H overlapped
+ * with nothing else; the end-to-end path bench.py times.  sizes_out may be NULL. */
+VGB_API int vgb_batch_execute(vgb_batch* b, uint32_t flags, float* pos, uint32_t* color, void* index,
+                              uint64_t vtx_capacity, uint64_t idx_capacity,
+                              uint64_t* mesh_vtx_off, uint64_t* mesh_idx_off, vgb_sizes* sizes_out);
+
+/* elapsed device time (ms, CUDA events on the batch stream) of the kernels of the last run */
+VGB_API int vgb_batch_last_run_ms(vgb_batch* b, float* total_ms, float* flatten_ms, float* stroke_count_ms, float* emit_ms);
+
+/* pinned host memory helpers (cudaHostAlloc / cudaFreeHost) for the host-buffer path */
+VGB_API void* vgb_host_alloc(size_t bytes);
+VGB_API void vgb_host_free(void* p);
+/* raw stream handle (cudaStream_t) of the batch, for callers that time with their own events */
+VGB_API void* vgb_batch_stream(vgb_batch* b);
+
+/* ---- per-object API, 1:1 with include/vg/path.h and include/vg/stroker.h ------------------
+ * Same call pattern, ownership and (absence of) error reporting as the reference: getters and
+ * vgb_mesh pointers are borrowed views valid until the next mutating call on the object. */
+typedef struct vgb_path vgb_path;
+typedef struct vgb_stroker vgb_stroker;
+/* allocator callback = the single virtual of bx::AllocatorI; NULL -> malloc/free */
+typedef void* (*vgb_realloc_fn)(void* user, void* ptr, size_t size, size_t align);
+
+VGB_API vgb_path* vgb_path_create(vgb_realloc_fn alloc, void* user);
+VGB_API void vgb_path_destroy(vgb_path* p);
+VGB_API void vgb_path_reset(vgb_path* p, float scale, float tess_tol);
+VGB_API void vgb_path_move_to(vgb_path* p, float x, float y);
+VGB_API void vgb_path_line_to(vgb_path* p, float x, float y);
+VGB_API void vgb_path_cubic_to(vgb_path* p, float c1x, float c1y, float c2x, float c2y, float x, float y);
+VGB_API void vgb_path_quadratic_to(vgb_path* p, float cx, float cy, float x, float y);
+VGB_API void vgb_path_arc_to(vgb_path* p, float x1, float y1, float x2, float y2, float r);
+VGB_API void vgb_path_rect(vgb_path* p, float x, float y, float w, float h);
+VGB_API void vgb_path_rounded_rect(vgb_path* p, float x, float y, float w, float h, float r);
+VGB_API void vgb_path_rounded_rect_varying(vgb_path* p, float x, float y, float w, float h, float rtl, float rtr, float rbr, float rbl);
+VGB_API void vgb_path_circle(vgb_path* p, float x, float y, float r);
+VGB_API void vgb_path_ellipse(vgb_path* p, float x, float y, float rx, float ry);
+VGB_API void vgb_path_arc(vgb_path* p, float x, float y, float r, float a0, float a1, uint32_t dir);
+VGB_API void vgb_path_polyline(vgb_path* p, const float* coords, uint32_t num_points);
+VGB_API void vgb_path_close(vgb_path* p);
+VGB_API const float* vgb_path_get_vertices(vgb_path* p);
+VGB_API uint32_t vgb_path_get_num_vertices(vgb_path* p);
+VGB_API const vgb_subpath* vgb_path_get_subpaths(vgb_path* p);
+VGB_API uint32_t vgb_path_get_num_subpaths(vgb_path* p);
+
+VGB_API vgb_stroker* vgb_stroker_create(vgb_realloc_fn alloc, void* user);
+VGB_API void vgb_stroker_destroy(vgb_stroker* s);
+VGB_API void vgb_stroker_reset(vgb_stroker* s, float scale, float tess_tol, float fringe_width);
+VGB_API void vgb_stroker_polyline_stroke(vgb_stroker* s, vgb_mesh* mesh, const float* vtx, uint32_t n, int closed, float width, uint32_t cap, uint32_t join);
+VGB_API void vgb_stroker_polyline_stroke_aa(vgb_stroker* s, vgb_mesh* mesh, const float* vtx, uint32_t n, int closed, uint32_t color, float width, uint32_t cap, uint32_t join);
+VGB_API void vgb_stroker_polyline_stroke_aa_thin(vgb_stroker* s, vgb_mesh* mesh, const float* vtx, uint32_t n, int closed, uint32_t color, uint32_t cap, uint32_t join);
+VGB_API void vgb_stroker_convex_fill(vgb_stroker* s, vgb_mesh* mesh, const float* vtx, uint32_t n);
+VGB_API void vgb_stroker_convex_fill_aa(vgb_stroker* s, vgb_mesh* mesh, const float* vtx, uint32_t n, uint32_t color);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* VGB_H */

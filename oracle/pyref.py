@@ -1,0 +1,139 @@
+"""ctypes loader for the ORACLE side (test infrastructure, never the product path).
+
+  RefLib("scalar"|"sse"|"libm")  -> oracle/_ref/libvgref*.so : the reference's own path.cpp /
+                                    stroker.cpp compiled against oracle/bx_shim (oracle/Makefile)
+  OracleLib()                     -> oracle/liboracle.so      : this repo's plain-C restatement
+
+Both expose the same three calls: flatten(cmds) / mesh(op, polyline, ...) / run_batch(tables).
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs import this.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+# command ids / arities mirror include/vgb.h
+CMD_MOVE_TO, CMD_LINE_TO, CMD_CUBIC_TO, CMD_QUAD_TO, CMD_ARC_TO, CMD_RECT, CMD_ROUNDED_RECT, \
+    CMD_ROUNDED_RECT_VARYING, CMD_CIRCLE, CMD_ELLIPSE, CMD_ARC, CMD_POLYLINE, CMD_CLOSE = range(13)
+OP_STROKE_AA, OP_CONVEX_FILL_AA, OP_STROKE, OP_STROKE_AA_THIN, OP_CONVEX_FILL = range(5)
+CAP_BUTT, CAP_ROUND, CAP_SQUARE = 0, 1, 2
+JOIN_MITER, JOIN_ROUND, JOIN_BEVEL = 0, 1, 2
+
+
+class SubPath(C.Structure):
+    _fields_ = [("first_vertex", C.c_uint32), ("num_vertices", C.c_uint32), ("is_closed", C.c_uint8)]
+
+
+def _p(a, t):
+    return a.ctypes.data_as(C.POINTER(t)) if a is not None else None
+
+
+class _Lib:
+    prefix = "vgref"
+
+    def __init__(self, path):
+        if not os.path.exists(path):
+            raise FileNotFoundError(f"{path} missing: run `make -C oracle` (needs /root/reference for _ref)")
+        self.path = path
+        self.lib = C.CDLL(path)
+        self._flatten = getattr(self.lib, self.prefix + "_flatten")
+        self._mesh = getattr(self.lib, self.prefix + "_mesh")
+        self._run = getattr(self.lib, self.prefix + "_run_batch")
+        for f in (self._flatten, self._mesh, self._run):
+            f.restype = C.c_int
+
+    def variant(self):
+        f = getattr(self.lib, self.prefix + "_variant")
+        f.restype = C.c_uint32
+        return f()
+
+    def flatten(self, cmds, data, scale=1.0, tol=0.25, cap=1 << 16):
+        cmds = np.ascontiguousarray(cmds, np.uint8)
+        data = np.ascontiguousarray(data, np.float32)
+        while True:
+            pts = np.empty((cap, 2), np.float32)
+            sp = (SubPath * 4096)()
+            npts, nsp = C.c_uint32(), C.c_uint32()
+            rc = self._flatten(_p(cmds, C.c_uint8), C.c_uint32(len(cmds)), _p(data, C.c_float), C.c_float(scale), C.c_float(tol),
+                               _p(pts, C.c_float), C.c_uint32(cap), sp, C.c_uint32(4096), C.byref(npts), C.byref(nsp))
+            if rc == -5 and cap < (1 << 26):
+                cap *= 8
+                continue
+            if rc != 0:
+                raise RuntimeError(f"flatten rc={rc}")
+            subs = [(sp[i].first_vertex, sp[i].num_vertices, bool(sp[i].is_closed)) for i in range(nsp.value)]
+            return pts[: npts.value].copy(), subs
+
+    def mesh(self, op, vtx, closed=False, color=0xFF0000FF, width=4.0, cap=CAP_BUTT, join=JOIN_MITER,
+             scale=1.0, tol=0.25, fringe=1.0):
+        vtx = np.ascontiguousarray(vtx, np.float32).reshape(-1, 2)
+        vcap, icap = 1 << 17, 1 << 20
+        pos = np.empty((vcap, 2), np.float32)
+        col = np.zeros(vcap, np.uint32)
+        idx = np.empty(icap, np.uint16)
+        nv, ni, hc = C.c_uint32(), C.c_uint32(), C.c_int()
+        rc = self._mesh(C.c_uint32(op), _p(vtx, C.c_float), C.c_uint32(len(vtx)), C.c_int(int(closed)), C.c_uint32(color),
+                        C.c_float(width), C.c_uint32(cap), C.c_uint32(join), C.c_float(scale), C.c_float(tol), C.c_float(fringe),
+                        _p(pos, C.c_float), _p(col, C.c_uint32), _p(idx, C.c_uint16), C.c_uint32(vcap), C.c_uint32(icap),
+                        C.byref(nv), C.byref(ni), C.byref(hc))
+        if rc != 0:
+            raise RuntimeError(f"mesh rc={rc}")
+        return pos[: nv.value].copy(), (col[: nv.value].copy() if hc.value else None), idx[: ni.value].copy()
+
+    def run_batch(self, t, store=True, path_range=None):
+        """t: vg_renderer_b200.tables.BatchTables-like object (numpy arrays). Returns dict."""
+        p0, p1 = path_range if path_range is not None else (0, t.num_paths)
+        totals = np.zeros(6, np.uint64)
+        if store:
+            # size by a dry run
+            self.run_batch(t, store=False, path_range=(p0, p1))
+            tot = self._last_totals
+            nv, ni, nm = int(tot[0]), int(tot[1]), int(tot[3])
+            pos = np.empty((max(nv, 1), 2), np.float32)
+            col = np.empty(max(nv, 1), np.uint32)
+            idx = np.empty(max(ni, 1), np.uint16)
+            mvo = np.zeros(nm + 1, np.uint64)
+            mio = np.zeros(nm + 1, np.uint64)
+        else:
+            nv = ni = nm = 0
+            pos = col = idx = mvo = mio = None
+        rc = self._run(C.c_uint32(p0), C.c_uint32(p1),
+                       _p(t.path_cmd_off, C.c_uint32), _p(t.path_data_off, C.c_uint32), _p(t.cmd, C.c_uint8), _p(t.data, C.c_float),
+                       _p(t.path_scale, C.c_float), _p(t.path_tol, C.c_float), _p(t.path_xform, C.c_float), C.c_float(t.fringe),
+                       _p(t.draw_begin, C.c_uint32), _p(t.draw_op, C.c_uint32), _p(t.draw_color, C.c_uint32), _p(t.draw_width, C.c_float),
+                       _p(t.draw_cap, C.c_uint8), _p(t.draw_join, C.c_uint8),
+                       C.c_int(int(store)), _p(pos, C.c_float), _p(col, C.c_uint32), _p(idx, C.c_uint16),
+                       C.c_uint64(nv), C.c_uint64(ni), _p(mvo, C.c_uint64), _p(mio, C.c_uint64), C.c_uint32(nm),
+                       _p(totals, C.c_uint64))
+        if rc != 0:
+            raise RuntimeError(f"run_batch rc={rc}")
+        self._last_totals = totals
+        out = dict(num_vertices=int(totals[0]), num_indices=int(totals[1]), num_points=int(totals[2]),
+                   num_meshes=int(totals[3]), checksum=int(totals[4]), num_subpaths=int(totals[5]))
+        if store:
+            out.update(pos=pos[:nv], color=col[:nv], index=idx[:ni], mesh_vtx_off=mvo, mesh_idx_off=mio)
+        return out
+
+
+class RefLib(_Lib):
+    """The compiled reference (oracle/_ref). kind: scalar (golden) | sse | libm."""
+    prefix = "vgref"
+
+    def __init__(self, kind="scalar"):
+        name = {"scalar": "libvgref.so", "sse": "libvgref_sse.so", "libm": "libvgref_libm.so"}[kind]
+        super().__init__(os.path.join(HERE, "_ref", name))
+
+
+class OracleLib(_Lib):
+    """This repo's plain-C restatement of the algorithm (oracle/vg_oracle.c)."""
+    prefix = "vgo"
+
+    def __init__(self):
+        super().__init__(os.path.join(HERE, "liboracle.so"))
+
+
+def have_ref(kind="scalar"):
+    name = {"scalar": "libvgref.so", "sse": "libvgref_sse.so", "libm": "libvgref_libm.so"}[kind]
+    return os.path.exists(os.path.join(HERE, "_ref", name))
