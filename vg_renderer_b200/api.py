@@ -1,0 +1,389 @@
+"""ctypes binding of libvgb200.so (include/vgb.h).
+
+Classes mirror the reference's interfaces for this path:
+  Batch    -- record / run / read for many paths (the batched entry the GPU needs; recording
+              calls are named after vg::beginPath / moveTo / ... / strokePath / fillPath)
+  Path     -- include/vg/path.h:19-38     (createPath .. pathGetNumSubPaths)
+  Stroker  -- include/vg/stroker.h:11-70  (createStroker .. strokerConvexFillAA)
+The library must be built first (`python -c "import __graft_entry__ as g; g.build()"` or
+`make -C vg_renderer_b200/csrc`); loading fails loudly if it is missing -- there is no fallback.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+CAP_BUTT, CAP_ROUND, CAP_SQUARE = 0, 1, 2
+JOIN_MITER, JOIN_ROUND, JOIN_BEVEL = 0, 1, 2
+WINDING_CCW, WINDING_CW = 0, 1
+OP_STROKE_AA, OP_CONVEX_FILL_AA, OP_STROKE, OP_STROKE_AA_THIN, OP_CONVEX_FILL = range(5)
+INDEX_U16, INDEX_U32 = 0, 1
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def lib_path():
+    return os.path.join(_HERE, "lib", "libvgb200.so")
+
+
+class VgbError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"vgb error {code}: {msg}")
+        self.code = code
+
+
+class Sizes(C.Structure):
+    _fields_ = [("num_vertices", C.c_uint64), ("num_indices", C.c_uint64), ("num_points", C.c_uint64),
+                ("num_subpaths", C.c_uint32), ("num_meshes", C.c_uint32), ("kernel_launches", C.c_uint32),
+                ("reserved", C.c_uint32)]
+
+
+class SubPath(C.Structure):
+    _fields_ = [("first_vertex", C.c_uint32), ("num_vertices", C.c_uint32), ("is_closed", C.c_uint8)]
+
+
+class Mesh(C.Structure):
+    _fields_ = [("pos", C.POINTER(C.c_float)), ("color", C.POINTER(C.c_uint32)), ("index", C.POINTER(C.c_uint16)),
+                ("num_vertices", C.c_uint32), ("num_indices", C.c_uint32)]
+
+
+_lib = None
+
+
+def load_library():
+    """dlopen libvgb200.so once; declares argument types for the entry points used here."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    p = lib_path()
+    if not os.path.exists(p):
+        raise FileNotFoundError(f"{p} not built: run __graft_entry__.build() / make -C vg_renderer_b200/csrc")
+    L = C.CDLL(p)
+    f, u32, u64, vp, i = C.c_float, C.c_uint32, C.c_uint64, C.c_void_p, C.c_int
+    L.vgb_last_error.restype = C.c_char_p
+    L.vgb_version.restype = C.c_char_p
+    L.vgb_batch_create.restype = vp
+    L.vgb_batch_create.argtypes = [i]
+    L.vgb_batch_destroy.argtypes = [vp]
+    L.vgb_batch_reset.argtypes = [vp, f]
+    L.vgb_batch_begin_path.argtypes = [vp, f, f, vp]
+    L.vgb_batch_move_to.argtypes = [vp, f, f]
+    L.vgb_batch_line_to.argtypes = [vp, f, f]
+    L.vgb_batch_cubic_to.argtypes = [vp] + [f] * 6
+    L.vgb_batch_quadratic_to.argtypes = [vp] + [f] * 4
+    L.vgb_batch_arc_to.argtypes = [vp] + [f] * 5
+    L.vgb_batch_rect.argtypes = [vp] + [f] * 4
+    L.vgb_batch_rounded_rect.argtypes = [vp] + [f] * 5
+    L.vgb_batch_rounded_rect_varying.argtypes = [vp] + [f] * 8
+    L.vgb_batch_circle.argtypes = [vp] + [f] * 3
+    L.vgb_batch_ellipse.argtypes = [vp] + [f] * 4
+    L.vgb_batch_arc.argtypes = [vp] + [f] * 5 + [u32]
+    L.vgb_batch_polyline.argtypes = [vp, vp, u32]
+    L.vgb_batch_close.argtypes = [vp]
+    L.vgb_batch_stroke.argtypes = [vp, u32, u32, f, u32, u32]
+    L.vgb_batch_convex_fill.argtypes = [vp, u32, i]
+    L.vgb_batch_add_cubic_strokes.argtypes = [vp, vp, u32, f, f, u32, u32, f, u32, u32]
+    L.vgb_batch_add_rounded_rect_fills.argtypes = [vp, vp, u32, f, f, u32, i]
+    L.vgb_batch_set_polylines.argtypes = [vp, vp, u32, vp, vp, vp, u32, f, f]
+    L.vgb_batch_draw_polyline.argtypes = [vp, u32, u32, u32, f, u32, u32]
+    L.vgb_batch_draw_all.argtypes = [vp, u32, u32, f, u32, u32]
+    L.vgb_batch_upload.argtypes = [vp]
+    L.vgb_batch_run.argtypes = [vp, u32, u64]
+    L.vgb_batch_sync.argtypes = [vp]
+    L.vgb_batch_get_sizes.argtypes = [vp, C.POINTER(Sizes)]
+    L.vgb_batch_device_ptrs.argtypes = [vp] + [C.POINTER(vp)] * 7
+    L.vgb_batch_download.argtypes = [vp, vp, vp, vp, u64, u64, vp, vp]
+    L.vgb_batch_download_paths.argtypes = [vp, vp, u64, vp, u32]
+    L.vgb_batch_execute.argtypes = [vp, u32, vp, vp, vp, u64, u64, vp, vp, C.POINTER(Sizes)]
+    L.vgb_batch_last_run_ms.argtypes = [vp] + [C.POINTER(f)] * 4
+    L.vgb_host_alloc.restype = vp
+    L.vgb_host_alloc.argtypes = [C.c_size_t]
+    L.vgb_host_free.argtypes = [vp]
+    L.vgb_batch_stream.restype = vp
+    L.vgb_batch_stream.argtypes = [vp]
+    # per-object API
+    L.vgb_path_create.restype = vp
+    L.vgb_path_create.argtypes = [vp, vp]
+    L.vgb_path_destroy.argtypes = [vp]
+    L.vgb_path_reset.argtypes = [vp, f, f]
+    L.vgb_path_move_to.argtypes = [vp, f, f]
+    L.vgb_path_line_to.argtypes = [vp, f, f]
+    L.vgb_path_cubic_to.argtypes = [vp] + [f] * 6
+    L.vgb_path_quadratic_to.argtypes = [vp] + [f] * 4
+    L.vgb_path_arc_to.argtypes = [vp] + [f] * 5
+    L.vgb_path_rect.argtypes = [vp] + [f] * 4
+    L.vgb_path_rounded_rect.argtypes = [vp] + [f] * 5
+    L.vgb_path_rounded_rect_varying.argtypes = [vp] + [f] * 8
+    L.vgb_path_circle.argtypes = [vp] + [f] * 3
+    L.vgb_path_ellipse.argtypes = [vp] + [f] * 4
+    L.vgb_path_arc.argtypes = [vp] + [f] * 5 + [u32]
+    L.vgb_path_polyline.argtypes = [vp, vp, u32]
+    L.vgb_path_close.argtypes = [vp]
+    L.vgb_path_get_vertices.restype = C.POINTER(f)
+    L.vgb_path_get_vertices.argtypes = [vp]
+    L.vgb_path_get_num_vertices.restype = u32
+    L.vgb_path_get_num_vertices.argtypes = [vp]
+    L.vgb_path_get_subpaths.restype = C.POINTER(SubPath)
+    L.vgb_path_get_subpaths.argtypes = [vp]
+    L.vgb_path_get_num_subpaths.restype = u32
+    L.vgb_path_get_num_subpaths.argtypes = [vp]
+    L.vgb_stroker_create.restype = vp
+    L.vgb_stroker_create.argtypes = [vp, vp]
+    L.vgb_stroker_destroy.argtypes = [vp]
+    L.vgb_stroker_reset.argtypes = [vp, f, f, f]
+    L.vgb_stroker_polyline_stroke.argtypes = [vp, C.POINTER(Mesh), vp, u32, i, f, u32, u32]
+    L.vgb_stroker_polyline_stroke_aa.argtypes = [vp, C.POINTER(Mesh), vp, u32, i, u32, f, u32, u32]
+    L.vgb_stroker_polyline_stroke_aa_thin.argtypes = [vp, C.POINTER(Mesh), vp, u32, i, u32, u32, u32]
+    L.vgb_stroker_convex_fill.argtypes = [vp, C.POINTER(Mesh), vp, u32]
+    L.vgb_stroker_convex_fill_aa.argtypes = [vp, C.POINTER(Mesh), vp, u32, u32]
+    _lib = L
+    return L
+
+
+def device_count():
+    return load_library().vgb_device_count()
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class Batch:
+    """Batched record -> run -> read. One CUDA stream and one set of device buffers per Batch."""
+
+    def __init__(self, device=0, fringe=1.0):
+        self.L = load_library()
+        self.h = self.L.vgb_batch_create(device)
+        if not self.h:
+            raise VgbError(-4, self.L.vgb_last_error().decode())
+        self.index_u32 = False
+        self._chk(self.L.vgb_batch_reset(self.h, fringe))
+
+    def __del__(self):
+        try:
+            if getattr(self, "h", None):
+                self.L.vgb_batch_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    def _chk(self, rc):
+        if rc != 0:
+            raise VgbError(rc, self.L.vgb_last_error().decode())
+        return self
+
+    # ---- recording (names follow vg::beginPath/moveTo/.../strokePath/fillPath) ----
+    def reset(self, fringe=1.0): return self._chk(self.L.vgb_batch_reset(self.h, fringe))
+
+    def begin_path(self, scale=1.0, tol=0.25, xform=None):
+        m = None if xform is None else (C.c_float * 6)(*[float(v) for v in xform])
+        return self._chk(self.L.vgb_batch_begin_path(self.h, scale, tol, C.cast(m, C.c_void_p) if m is not None else None))
+
+    def move_to(self, x, y): return self._chk(self.L.vgb_batch_move_to(self.h, x, y))
+    def line_to(self, x, y): return self._chk(self.L.vgb_batch_line_to(self.h, x, y))
+    def cubic_to(self, a, b, c, d, x, y): return self._chk(self.L.vgb_batch_cubic_to(self.h, a, b, c, d, x, y))
+    def quadratic_to(self, cx, cy, x, y): return self._chk(self.L.vgb_batch_quadratic_to(self.h, cx, cy, x, y))
+    def arc_to(self, x1, y1, x2, y2, r): return self._chk(self.L.vgb_batch_arc_to(self.h, x1, y1, x2, y2, r))
+    def rect(self, x, y, w, h): return self._chk(self.L.vgb_batch_rect(self.h, x, y, w, h))
+    def rounded_rect(self, x, y, w, h, r): return self._chk(self.L.vgb_batch_rounded_rect(self.h, x, y, w, h, r))
+    def rounded_rect_varying(self, x, y, w, h, a, b, c, d): return self._chk(self.L.vgb_batch_rounded_rect_varying(self.h, x, y, w, h, a, b, c, d))
+    def circle(self, x, y, r): return self._chk(self.L.vgb_batch_circle(self.h, x, y, r))
+    def ellipse(self, x, y, rx, ry): return self._chk(self.L.vgb_batch_ellipse(self.h, x, y, rx, ry))
+    def arc(self, x, y, r, a0, a1, dir_): return self._chk(self.L.vgb_batch_arc(self.h, x, y, r, a0, a1, dir_))
+    def close(self): return self._chk(self.L.vgb_batch_close(self.h))
+
+    def polyline(self, coords):
+        c = np.ascontiguousarray(coords, np.float32).reshape(-1)
+        return self._chk(self.L.vgb_batch_polyline(self.h, _ptr(c), len(c) // 2))
+
+    def stroke(self, op=OP_STROKE_AA, color=0xFF0000FF, width=4.0, cap=CAP_BUTT, join=JOIN_MITER):
+        return self._chk(self.L.vgb_batch_stroke(self.h, op, color, width, cap, join))
+
+    def convex_fill(self, color=0xFF00FF00, aa=True):
+        return self._chk(self.L.vgb_batch_convex_fill(self.h, color, int(aa)))
+
+    def add_cubic_strokes(self, p8, scale=1.0, tol=0.25, op=OP_STROKE_AA, color=0xFF0000FF, width=4.0, cap=CAP_ROUND, join=JOIN_ROUND):
+        p8 = np.ascontiguousarray(p8, np.float32).reshape(-1, 8)
+        return self._chk(self.L.vgb_batch_add_cubic_strokes(self.h, _ptr(p8), len(p8), scale, tol, op, color, width, cap, join))
+
+    def add_rounded_rect_fills(self, xywhr, scale=1.0, tol=0.25, color=0xFF00FF00, aa=True):
+        q = np.ascontiguousarray(xywhr, np.float32).reshape(-1, 5)
+        return self._chk(self.L.vgb_batch_add_rounded_rect_fills(self.h, _ptr(q), len(q), scale, tol, color, int(aa)))
+
+    def set_polylines(self, pts, first, num, closed, scale=1.0, tol=0.25):
+        pts = np.ascontiguousarray(pts, np.float32).reshape(-1, 2)
+        first = np.ascontiguousarray(first, np.uint32)
+        num = np.ascontiguousarray(num, np.uint32)
+        closed = np.ascontiguousarray(closed, np.uint8)
+        return self._chk(self.L.vgb_batch_set_polylines(self.h, _ptr(pts), len(pts), _ptr(first), _ptr(num), _ptr(closed), len(first), scale, tol))
+
+    def draw_polyline(self, sub, op=OP_STROKE_AA, color=0xFF0000FF, width=4.0, cap=CAP_BUTT, join=JOIN_MITER):
+        return self._chk(self.L.vgb_batch_draw_polyline(self.h, sub, op, color, width, cap, join))
+
+    def draw_all(self, op=OP_STROKE_AA, color=0xFF0000FF, width=4.0, cap=CAP_BUTT, join=JOIN_MITER):
+        return self._chk(self.L.vgb_batch_draw_all(self.h, op, color, width, cap, join))
+
+    # ---- execution ----
+    def upload(self): return self._chk(self.L.vgb_batch_upload(self.h))
+
+    def run(self, index_u32=False, vertex_base=0):
+        self.index_u32 = bool(index_u32)
+        return self._chk(self.L.vgb_batch_run(self.h, INDEX_U32 if index_u32 else INDEX_U16, vertex_base))
+
+    def sync(self): return self._chk(self.L.vgb_batch_sync(self.h))
+
+    def sizes(self):
+        s = Sizes()
+        self._chk(self.L.vgb_batch_get_sizes(self.h, C.byref(s)))
+        return s
+
+    def last_run_ms(self):
+        v = [C.c_float() for _ in range(4)]
+        self._chk(self.L.vgb_batch_last_run_ms(self.h, *[C.byref(x) for x in v]))
+        return dict(total=v[0].value, flatten=v[1].value, stroke_count=v[2].value, emit=v[3].value)
+
+    def device_ptrs(self):
+        p = [C.c_void_p() for _ in range(7)]
+        self._chk(self.L.vgb_batch_device_ptrs(self.h, *[C.byref(x) for x in p]))
+        return dict(zip(("pos", "color", "index", "mesh_vtx_off", "mesh_idx_off", "points", "subpaths"), [x.value for x in p]))
+
+    def download(self, want_mesh_table=True):
+        """-> dict(pos[V,2] f32, color[V] u32, index[I] u16|u32, mesh_vtx_off, mesh_idx_off)"""
+        s = self.sizes()
+        nv, ni, nm = int(s.num_vertices), int(s.num_indices), int(s.num_meshes)
+        pos = np.empty((nv, 2), np.float32)
+        col = np.empty(nv, np.uint32)
+        idx = np.empty(ni, np.uint32 if self.index_u32 else np.uint16)
+        mvo = np.zeros(nm + 1, np.uint64) if want_mesh_table else None
+        mio = np.zeros(nm + 1, np.uint64) if want_mesh_table else None
+        self._chk(self.L.vgb_batch_download(self.h, _ptr(pos), _ptr(col), _ptr(idx), nv, ni, _ptr(mvo), _ptr(mio)))
+        return dict(pos=pos, color=col, index=idx, mesh_vtx_off=mvo, mesh_idx_off=mio,
+                    num_vertices=nv, num_indices=ni, num_meshes=nm, num_points=int(s.num_points))
+
+    def download_paths(self):
+        """-> (pts[T,2] f32, [(first, num, closed), ...])"""
+        s = self.sizes()
+        pts = np.empty((int(s.num_points), 2), np.float32)
+        subs = (SubPath * max(1, s.num_subpaths))()
+        self._chk(self.L.vgb_batch_download_paths(self.h, _ptr(pts), len(pts), C.cast(subs, C.c_void_p), s.num_subpaths))
+        return pts, [(subs[i].first_vertex, subs[i].num_vertices, bool(subs[i].is_closed)) for i in range(s.num_subpaths)]
+
+    def execute_into(self, pos, col, idx, index_u32=False):
+        """upload + run + D2H into caller (pinned) numpy buffers; returns Sizes."""
+        self.index_u32 = bool(index_u32)
+        s = Sizes()
+        self._chk(self.L.vgb_batch_execute(self.h, INDEX_U32 if index_u32 else INDEX_U16, _ptr(pos), _ptr(col), _ptr(idx),
+                                           len(pos), len(idx), None, None, C.byref(s)))
+        return s
+
+
+def pinned_empty(shape, dtype):
+    """numpy array backed by cudaHostAlloc'd memory (kept alive by the returned array's base)."""
+    L = load_library()
+    n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+    p = L.vgb_host_alloc(max(n, 16))
+    if not p:
+        raise MemoryError("cudaHostAlloc failed")
+    buf = (C.c_uint8 * max(n, 16)).from_address(p)
+    arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+    return arr, p
+
+
+class Path:
+    """vg::Path (include/vg/path.h:19-38): same call pattern; getters trigger the GPU flatten."""
+
+    def __init__(self):
+        self.L = load_library()
+        self.h = self.L.vgb_path_create(None, None)
+
+    def __del__(self):
+        try:
+            if getattr(self, "h", None):
+                self.L.vgb_path_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    def reset(self, scale=1.0, tol=0.25): self.L.vgb_path_reset(self.h, scale, tol)
+    def move_to(self, x, y): self.L.vgb_path_move_to(self.h, x, y)
+    def line_to(self, x, y): self.L.vgb_path_line_to(self.h, x, y)
+    def cubic_to(self, a, b, c, d, x, y): self.L.vgb_path_cubic_to(self.h, a, b, c, d, x, y)
+    def quadratic_to(self, cx, cy, x, y): self.L.vgb_path_quadratic_to(self.h, cx, cy, x, y)
+    def arc_to(self, x1, y1, x2, y2, r): self.L.vgb_path_arc_to(self.h, x1, y1, x2, y2, r)
+    def rect(self, x, y, w, h): self.L.vgb_path_rect(self.h, x, y, w, h)
+    def rounded_rect(self, x, y, w, h, r): self.L.vgb_path_rounded_rect(self.h, x, y, w, h, r)
+    def rounded_rect_varying(self, x, y, w, h, a, b, c, d): self.L.vgb_path_rounded_rect_varying(self.h, x, y, w, h, a, b, c, d)
+    def circle(self, x, y, r): self.L.vgb_path_circle(self.h, x, y, r)
+    def ellipse(self, x, y, rx, ry): self.L.vgb_path_ellipse(self.h, x, y, rx, ry)
+    def arc(self, x, y, r, a0, a1, dir_): self.L.vgb_path_arc(self.h, x, y, r, a0, a1, dir_)
+    def close(self): self.L.vgb_path_close(self.h)
+
+    def polyline(self, coords):
+        c = np.ascontiguousarray(coords, np.float32).reshape(-1)
+        self.L.vgb_path_polyline(self.h, _ptr(c), len(c) // 2)
+
+    def vertices(self):
+        n = self.L.vgb_path_get_num_vertices(self.h)
+        p = self.L.vgb_path_get_vertices(self.h)
+        return np.ctypeslib.as_array(p, shape=(n, 2)).copy() if n else np.zeros((0, 2), np.float32)
+
+    def subpaths(self):
+        n = self.L.vgb_path_get_num_subpaths(self.h)
+        s = self.L.vgb_path_get_subpaths(self.h)
+        return [(s[i].first_vertex, s[i].num_vertices, bool(s[i].is_closed)) for i in range(n)]
+
+
+class Stroker:
+    """vg::Stroker (include/vg/stroker.h:11-70)."""
+
+    def __init__(self):
+        self.L = load_library()
+        self.h = self.L.vgb_stroker_create(None, None)
+
+    def __del__(self):
+        try:
+            if getattr(self, "h", None):
+                self.L.vgb_stroker_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    def reset(self, scale=1.0, tol=0.25, fringe=1.0): self.L.vgb_stroker_reset(self.h, scale, tol, fringe)
+
+    @staticmethod
+    def _out(m):
+        nv, ni = m.num_vertices, m.num_indices
+        pos = np.ctypeslib.as_array(m.pos, shape=(nv, 2)).copy() if nv else np.zeros((0, 2), np.float32)
+        col = np.ctypeslib.as_array(m.color, shape=(nv,)).copy() if (nv and m.color) else None
+        idx = np.ctypeslib.as_array(m.index, shape=(ni,)).copy() if ni else np.zeros(0, np.uint16)
+        return pos, col, idx
+
+    def polyline_stroke_aa(self, vtx, closed, color, width, cap, join):
+        v = np.ascontiguousarray(vtx, np.float32).reshape(-1, 2)
+        m = Mesh()
+        self.L.vgb_stroker_polyline_stroke_aa(self.h, C.byref(m), _ptr(v), len(v), int(closed), color, width, cap, join)
+        return self._out(m)
+
+    def polyline_stroke(self, vtx, closed, width, cap, join):
+        v = np.ascontiguousarray(vtx, np.float32).reshape(-1, 2)
+        m = Mesh()
+        self.L.vgb_stroker_polyline_stroke(self.h, C.byref(m), _ptr(v), len(v), int(closed), width, cap, join)
+        return self._out(m)
+
+    def polyline_stroke_aa_thin(self, vtx, closed, color, cap, join):
+        v = np.ascontiguousarray(vtx, np.float32).reshape(-1, 2)
+        m = Mesh()
+        self.L.vgb_stroker_polyline_stroke_aa_thin(self.h, C.byref(m), _ptr(v), len(v), int(closed), color, cap, join)
+        return self._out(m)
+
+    def convex_fill_aa(self, vtx, color):
+        v = np.ascontiguousarray(vtx, np.float32).reshape(-1, 2)
+        m = Mesh()
+        self.L.vgb_stroker_convex_fill_aa(self.h, C.byref(m), _ptr(v), len(v), color)
+        return self._out(m)
+
+    def convex_fill(self, vtx):
+        v = np.ascontiguousarray(vtx, np.float32).reshape(-1, 2)
+        m = Mesh()
+        self.L.vgb_stroker_convex_fill(self.h, C.byref(m), _ptr(v), len(v))
+        return self._out(m)

@@ -1,0 +1,923 @@
+/*
+ * vgb_device.cu -- the sm_100a device pipeline of libvgb200.
+ *
+ * Kernels (all HBM-streaming fp32/integer work: no tensor cores -- there is no dense
+ * contraction anywhere on this path):
+ *
+ *   k_flatten<false>   thread per sub-path: walk commands, count polyline points
+ *   scan (u32)         sub-path point counts -> first-vertex offsets
+ *   k_flatten<true>    same walk, store (transformed) points at the scanned offsets
+ *   k_draw_prep        per-draw constants (hsw, da, nHC ...) with the shared fp32 math
+ *   k_job_pieces       pieces per job (mesh)            -> scan -> pieceStart
+ *   k_block_first_job  first job overlapping each 128-piece block
+ *   k_piece_count      thread per piece: classify() -> per-block (V,I) totals + per-mesh totals
+ *   scan (u32x2->u64x2) block totals -> block bases; mesh totals -> mesh table
+ *   k_piece_emit       the hot kernel: thread per piece emits its vertices/colours/indices into
+ *                      a shared-memory image of the block's (contiguous) output range, then the
+ *                      whole block streams that image to HBM with 128-bit coalesced stores.
+ *
+ * Build: nvcc -gencode arch=compute_100a,code=sm_100a -fmad=false (see Makefile).  -fmad=false
+ * plus vgb_math.h's __f*_rn intrinsics make every float result identical to the non-FMA CPU
+ * oracle, which is what keeps vertex COUNTS (hence index buffers) bit-exact.
+ */
+#include "vgb_flatten.cuh"
+#include "vgb_stroke.cuh"
+#include "vgb_internal.h"
+
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+
+namespace vgb
+{
+#define VGB_CUDA(call)                                                                        \
+	do {                                                                                      \
+		cudaError_t e_ = (call);                                                              \
+		if (e_ != cudaSuccess) {                                                              \
+			if (err) *err = std::string(#call) + ": " + cudaGetErrorString(e_);               \
+			return VGB_ERR_CUDA;                                                              \
+		}                                                                                     \
+	} while (0)
+
+static constexpr uint32_t PPB = 128;          /* pieces per block == threads per block        */
+static constexpr uint32_t CV = 2048;          /* staged vertices per round                    */
+static constexpr uint32_t CI_BYTES = 18432;   /* staged index bytes per round                 */
+
+/* =========================================================================================
+ * scans
+ * ======================================================================================= */
+template<class T> struct ScanOps;
+template<> struct ScanOps<uint32_t>
+{
+	typedef uint32_t In;
+	typedef uint32_t Acc;
+	__device__ static Acc zero() { return 0u; }
+	__device__ static Acc cvt(In a) { return a; }
+	__device__ static Acc add(Acc a, Acc b) { return a + b; }
+	__device__ static Acc shflUp(Acc a, int d) { return __shfl_up_sync(0xffffffffu, a, d); }
+};
+template<> struct ScanOps<uint2>
+{
+	typedef uint2 In;
+	typedef ulonglong2 Acc;
+	__device__ static Acc zero() { return make_ulonglong2(0ull, 0ull); }
+	__device__ static Acc cvt(In a) { return make_ulonglong2(a.x, a.y); }
+	__device__ static Acc add(Acc a, Acc b) { return make_ulonglong2(a.x + b.x, a.y + b.y); }
+	__device__ static Acc shflUp(Acc a, int d)
+	{
+		return make_ulonglong2(__shfl_up_sync(0xffffffffu, a.x, d), __shfl_up_sync(0xffffffffu, a.y, d));
+	}
+};
+
+static constexpr uint32_t SCAN_THREADS = 256;
+static constexpr uint32_t SCAN_ITEMS = 4;
+static constexpr uint32_t SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
+
+/* inclusive block scan of one value per thread; returns inclusive value, *total = block sum */
+template<class O>
+__device__ __forceinline__ typename O::Acc blockInclusive(typename O::Acc v, typename O::Acc* total)
+{
+	typedef typename O::Acc Acc;
+	__shared__ Acc warpSum[32];
+	const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+#pragma unroll
+	for (int d = 1; d < 32; d <<= 1) {
+		const Acc u = O::shflUp(v, d);
+		if (lane >= (uint32_t)d) v = O::add(v, u);
+	}
+	if (lane == 31) warpSum[warp] = v;
+	__syncthreads();
+	if (warp == 0) {
+		Acc w = lane < nw ? warpSum[lane] : O::zero();
+#pragma unroll
+		for (int d = 1; d < 32; d <<= 1) {
+			const Acc u = O::shflUp(w, d);
+			if (lane >= (uint32_t)d) w = O::add(w, u);
+		}
+		warpSum[lane] = w;
+	}
+	__syncthreads();
+	if (warp > 0) v = O::add(v, warpSum[warp - 1]);
+	*total = warpSum[nw - 1];
+	__syncthreads();
+	return v;
+}
+
+template<class O>
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_reduce(const typename O::In* __restrict__ in, uint32_t n, typename O::Acc* __restrict__ partial)
+{
+	typedef typename O::Acc Acc;
+	const uint32_t base = blockIdx.x * SCAN_TILE;
+	Acc s = O::zero();
+#pragma unroll
+	for (uint32_t k = 0; k < SCAN_ITEMS; ++k) {
+		const uint32_t i = base + k * SCAN_THREADS + threadIdx.x;
+		if (i < n) s = O::add(s, O::cvt(in[i]));
+	}
+	Acc total;
+	blockInclusive<O>(s, &total);
+	if (threadIdx.x == 0) partial[blockIdx.x] = total;
+}
+
+__device__ __forceinline__ uint32_t accSub(uint32_t a, uint32_t b) { return a - b; }
+__device__ __forceinline__ ulonglong2 accSub(ulonglong2 a, ulonglong2 b) { return make_ulonglong2(a.x - b.x, a.y - b.y); }
+
+/* one block: exclusive scan of the partials in place */
+template<class O>
+__global__ void __launch_bounds__(1024) k_scan_partials(typename O::Acc* __restrict__ partial, uint32_t m)
+{
+	typedef typename O::Acc Acc;
+	__shared__ Acc carry;
+	if (threadIdx.x == 0) carry = O::zero();
+	__syncthreads();
+	for (uint32_t base = 0; base < m; base += blockDim.x) {
+		const uint32_t i = base + threadIdx.x;
+		const Acc v = i < m ? partial[i] : O::zero();
+		Acc total;
+		const Acc inc = blockInclusive<O>(v, &total);
+		const Acc c = carry;
+		if (i < m) partial[i] = accSub(O::add(c, inc), v);
+		__syncthreads();
+		if (threadIdx.x == 0) carry = O::add(c, total);
+		__syncthreads();
+	}
+}
+
+/* out[i] = exclusive prefix, out[n] = total */
+template<class O>
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_final(const typename O::In* __restrict__ in, uint32_t n,
+                                                            const typename O::Acc* __restrict__ partial, typename O::Acc* __restrict__ out)
+{
+	typedef typename O::Acc Acc;
+	const uint32_t base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
+	Acc v[SCAN_ITEMS];
+	Acc s = O::zero();
+#pragma unroll
+	for (uint32_t k = 0; k < SCAN_ITEMS; ++k) {
+		v[k] = (base + k < n) ? O::cvt(in[base + k]) : O::zero();
+		s = O::add(s, v[k]);
+	}
+	Acc total;
+	const Acc inc = blockInclusive<O>(s, &total);
+	Acc run = O::add(partial[blockIdx.x], accSub(inc, s));
+#pragma unroll
+	for (uint32_t k = 0; k < SCAN_ITEMS; ++k) {
+		if (base + k < n) out[base + k] = run;
+		run = O::add(run, v[k]);
+		if (base + k + 1 == n) out[n] = run;
+	}
+	if (n == 0 && blockIdx.x == 0 && threadIdx.x == 0) out[0] = O::zero();
+}
+
+/* =========================================================================================
+ * flatten
+ * ======================================================================================= */
+struct FlattenArgs
+{
+	const SubRec* subRec;
+	uint32_t numSub;
+	const uint8_t* cmd;
+	const float* data;
+	const float* pathScale;
+	const float* pathTol;
+	const float* pathXform;
+	uint32_t* subNum;         /* count pass output                  */
+	const uint32_t* subFirst; /* emit pass input (scanned)          */
+	uint8_t* subClosed;       /* emit pass output                   */
+	float2* pts;              /* emit pass output                   */
+};
+
+template<bool EMIT>
+__global__ void __launch_bounds__(128) k_flatten(FlattenArgs a)
+{
+	const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+	if (s >= a.numSub) return;
+	const SubRec r = a.subRec[s];
+	SubPathWalker<EMIT> w;
+	w.lx = w.ly = w.px = w.py = w.fx = w.fy = 0.0f;
+	w.n = 0;
+	w.closed = false;
+	w.scale = a.pathScale[r.pathId];
+	w.tol = a.pathTol[r.pathId];
+	w.m = (EMIT && a.pathXform) ? a.pathXform + 6 * (size_t)r.pathId : nullptr;
+	w.out = EMIT ? a.pts + a.subFirst[s] : nullptr;
+	w.limit = EMIT ? a.subNum[s] : 0u;
+	w.run(a.cmd, r.cmdBegin, r.cmdEnd, a.data + r.dataBegin);
+	if (EMIT) {
+		a.subClosed[s] = w.closed ? 1 : 0;
+	} else {
+		a.subNum[s] = w.n;
+	}
+}
+
+/* =========================================================================================
+ * draws / jobs / pieces
+ * ======================================================================================= */
+__global__ void k_draw_prep(const DrawRec* __restrict__ draws, uint32_t n, const float* __restrict__ pathScale,
+                            const float* __restrict__ pathTol, float fringe, DrawDerived* __restrict__ out)
+{
+	const uint32_t d = blockIdx.x * blockDim.x + threadIdx.x;
+	if (d >= n) return;
+	const DrawRec r = draws[d];
+	const float scale = pathScale[r.pathId];
+	const float tol = pathTol[r.pathId];
+	const uint32_t op = r.ocj & 0xFF;
+	DrawDerived o;
+	o.fringe = fringe;
+	o.color = r.color;
+	o.c0 = r.color & 0x00FFFFFFu; /* colorSetAlpha(color, 0), vg.inl:92-95 */
+	o.ocj = r.ocj;
+	o.hsw = o.hsw_aa = o.da = 0.0f;
+	o.nHC = 2;
+	if (op == VGB_OP_STROKE_AA) {
+		/* stroker.cpp:1396-1399 */
+		o.hsw = (r.width - fringe) * 0.5f;
+		o.hsw_aa = o.hsw + fringe;
+		o.da = vgb_acos((scale * o.hsw) / ((scale * o.hsw) + tol)) * 2.0f;
+		o.nHC = vgb_umax(2u, (uint32_t)vgb_ceil(VGB_PI / o.da));
+	}
+	out[d] = o;
+}
+
+__global__ void k_job_pieces(const uint32_t* __restrict__ jobSub, const uint32_t* __restrict__ jobDraw, uint32_t numJobs,
+                             const uint32_t* __restrict__ subNum, const DrawRec* __restrict__ draws, uint32_t* __restrict__ jobPieces)
+{
+	const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+	if (j >= numJobs) return;
+	jobPieces[j] = pieceCount(draws[jobDraw[j]].ocj & 0xFF, subNum[jobSub[j]]);
+}
+
+__global__ void k_block_first_job(const uint32_t* __restrict__ pieceStart, uint32_t numJobs, uint32_t* __restrict__ blockFirstJob)
+{
+	const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+	if (j >= numJobs) return;
+	const uint32_t s = pieceStart[j], e = pieceStart[j + 1];
+	if (e == s) return;
+	for (uint32_t b = (s + PPB - 1) / PPB; b * PPB < e; ++b) {
+		blockFirstJob[b] = j;
+	}
+}
+
+struct PieceArgs
+{
+	uint32_t numPieces, numJobs;
+	const uint32_t* pieceStart;    /* numJobs + 1 */
+	const uint32_t* blockFirstJob; /* per block   */
+	const uint32_t* jobSub;
+	const uint32_t* jobDraw;
+	const uint32_t* subFirst;
+	const uint32_t* subNum;
+	const uint8_t* subClosed;
+	const DrawDerived* dd;
+	const float2* pts;
+	/* count outputs */
+	uint2* blockTotals;
+	uint2* meshTotals; /* zeroed before the count kernel */
+	/* emit inputs */
+	const ulonglong2* blockBase; /* numBlocks + 1 */
+	const ulonglong2* meshOff;   /* numJobs + 1   */
+	uint64_t vertexBase;
+	/* emit outputs */
+	float2* pos;
+	uint32_t* col;
+	void* idx;
+};
+
+/* job of global piece g: window of pieceStart staged in shared memory, global search fallback */
+__device__ __forceinline__ uint32_t findJob(const PieceArgs& a, const uint32_t* sStart, uint32_t j0, uint32_t win, uint32_t g)
+{
+	/* largest w in [0, win) with sStart[w] <= g  (sStart[0] <= g by construction) */
+	if (sStart[win] > g) {
+		uint32_t lo = 0, hi = win; /* invariant: sStart[lo] <= g < sStart[hi] */
+		while (hi - lo > 1) {
+			const uint32_t mid = (lo + hi) >> 1;
+			if (sStart[mid] <= g) lo = mid; else hi = mid;
+		}
+		return j0 + lo;
+	}
+	/* window exhausted (many empty jobs in a row): search the global table */
+	uint32_t lo = j0 + win, hi = a.numJobs; /* pieceStart[lo] <= g < pieceStart[hi] */
+	while (hi - lo > 1) {
+		const uint32_t mid = (lo + hi) >> 1;
+		if (a.pieceStart[mid] <= g) lo = mid; else hi = mid;
+	}
+	return lo;
+}
+
+__device__ __forceinline__ JobCtx loadJob(const PieceArgs& a, uint32_t j)
+{
+	const uint32_t s = a.jobSub[j];
+	const DrawDerived d = a.dd[a.jobDraw[j]];
+	JobCtx J;
+	J.first = a.subFirst[s];
+	J.N = a.subNum[s];
+	J.closed = a.subClosed[s];
+	J.op = d.ocj & 0xFF;
+	J.cap = (d.ocj >> 8) & 0xFF;
+	J.join = (d.ocj >> 16) & 0xFF;
+	J.hsw = d.hsw;
+	J.hsw_aa = d.hsw_aa;
+	J.da = d.da;
+	J.fringe = d.fringe;
+	J.nHC = d.nHC;
+	J.color = d.color;
+	J.c0 = d.c0;
+	/* closed paths ignore the cap (dispatch forces Butt, stroker.cpp:285-303) */
+	return J;
+}
+
+/* shared prologue of count and emit: which job / local piece does this thread own */
+struct Owner
+{
+	uint32_t j, q;
+	bool valid;
+};
+
+__device__ __forceinline__ Owner findOwner(const PieceArgs& a, uint32_t* sStart)
+{
+	const uint32_t g0 = blockIdx.x * PPB;
+	const uint32_t g = g0 + threadIdx.x;
+	const uint32_t j0 = a.blockFirstJob[blockIdx.x];
+	const uint32_t win = min(PPB + 1, a.numJobs - j0); /* entries j0 .. j0+win (inclusive) exist */
+	for (uint32_t w = threadIdx.x; w <= win; w += blockDim.x) {
+		sStart[w] = a.pieceStart[j0 + w];
+	}
+	__syncthreads();
+	Owner o;
+	o.valid = g < a.numPieces;
+	o.j = 0;
+	o.q = 0;
+	if (o.valid) {
+		o.j = findJob(a, sStart, j0, win, g);
+		o.q = g - a.pieceStart[o.j];
+	}
+	return o;
+}
+
+__global__ void __launch_bounds__(PPB) k_piece_count(PieceArgs a)
+{
+	__shared__ uint32_t sStart[PPB + 2];
+	const Owner o = findOwner(a, sStart);
+	uint32_t vc = 0, ic = 0;
+	if (o.valid) {
+		const JobCtx J = loadJob(a, o.j);
+		const Piece P = classify(J, o.q, a.pts);
+		vc = P.vcount;
+		ic = P.icount;
+	}
+	/* per-mesh totals: lanes of one warp owning the same job reduce first, one atomic per run */
+	{
+		const uint32_t key = o.valid ? o.j : 0xFFFFFFFFu;
+		const uint32_t m = __match_any_sync(0xffffffffu, key);
+		const uint32_t sv = __reduce_add_sync(m, vc);
+		const uint32_t si = __reduce_add_sync(m, ic);
+		if (o.valid && (threadIdx.x & 31) == (uint32_t)(__ffs(m) - 1)) {
+			atomicAdd(&a.meshTotals[o.j].x, sv);
+			atomicAdd(&a.meshTotals[o.j].y, si);
+		}
+	}
+	ulonglong2 total;
+	blockInclusive<ScanOps<uint2>>(make_ulonglong2(vc, ic), &total);
+	if (threadIdx.x == 0) {
+		a.blockTotals[blockIdx.x] = make_uint2((uint32_t)total.x, (uint32_t)total.y);
+	}
+}
+
+/* stream `count` elements of shared memory (image laid out so that element e sits at
+ * sbuf[e - alignedBase]) to global memory starting at element gs: 16-byte stores for the
+ * aligned body, element stores for the ragged head/tail. */
+template<class T>
+__device__ __forceinline__ void copyOut(T* __restrict__ gbase, uint64_t gs, uint32_t count, const T* sbuf)
+{
+	constexpr uint32_t K = 16 / sizeof(T);
+	const uint64_t ge = gs + count;
+	const uint64_t alignedBase = gs & ~(uint64_t)(K - 1);
+	const uint64_t bodyBegin = (gs + K - 1) & ~(uint64_t)(K - 1);
+	const uint64_t bodyEnd = ge & ~(uint64_t)(K - 1);
+	if (bodyEnd > bodyBegin) {
+		const uint32_t chunks = (uint32_t)((bodyEnd - bodyBegin) / K);
+		const uint4* s4 = reinterpret_cast<const uint4*>(sbuf + (bodyBegin - alignedBase));
+		uint4* g4 = reinterpret_cast<uint4*>(gbase + bodyBegin);
+		for (uint32_t c = threadIdx.x; c < chunks; c += blockDim.x) {
+			__stcs(g4 + c, s4[c]);
+		}
+		/* head and tail (fewer than K elements each) */
+		const uint32_t head = (uint32_t)(bodyBegin - gs);
+		const uint32_t tail = (uint32_t)(ge - bodyEnd);
+		if (threadIdx.x < head) {
+			gbase[gs + threadIdx.x] = sbuf[(gs - alignedBase) + threadIdx.x];
+		} else if (threadIdx.x >= 32 && threadIdx.x - 32 < tail) {
+			gbase[bodyEnd + (threadIdx.x - 32)] = sbuf[(bodyEnd - alignedBase) + (threadIdx.x - 32)];
+		}
+	} else {
+		for (uint32_t e = threadIdx.x; e < count; e += blockDim.x) {
+			gbase[gs + e] = sbuf[(gs - alignedBase) + e];
+		}
+	}
+}
+
+template<class IDX>
+__device__ __forceinline__ void emitPiece(const PieceArgs& a, const JobCtx& J, const Piece& P, uint32_t F, uint4 prev, const Sink<IDX>& S)
+{
+	switch (P.kind) {
+	case PK_CAP_START: emitCapStartAA(J, P, F, S); break;
+	case PK_CAP_END: emitCapEndAA(J, P, F, prev, S); break;
+	case PK_JOIN: {
+		const bool firstLeft = (P.flags & PF_CLOSING) ? firstJoinLeft(J, a.pts) : false;
+		emitJoinAA(J, P, F, prev, firstLeft, S);
+	} break;
+	case PK_FILL_FAN: emitFillFan(P, S); break;
+	case PK_FILL_VTX: emitFillVtx(J, P, a.pts, S); break;
+	default: break;
+	}
+}
+
+template<class IDX>
+__global__ void __launch_bounds__(PPB) k_piece_emit(PieceArgs a)
+{
+	constexpr uint32_t CI = CI_BYTES / sizeof(IDX);
+	constexpr uint32_t KI = 16 / sizeof(IDX);
+	__shared__ uint32_t sStart[PPB + 2];
+	__shared__ uint32_t sVl[PPB + 1];
+	__shared__ uint32_t sIl[PPB + 1];
+	__shared__ uint4 sOut4[PPB];
+	__shared__ __align__(16) float2 sPos[CV + 2];
+	__shared__ __align__(16) uint32_t sCol[CV + 4];
+	__shared__ __align__(16) IDX sIdx[CI + KI];
+
+	const uint32_t t = threadIdx.x;
+	const Owner o = findOwner(a, sStart);
+	JobCtx J;
+	Piece P;
+	P.kind = PK_NONE;
+	P.vcount = P.icount = 0;
+	if (o.valid) {
+		J = loadJob(a, o.j);
+		P = classify(J, o.q, a.pts);
+	}
+	/* local offsets */
+	ulonglong2 total;
+	const ulonglong2 inc = blockInclusive<ScanOps<uint2>>(make_ulonglong2(P.vcount, P.icount), &total);
+	const uint32_t vl = (uint32_t)inc.x - P.vcount;
+	const uint32_t il = (uint32_t)inc.y - P.icount;
+	sVl[t] = vl;
+	sIl[t] = il;
+	if (t == 0) {
+		sVl[PPB] = (uint32_t)total.x;
+		sIl[PPB] = (uint32_t)total.y;
+	}
+	const ulonglong2 bb = a.blockBase[blockIdx.x];
+	/* mesh-local id of this piece's first vertex, and what it hands to the next piece */
+	uint32_t F = 0;
+	ulonglong2 mo = make_ulonglong2(0, 0);
+	if (o.valid) {
+		mo = a.meshOff[o.j];
+		F = (uint32_t)(bb.x + vl - mo.x);
+		sOut4[t] = pieceOut4(J, P, F);
+	}
+	__syncthreads();
+	uint4 prev = make_uint4(0, 0, 0, 0);
+	if (o.valid && (P.flags & PF_HAS_PREV)) {
+		if (t > 0) {
+			prev = sOut4[t - 1]; /* piece q-1 of the same job is owned by thread t-1 */
+		} else {
+			/* halo: the previous piece belongs to the previous block; recompute it */
+			const Piece H = classify(J, o.q - 1, a.pts);
+			prev = pieceOut4(J, H, F - H.vcount);
+		}
+	}
+	const uint32_t idxBase = sizeof(IDX) == 2 ? 0u : (uint32_t)(mo.x + a.vertexBase);
+
+	/* rounds: as many consecutive pieces as fit the staging buffers */
+	const uint32_t nThreads = min(PPB, a.numPieces - blockIdx.x * PPB);
+	uint32_t ta = 0;
+	while (ta < nThreads) {
+		const uint32_t v0 = sVl[ta], i0 = sIl[ta];
+		const bool fits = t >= ta && t < nThreads && (sVl[t + 1] - v0) <= CV && (sIl[t + 1] - i0) <= CI;
+		const uint32_t cnt = __syncthreads_count(fits);
+		const uint64_t gv = bb.x + v0; /* global element offsets of the round */
+		const uint64_t gi = bb.y + i0;
+		if (cnt == 0) {
+			/* a single piece larger than the staging buffers: its owner writes it straight to HBM */
+			if (t == ta) {
+				Sink<IDX> S;
+				S.pos = a.pos + gv;
+				S.col = a.col + gv;
+				S.idx = reinterpret_cast<IDX*>(a.idx) + gi;
+				S.base = idxBase;
+				emitPiece(a, J, P, F, prev, S);
+			}
+			ta += 1;
+			__syncthreads();
+			continue;
+		}
+		const uint32_t tb = ta + cnt;
+		const uint32_t shV2 = (uint32_t)(gv & 1), shV4 = (uint32_t)(gv & 3), shI = (uint32_t)(gi & (KI - 1));
+		if (t >= ta && t < tb) {
+			Sink<IDX> S;
+			S.pos = sPos + shV2 + (vl - v0);
+			S.col = sCol + shV4 + (vl - v0);
+			S.idx = sIdx + shI + (il - i0);
+			S.base = idxBase;
+			emitPiece(a, J, P, F, prev, S);
+		}
+		__syncthreads();
+		const uint32_t nv = sVl[tb] - v0, ni = sIl[tb] - i0;
+		copyOut<float2>(a.pos, gv, nv, sPos);
+		copyOut<uint32_t>(a.col, gv, nv, sCol);
+		copyOut<IDX>(reinterpret_cast<IDX*>(a.idx), gi, ni, sIdx);
+		__syncthreads();
+		ta = tb;
+	}
+}
+
+/* =========================================================================================
+ * host side
+ * ======================================================================================= */
+struct DevBuf
+{
+	void* p = nullptr;
+	size_t cap = 0;
+	int ensure(size_t bytes, std::string* err)
+	{
+		if (bytes <= cap) return 0;
+		if (p) cudaFree(p);
+		p = nullptr;
+		cap = 0;
+		const size_t want = bytes + bytes / 8 + 256;
+		VGB_CUDA(cudaMalloc(&p, want));
+		cap = want;
+		return 0;
+	}
+	void release()
+	{
+		if (p) cudaFree(p);
+		p = nullptr;
+		cap = 0;
+	}
+	template<class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+class PipelineImpl : public Pipeline
+{
+public:
+	int dev = 0;
+	cudaStream_t st = nullptr;
+	cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+	/* inputs */
+	DevBuf dSubRec, dCmd, dData, dScale, dTol, dXform, dDraws, dJobSub, dJobDraw;
+	/* intermediates */
+	DevBuf dSubNum, dSubFirst, dSubClosed, dPts, dDD, dJobPieces, dPieceStart, dBlockFirstJob;
+	DevBuf dBlockTotals, dBlockBase, dMeshTotals, dMeshOff, dScanTmp;
+	/* outputs */
+	DevBuf dPos, dCol, dIdx;
+	void* hPinned = nullptr; /* small pinned readback area */
+	HostTables ht;
+	bool hasXform = false, rawMode = false, uploaded = false, ran = false;
+	uint32_t numSub = 0, numJobs = 0, numDraws = 0, numPaths = 0;
+	uint32_t idxBytes = 2;
+	vgb_sizes sz;
+	RunTimes rt;
+	uint32_t launches = 0;
+
+	~PipelineImpl() override
+	{
+		cudaSetDevice(dev);
+		DevBuf* all[] = {&dSubRec, &dCmd, &dData, &dScale, &dTol, &dXform, &dDraws, &dJobSub, &dJobDraw, &dSubNum, &dSubFirst,
+		                 &dSubClosed, &dPts, &dDD, &dJobPieces, &dPieceStart, &dBlockFirstJob, &dBlockTotals, &dBlockBase,
+		                 &dMeshTotals, &dMeshOff, &dScanTmp, &dPos, &dCol, &dIdx};
+		for (DevBuf* b : all) b->release();
+		for (auto& e : ev) if (e) cudaEventDestroy(e);
+		if (hPinned) cudaFreeHost(hPinned);
+		if (st) cudaStreamDestroy(st);
+	}
+
+	int init(int device, std::string* err)
+	{
+		int n = 0;
+		if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
+			if (err) *err = "no CUDA device visible: libvgb200 has no CPU fallback";
+			return VGB_ERR_NOGPU;
+		}
+		if (device < 0 || device >= n) {
+			if (err) *err = "device ordinal out of range";
+			return VGB_ERR_INVALID;
+		}
+		dev = device;
+		VGB_CUDA(cudaSetDevice(dev));
+		VGB_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+		for (auto& e : ev) VGB_CUDA(cudaEventCreate(&e));
+		VGB_CUDA(cudaHostAlloc(&hPinned, 256, cudaHostAllocDefault));
+		memset(&sz, 0, sizeof(sz));
+		return 0;
+	}
+
+	template<class T>
+	int up(DevBuf& b, const T* src, size_t n, std::string* err)
+	{
+		if (b.ensure(n * sizeof(T) + 16, err)) return VGB_ERR_CUDA;
+		if (n) VGB_CUDA(cudaMemcpyAsync(b.p, src, n * sizeof(T), cudaMemcpyHostToDevice, st));
+		return 0;
+	}
+
+	int upload(const HostTables& t, std::string* err) override
+	{
+		VGB_CUDA(cudaSetDevice(dev));
+		ht = t;
+		rawMode = t.rawPts != nullptr;
+		numSub = t.numSub;
+		numJobs = t.numJobs;
+		numDraws = t.numDraws;
+		numPaths = t.numPaths;
+		hasXform = t.pathXform != nullptr;
+		int rc = 0;
+		rc |= up(dScale, t.pathScale, t.numPaths, err);
+		rc |= up(dTol, t.pathTol, t.numPaths, err);
+		if (rawMode) {
+			rc |= up(dPts, t.rawPts, 2 * (size_t)t.numRawPts, err);
+			rc |= up(dSubNum, t.rawNum, t.numSub, err);
+			rc |= up(dSubFirst, t.rawFirst, t.numSub, err);
+			rc |= up(dSubClosed, t.rawClosed, t.numSub, err);
+		} else {
+			rc |= up(dSubRec, t.subRec, t.numSub, err);
+			rc |= up(dCmd, t.cmd, t.numCmd, err);
+			rc |= up(dData, t.data, t.numData, err);
+			if (hasXform) rc |= up(dXform, t.pathXform, 6 * (size_t)t.numPaths, err);
+		}
+		rc |= up(dDraws, t.draws, t.numDraws, err);
+		rc |= up(dJobSub, t.jobSub, t.numJobs, err);
+		rc |= up(dJobDraw, t.jobDraw, t.numJobs, err);
+		if (rc) return VGB_ERR_CUDA;
+		uploaded = true;
+		ran = false;
+		return 0;
+	}
+
+	template<class O>
+	int scan(const typename O::In* in, uint32_t n, typename O::Acc* out, std::string* err)
+	{
+		typedef typename O::Acc Acc;
+		const uint32_t blocks = (n + SCAN_TILE - 1) / SCAN_TILE;
+		if (dScanTmp.ensure((size_t)(blocks + 1) * sizeof(Acc), err)) return VGB_ERR_CUDA;
+		Acc* partial = dScanTmp.as<Acc>();
+		if (blocks == 0) {
+			VGB_CUDA(cudaMemsetAsync(out, 0, sizeof(Acc), st));
+			return 0;
+		}
+		k_scan_reduce<O><<<blocks, SCAN_THREADS, 0, st>>>(in, n, partial);
+		k_scan_partials<O><<<1, 1024, 0, st>>>(partial, blocks);
+		k_scan_final<O><<<blocks, SCAN_THREADS, 0, st>>>(in, n, partial, out);
+		launches += 3;
+		VGB_CUDA(cudaGetLastError());
+		return 0;
+	}
+
+	/* read back a few bytes (synchronises the stream) */
+	int readback(void* dst, const void* src, size_t bytes, std::string* err)
+	{
+		VGB_CUDA(cudaMemcpyAsync(hPinned, src, bytes, cudaMemcpyDeviceToHost, st));
+		VGB_CUDA(cudaStreamSynchronize(st));
+		memcpy(dst, hPinned, bytes);
+		return 0;
+	}
+
+	int run(uint32_t flags, uint64_t vertexBase, std::string* err) override
+	{
+		if (!uploaded) {
+			if (err) *err = "run before upload";
+			return VGB_ERR_STATE;
+		}
+		VGB_CUDA(cudaSetDevice(dev));
+		launches = 0;
+		idxBytes = (flags & VGB_RUN_INDEX_U32) ? 4 : 2;
+		memset(&sz, 0, sizeof(sz));
+		sz.num_subpaths = numSub;
+		sz.num_meshes = numJobs;
+		VGB_CUDA(cudaEventRecord(ev[0], st));
+
+		/* ---- flatten ---- */
+		uint32_t numPts = 0;
+		if (rawMode) {
+			numPts = ht.numRawPts;
+		} else if (numSub) {
+			if (dSubNum.ensure((size_t)numSub * 4, err) || dSubFirst.ensure((size_t)(numSub + 1) * 4, err) || dSubClosed.ensure(numSub, err))
+				return VGB_ERR_CUDA;
+			FlattenArgs fa;
+			fa.subRec = dSubRec.as<SubRec>();
+			fa.numSub = numSub;
+			fa.cmd = dCmd.as<uint8_t>();
+			fa.data = dData.as<float>();
+			fa.pathScale = dScale.as<float>();
+			fa.pathTol = dTol.as<float>();
+			fa.pathXform = hasXform ? dXform.as<float>() : nullptr;
+			fa.subNum = dSubNum.as<uint32_t>();
+			fa.subFirst = dSubFirst.as<uint32_t>();
+			fa.subClosed = dSubClosed.as<uint8_t>();
+			fa.pts = nullptr;
+			const uint32_t fb = (numSub + 127) / 128;
+			k_flatten<false><<<fb, 128, 0, st>>>(fa);
+			++launches;
+			if (scan<ScanOps<uint32_t>>(dSubNum.as<uint32_t>(), numSub, dSubFirst.as<uint32_t>(), err)) return VGB_ERR_CUDA;
+			if (readback(&numPts, dSubFirst.as<uint32_t>() + numSub, 4, err)) return VGB_ERR_CUDA;
+			if (dPts.ensure((size_t)numPts * 8 + 16, err)) return VGB_ERR_CUDA;
+			fa.pts = dPts.as<float2>();
+			k_flatten<true><<<fb, 128, 0, st>>>(fa);
+			++launches;
+			VGB_CUDA(cudaGetLastError());
+		}
+		sz.num_points = numPts;
+		VGB_CUDA(cudaEventRecord(ev[1], st));
+
+		/* ---- draws, jobs, pieces ---- */
+		uint32_t numPieces = 0;
+		if (numJobs) {
+			if (dDD.ensure((size_t)numDraws * sizeof(DrawDerived), err) || dJobPieces.ensure((size_t)numJobs * 4, err) ||
+			    dPieceStart.ensure((size_t)(numJobs + 1) * 4, err))
+				return VGB_ERR_CUDA;
+			k_draw_prep<<<(numDraws + 127) / 128, 128, 0, st>>>(dDraws.as<DrawRec>(), numDraws, dScale.as<float>(), dTol.as<float>(), ht.fringe,
+			                                                     dDD.as<DrawDerived>());
+			k_job_pieces<<<(numJobs + 255) / 256, 256, 0, st>>>(dJobSub.as<uint32_t>(), dJobDraw.as<uint32_t>(), numJobs, dSubNum.as<uint32_t>(),
+			                                                     dDraws.as<DrawRec>(), dJobPieces.as<uint32_t>());
+			launches += 2;
+			if (scan<ScanOps<uint32_t>>(dJobPieces.as<uint32_t>(), numJobs, dPieceStart.as<uint32_t>(), err)) return VGB_ERR_CUDA;
+			if (readback(&numPieces, dPieceStart.as<uint32_t>() + numJobs, 4, err)) return VGB_ERR_CUDA;
+		}
+		const uint32_t numBlocks = (numPieces + PPB - 1) / PPB;
+		uint64_t totals[2] = {0, 0};
+		if (dMeshOff.ensure((size_t)(numJobs + 1) * 16, err)) return VGB_ERR_CUDA;
+		PieceArgs pa;
+		memset(&pa, 0, sizeof(pa));
+		if (numPieces) {
+			if (dBlockFirstJob.ensure((size_t)numBlocks * 4, err) || dBlockTotals.ensure((size_t)numBlocks * 8, err) ||
+			    dBlockBase.ensure((size_t)(numBlocks + 1) * 16, err) || dMeshTotals.ensure((size_t)numJobs * 8, err))
+				return VGB_ERR_CUDA;
+			k_block_first_job<<<(numJobs + 255) / 256, 256, 0, st>>>(dPieceStart.as<uint32_t>(), numJobs, dBlockFirstJob.as<uint32_t>());
+			++launches;
+			VGB_CUDA(cudaMemsetAsync(dMeshTotals.p, 0, (size_t)numJobs * 8, st));
+			pa.numPieces = numPieces;
+			pa.numJobs = numJobs;
+			pa.pieceStart = dPieceStart.as<uint32_t>();
+			pa.blockFirstJob = dBlockFirstJob.as<uint32_t>();
+			pa.jobSub = dJobSub.as<uint32_t>();
+			pa.jobDraw = dJobDraw.as<uint32_t>();
+			pa.subFirst = dSubFirst.as<uint32_t>();
+			pa.subNum = dSubNum.as<uint32_t>();
+			pa.subClosed = dSubClosed.as<uint8_t>();
+			pa.dd = dDD.as<DrawDerived>();
+			pa.pts = dPts.as<float2>();
+			pa.blockTotals = dBlockTotals.as<uint2>();
+			pa.meshTotals = dMeshTotals.as<uint2>();
+			pa.blockBase = dBlockBase.as<ulonglong2>();
+			pa.meshOff = dMeshOff.as<ulonglong2>();
+			pa.vertexBase = vertexBase;
+			k_piece_count<<<numBlocks, PPB, 0, st>>>(pa);
+			++launches;
+			if (scan<ScanOps<uint2>>(dBlockTotals.as<uint2>(), numBlocks, dBlockBase.as<ulonglong2>(), err)) return VGB_ERR_CUDA;
+			if (scan<ScanOps<uint2>>(dMeshTotals.as<uint2>(), numJobs, dMeshOff.as<ulonglong2>(), err)) return VGB_ERR_CUDA;
+			if (readback(totals, dMeshOff.as<ulonglong2>() + numJobs, 16, err)) return VGB_ERR_CUDA;
+		} else {
+			VGB_CUDA(cudaMemsetAsync(dMeshOff.p, 0, (size_t)(numJobs + 1) * 16, st));
+		}
+		sz.num_vertices = totals[0];
+		sz.num_indices = totals[1];
+		VGB_CUDA(cudaEventRecord(ev[2], st));
+
+		/* ---- emit ---- */
+		if (numPieces) {
+			if (dPos.ensure(totals[0] * 8 + 32, err) || dCol.ensure(totals[0] * 4 + 32, err) || dIdx.ensure(totals[1] * idxBytes + 32, err))
+				return VGB_ERR_CUDA;
+			pa.pos = dPos.as<float2>();
+			pa.col = dCol.as<uint32_t>();
+			pa.idx = dIdx.p;
+			if (idxBytes == 2) {
+				k_piece_emit<uint16_t><<<numBlocks, PPB, 0, st>>>(pa);
+			} else {
+				k_piece_emit<uint32_t><<<numBlocks, PPB, 0, st>>>(pa);
+			}
+			++launches;
+			VGB_CUDA(cudaGetLastError());
+		}
+		VGB_CUDA(cudaEventRecord(ev[3], st));
+		sz.kernel_launches = launches;
+		ran = true;
+		return 0;
+	}
+
+	int sync(std::string* err) override
+	{
+		VGB_CUDA(cudaSetDevice(dev));
+		VGB_CUDA(cudaStreamSynchronize(st));
+		if (ran) {
+			cudaEventElapsedTime(&rt.total, ev[0], ev[3]);
+			cudaEventElapsedTime(&rt.flatten, ev[0], ev[1]);
+			cudaEventElapsedTime(&rt.strokeCount, ev[1], ev[2]);
+			cudaEventElapsedTime(&rt.emit, ev[2], ev[3]);
+		}
+		return 0;
+	}
+
+	void sizes(vgb_sizes* out) override { *out = sz; }
+	RunTimes times() override { return rt; }
+	void* stream() override { return (void*)st; }
+
+	void devicePtrs(void** pos, void** color, void** index, void** mvo, void** mio, void** pts, void** subs) override
+	{
+		if (pos) *pos = dPos.p;
+		if (color) *color = dCol.p;
+		if (index) *index = dIdx.p;
+		if (mvo) *mvo = dMeshOff.p; /* interleaved {vtx, idx} u64 pairs */
+		if (mio) *mio = dMeshOff.p ? (char*)dMeshOff.p + 8 : nullptr;
+		if (pts) *pts = dPts.p;
+		if (subs) *subs = dSubFirst.p;
+	}
+
+	int download(float* pos, uint32_t* color, void* index, uint64_t vcap, uint64_t icap, uint64_t* mvo, uint64_t* mio, std::string* err) override
+	{
+		if (!ran) {
+			if (err) *err = "download before run";
+			return VGB_ERR_STATE;
+		}
+		VGB_CUDA(cudaSetDevice(dev));
+		if ((pos || color) && vcap < sz.num_vertices) {
+			if (err) *err = "vertex capacity too small";
+			return VGB_ERR_CAPACITY;
+		}
+		if (index && icap < sz.num_indices) {
+			if (err) *err = "index capacity too small";
+			return VGB_ERR_CAPACITY;
+		}
+		if (pos && sz.num_vertices) VGB_CUDA(cudaMemcpyAsync(pos, dPos.p, sz.num_vertices * 8, cudaMemcpyDeviceToHost, st));
+		if (color && sz.num_vertices) VGB_CUDA(cudaMemcpyAsync(color, dCol.p, sz.num_vertices * 4, cudaMemcpyDeviceToHost, st));
+		if (index && sz.num_indices) VGB_CUDA(cudaMemcpyAsync(index, dIdx.p, sz.num_indices * idxBytes, cudaMemcpyDeviceToHost, st));
+		if (mvo || mio) {
+			std::vector<uint64_t> tmp(2 * ((size_t)numJobs + 1));
+			VGB_CUDA(cudaMemcpyAsync(tmp.data(), dMeshOff.p, tmp.size() * 8, cudaMemcpyDeviceToHost, st));
+			VGB_CUDA(cudaStreamSynchronize(st));
+			for (size_t j = 0; j <= numJobs; ++j) {
+				if (mvo) mvo[j] = tmp[2 * j];
+				if (mio) mio[j] = tmp[2 * j + 1];
+			}
+		}
+		VGB_CUDA(cudaStreamSynchronize(st));
+		return 0;
+	}
+
+	int downloadPaths(float* pts, uint64_t ptsCap, vgb_subpath* subs, uint32_t subCap, std::string* err) override
+	{
+		if (!ran) {
+			if (err) *err = "download before run";
+			return VGB_ERR_STATE;
+		}
+		VGB_CUDA(cudaSetDevice(dev));
+		if ((pts && ptsCap < sz.num_points) || (subs && subCap < numSub)) {
+			if (err) *err = "capacity too small";
+			return VGB_ERR_CAPACITY;
+		}
+		if (pts && sz.num_points) VGB_CUDA(cudaMemcpyAsync(pts, dPts.p, sz.num_points * 8, cudaMemcpyDeviceToHost, st));
+		if (subs && numSub) {
+			std::vector<uint32_t> f(numSub), n(numSub);
+			std::vector<uint8_t> c(numSub);
+			VGB_CUDA(cudaMemcpyAsync(f.data(), dSubFirst.p, (size_t)numSub * 4, cudaMemcpyDeviceToHost, st));
+			VGB_CUDA(cudaMemcpyAsync(n.data(), dSubNum.p, (size_t)numSub * 4, cudaMemcpyDeviceToHost, st));
+			VGB_CUDA(cudaMemcpyAsync(c.data(), dSubClosed.p, (size_t)numSub, cudaMemcpyDeviceToHost, st));
+			VGB_CUDA(cudaStreamSynchronize(st));
+			for (uint32_t s = 0; s < numSub; ++s) {
+				subs[s].first_vertex = f[s];
+				subs[s].num_vertices = n[s];
+				subs[s].is_closed = c[s];
+			}
+		}
+		VGB_CUDA(cudaStreamSynchronize(st));
+		return 0;
+	}
+};
+
+Pipeline* Pipeline::create(int device, std::string* err)
+{
+	PipelineImpl* p = new PipelineImpl();
+	if (p->init(device, err) != 0) {
+		delete p;
+		return nullptr;
+	}
+	return p;
+}
+
+int deviceCount()
+{
+	int n = 0;
+	if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+	return n;
+}
+
+void* hostAlloc(size_t bytes)
+{
+	void* p = nullptr;
+	if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) return nullptr;
+	return p;
+}
+
+void hostFree(void* p)
+{
+	if (p) cudaFreeHost(p);
+}
+} // namespace vgb

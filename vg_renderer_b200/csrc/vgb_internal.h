@@ -1,0 +1,95 @@
+/*
+ * vgb_internal.h -- interface between the host-side recorder / C ABI (vgb_batch.cpp,
+ * vgb_objects.cpp) and the device pipeline (vgb_device.cu).  Not installed.
+ */
+#ifndef VGB_INTERNAL_H
+#define VGB_INTERNAL_H
+
+#include "vgb.h"
+#include <stddef.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+
+namespace vgb
+{
+/* one sub-path's slice of the command stream: {cmdBegin, cmdEnd, dataBegin, pathId} */
+struct SubRec
+{
+	uint32_t cmdBegin, cmdEnd, dataBegin, pathId;
+};
+
+/* one draw = one strokerXXX configuration applied to every sub-path of one path */
+struct DrawRec
+{
+	uint32_t ocj;   /* op | cap << 8 | join << 16 */
+	uint32_t color;
+	float width;
+	uint32_t pathId;
+};
+
+/* per-draw constants derived on the device by k_draw_prep (stroker.cpp:1393-1399 etc.) */
+struct DrawDerived
+{
+	float hsw, hsw_aa, da, fringe;
+	uint32_t nHC, color, c0, ocj;
+};
+
+/* everything the host hands to a run (all host pointers; sizes in elements) */
+struct HostTables
+{
+	/* flatten stage input */
+	const SubRec* subRec = nullptr;
+	uint32_t numSub = 0;
+	const uint8_t* cmd = nullptr;
+	uint32_t numCmd = 0;
+	const float* data = nullptr;
+	uint32_t numData = 0;
+	const float* pathScale = nullptr;
+	const float* pathTol = nullptr;
+	const float* pathXform = nullptr; /* nullable: identity for every path */
+	uint32_t numPaths = 0;
+	/* raw-polyline mode (strokerXXX on caller polylines): replaces the flatten stage */
+	const float* rawPts = nullptr;
+	uint32_t numRawPts = 0;
+	const uint32_t* rawFirst = nullptr;
+	const uint32_t* rawNum = nullptr;
+	const uint8_t* rawClosed = nullptr;
+	/* draws and jobs */
+	const DrawRec* draws = nullptr;
+	uint32_t numDraws = 0;
+	const uint32_t* jobSub = nullptr;
+	const uint32_t* jobDraw = nullptr;
+	uint32_t numJobs = 0;
+	float fringe = 1.0f;
+};
+
+struct RunTimes
+{
+	float total = 0, flatten = 0, strokeCount = 0, emit = 0;
+};
+
+/* device pipeline: owns the stream, the device buffers and the kernels */
+class Pipeline
+{
+public:
+	static Pipeline* create(int device, std::string* err);
+	virtual ~Pipeline() {}
+	virtual int upload(const HostTables& t, std::string* err) = 0;
+	virtual int run(uint32_t flags, uint64_t vertexBase, std::string* err) = 0;
+	virtual int sync(std::string* err) = 0;
+	virtual void sizes(vgb_sizes* out) = 0;
+	virtual void devicePtrs(void** pos, void** color, void** index, void** mvo, void** mio, void** pts, void** subs) = 0;
+	virtual int download(float* pos, uint32_t* color, void* index, uint64_t vcap, uint64_t icap,
+	                     uint64_t* mvo, uint64_t* mio, std::string* err) = 0;
+	virtual int downloadPaths(float* pts, uint64_t ptsCap, vgb_subpath* subs, uint32_t subCap, std::string* err) = 0;
+	virtual RunTimes times() = 0;
+	virtual void* stream() = 0;
+};
+
+int deviceCount();
+void* hostAlloc(size_t bytes);
+void hostFree(void* p);
+} // namespace vgb
+
+#endif

@@ -1,0 +1,490 @@
+/*
+ * vgb_stroke.cuh -- device-side mesh generation, expressed per PIECE.
+ *
+ * A mesh (one strokerXXX call of the reference) is cut into pieces whose outputs are
+ * contiguous, in piece order, in the mesh's vertex AND index streams:
+ *   AA stroke of an N-point polyline (stroker.cpp:1390-1991): piece i = polyline vertex i
+ *       open:   0 = start cap, 1..N-2 = joins, N-1 = end cap
+ *       closed: 0..N-1 = joins (wrap-around); the last one also emits the closing connect
+ *   convex AA fill of an N-gon (stroker.cpp:713-806, scalar variant = golden):
+ *       pieces 0..N-3 = fan triangles (3 indices, no vertex), then N vertex pieces
+ *       (2 vertices + one fringe quad) -- exactly the reference's [fan][quads] index order.
+ * Piece sizes depend on data (round joins: n = max(2, uint(dAngle/da))), so sizes are counted
+ * (k_piece_count), scanned, then emitted (k_piece_emit) -- both call classify() below, which
+ * is therefore the single place where every count decision lives.
+ *
+ * All float expressions follow the reference's evaluation order operation by operation and the
+ * file is compiled with -fmad=false, so positions are bit-identical to a non-FMA x86-64 build.
+ */
+#ifndef VGB_STROKE_CUH
+#define VGB_STROKE_CUH
+
+#include "vgb_internal.h"
+#include "vgb_math.h"
+
+namespace vgb
+{
+enum { PK_NONE = 0, PK_CAP_START, PK_JOIN, PK_CAP_END, PK_FILL_FAN, PK_FILL_VTX };
+enum { PF_LEFT = 1, PF_HAS_PREV = 2, PF_CLOSING = 4 };
+
+/* one job = one mesh: (draw, sub-path) */
+struct JobCtx
+{
+	uint32_t first, N, closed;
+	uint32_t op, cap, join;
+	float hsw, hsw_aa, da, fringe;
+	uint32_t nHC, color, c0;
+};
+
+struct Piece
+{
+	uint32_t kind, vcount, icount, n, flags, li;
+	float2 p, d01, d12, v;
+	float a01, arcDa;
+};
+
+__device__ __forceinline__ float2 f2(float x, float y) { return make_float2(x, y); }
+
+/* vec2Dir, stroker.cpp:31-38 */
+__device__ __forceinline__ float2 vdir(float2 a, float2 b)
+{
+	const float dx = b.x - a.x;
+	const float dy = b.y - a.y;
+	const float lenSqr = dx * dx + dy * dy;
+	const float invLen = lenSqr < VGB_EPSILON ? 0.0f : vgb_rsqrt(lenSqr);
+	return f2(dx * invLen, dy * invLen);
+}
+
+/* calcExtrusionVector, stroker.cpp:40-53 */
+__device__ __forceinline__ float2 extrusion(float2 d01, float2 d12)
+{
+	float2 v = f2(-d01.y, d01.x);
+	const float cross = d12.x * d01.y - d01.x * d12.y;
+	if (fabsf(cross) > (1.0f / 100.0f)) {
+		const float s = 1.0f / cross;
+		v = f2((d01.x - d12.x) * s, (d01.y - d12.y) * s);
+	}
+	return v;
+}
+
+/* number of pieces of a job (0 = the caller skips this sub-path: vg.cpp:3101, 3450) */
+__host__ __device__ __forceinline__ uint32_t pieceCount(uint32_t op, uint32_t N)
+{
+	switch (op) {
+	case VGB_OP_STROKE_AA: return N >= 2 ? N : 0;
+	case VGB_OP_CONVEX_FILL_AA: return N >= 3 ? 2 * N - 2 : 0;
+	default: return 0;
+	}
+}
+
+/* side test + arc subdivision of one join (stroker.cpp:1528-1535, 1581-1596, 1737-1752) */
+__device__ __forceinline__ void classifyJoinAA(const JobCtx& J, Piece& P)
+{
+	P.v = extrusion(P.d01, P.d12);
+	const float vx = P.v.x * J.hsw_aa;
+	const float vy = P.v.y * J.hsw_aa;
+	const float proj = P.d12.x * vx + P.d12.y * vy;
+	const bool left = proj >= 0.0f;
+	if (left) {
+		P.flags |= PF_LEFT;
+	}
+	const uint32_t conn = (P.flags & PF_HAS_PREV) ? 18u : 0u;
+	if (J.join == VGB_JOIN_MITER) {
+		P.n = 0;
+		P.vcount = 4;
+		P.icount = conn;
+	} else {
+		uint32_t n = 1;
+		if (J.join == VGB_JOIN_ROUND) {
+			/* left inner: r = perpCW(d), right inner: l = perpCCW(d) */
+			const float2 s01 = left ? f2(P.d01.y, -P.d01.x) : f2(-P.d01.y, P.d01.x);
+			const float2 s12 = left ? f2(P.d12.y, -P.d12.x) : f2(-P.d12.y, P.d12.x);
+			const float a01 = vgb_atan2(s01.y, s01.x);
+			float a12 = vgb_atan2(s12.y, s12.x);
+			if (left) {
+				if (a12 < a01) {
+					a12 += VGB_PI2;
+				}
+				n = vgb_umax(2u, (uint32_t)((a12 - a01) / J.da));
+			} else {
+				if (a12 > a01) {
+					a12 -= VGB_PI2;
+				}
+				n = vgb_umax(2u, (uint32_t)((a01 - a12) / J.da));
+			}
+			P.a01 = a01;
+			P.arcDa = (a12 - a01) / (float)n;
+		}
+		P.n = n;
+		P.vcount = 2 * n + 4;
+		P.icount = conn + 9 * n;
+	}
+	if (P.flags & PF_CLOSING) {
+		P.icount += 18;
+	}
+}
+
+/* the single source of every count decision: piece q of job J */
+__device__ __forceinline__ Piece classify(const JobCtx& J, uint32_t q, const float2* __restrict__ pts)
+{
+	Piece P;
+	P.kind = PK_NONE;
+	P.vcount = 0;
+	P.icount = 0;
+	P.n = 0;
+	P.flags = 0;
+	P.li = q;
+	P.a01 = 0.0f;
+	P.arcDa = 0.0f;
+	P.p = P.d01 = P.d12 = P.v = f2(0.0f, 0.0f);
+	const float2* v = pts + J.first;
+	const uint32_t N = J.N;
+	if (J.op == VGB_OP_STROKE_AA) {
+		if (!J.closed && q == 0) {
+			P.kind = PK_CAP_START;
+			P.p = v[0];
+			P.d01 = vdir(P.p, v[1]);
+			if (J.cap == VGB_CAP_ROUND) {
+				P.n = J.nHC;
+				P.vcount = 2 * J.nHC;
+				P.icount = 9 * J.nHC - 12;
+			} else {
+				P.vcount = 4;
+				P.icount = 6;
+			}
+		} else if (!J.closed && q == N - 1) {
+			P.kind = PK_CAP_END;
+			P.p = v[N - 1];
+			P.d01 = vdir(v[N - 2], P.p);
+			P.flags = PF_HAS_PREV;
+			if (J.cap == VGB_CAP_ROUND) {
+				P.n = J.nHC;
+				P.vcount = 2 * J.nHC;
+				P.icount = 9 * J.nHC + 6;
+			} else {
+				P.vcount = 4;
+				P.icount = 24;
+			}
+		} else {
+			P.kind = PK_JOIN;
+			const float2 pm = v[q == 0 ? N - 1 : q - 1];
+			const float2 pn = v[q == N - 1 ? 0 : q + 1];
+			P.p = v[q];
+			P.d01 = vdir(pm, P.p);
+			P.d12 = vdir(P.p, pn);
+			if (!(J.closed && q == 0)) {
+				P.flags |= PF_HAS_PREV;
+			}
+			if (J.closed && q == N - 1) {
+				P.flags |= PF_CLOSING;
+			}
+			classifyJoinAA(J, P);
+		}
+	} else if (J.op == VGB_OP_CONVEX_FILL_AA) {
+		if (q < N - 2) {
+			P.kind = PK_FILL_FAN;
+			P.icount = 3;
+		} else {
+			const uint32_t i = q - (N - 2);
+			P.kind = PK_FILL_VTX;
+			P.li = i;
+			P.vcount = 2;
+			P.icount = 6;
+			const float2 pm = v[i == 0 ? N - 1 : i - 1];
+			const float2 pn = v[i == N - 1 ? 0 : i + 1];
+			P.p = v[i];
+			P.d01 = vdir(pm, P.p);
+			P.d12 = vdir(P.p, pn);
+		}
+	}
+	return P;
+}
+
+/* (LeftAA, Left, Right, RightAA) a piece hands to the next one; F = its first vertex id */
+__device__ __forceinline__ uint4 pieceOut4(const JobCtx& J, const Piece& P, uint32_t F)
+{
+	if (P.kind == PK_CAP_START) {
+		if (J.cap == VGB_CAP_ROUND) {
+			const uint32_t e = 2 * (P.n - 1);
+			return make_uint4(F + 1, F, F + e, F + e + 1);
+		}
+		return make_uint4(F, F + 1, F + 2, F + 3);
+	}
+	/* join */
+	const uint32_t n2 = (J.join == VGB_JOIN_MITER) ? 0u : 2 * P.n;
+	if (P.flags & PF_LEFT) {
+		return make_uint4(F, F + 1, F + 2 + n2, F + 3 + n2);
+	}
+	return make_uint4(F + 3 + n2, F + 2 + n2, F + 1, F);
+}
+
+/* the 4 ids of a join's entry cross-section (what the previous piece connects to) */
+__device__ __forceinline__ uint4 joinIn4(bool left, uint32_t F)
+{
+	return left ? make_uint4(F, F + 1, F + 2, F + 3) : make_uint4(F + 3, F + 2, F + 1, F);
+}
+
+template<class IDX>
+struct Sink
+{
+	float2* pos;
+	uint32_t* col;
+	IDX* idx;
+	uint32_t base; /* added to every index value (0 for per-mesh uint16) */
+
+	__device__ __forceinline__ void V(uint32_t k, float x, float y, uint32_t c) const
+	{
+		pos[k] = make_float2(x, y);
+		col[k] = c;
+	}
+	__device__ __forceinline__ void I(uint32_t k, uint32_t v) const { idx[k] = (IDX)(v + base); }
+	__device__ __forceinline__ void tri(uint32_t k, uint32_t a, uint32_t b, uint32_t c) const
+	{
+		I(k, a);
+		I(k + 1, b);
+		I(k + 2, c);
+	}
+	/* the 18-index strip between two cross-sections (stroker.cpp:1557-1564 and siblings) */
+	__device__ __forceinline__ void connect(uint32_t k, uint4 p, uint4 c) const
+	{
+		tri(k + 0, p.x, p.y, c.y);
+		tri(k + 3, p.x, c.y, c.x);
+		tri(k + 6, p.y, p.z, c.z);
+		tri(k + 9, p.y, c.z, c.y);
+		tri(k + 12, p.z, p.w, c.w);
+		tri(k + 15, p.z, c.w, c.z);
+	}
+};
+
+/* ---- AA stroke pieces ---------------------------------------------------------------- */
+template<class IDX>
+__device__ __forceinline__ void emitCapStartAA(const JobCtx& J, const Piece& P, uint32_t F, const Sink<IDX>& S)
+{
+	const float2 p0 = P.p, d = P.d01;
+	const float2 l = f2(-d.y, d.x);
+	const float hsw = J.hsw, hsw_aa = J.hsw_aa;
+	if (J.cap == VGB_CAP_ROUND) {
+		/* stroker.cpp:1475-1515 */
+		const uint32_t n = P.n;
+		const float startAngle = vgb_atan2(l.y, l.x);
+		for (uint32_t i = 0; i < n; ++i) {
+			const float a = startAngle + (float)i * VGB_PI / (float)(n - 1);
+			float sa, ca;
+			vgb_sincos(a, &sa, &ca);
+			S.V(2 * i, p0.x + ca * hsw, p0.y + sa * hsw, J.color);
+			S.V(2 * i + 1, p0.x + ca * hsw_aa, p0.y + sa * hsw_aa, J.c0);
+		}
+		uint32_t k = 0;
+		for (uint32_t i = 0; i < n - 2; ++i, k += 3) {
+			S.tri(k, F, F + 2 * i + 2, F + 2 * i + 4);
+		}
+		for (uint32_t i = 0; i < n - 1; ++i, k += 6) {
+			const uint32_t b = F + 2 * i;
+			S.tri(k, b, b + 1, b + 3);
+			S.tri(k + 3, b, b + 3, b + 2);
+		}
+		return;
+	}
+	const float lx = l.x * hsw, ly = l.y * hsw;
+	const float lax = l.x * hsw_aa, lay = l.y * hsw_aa;
+	if (J.cap == VGB_CAP_BUTT) {
+		/* stroker.cpp:1422-1447 */
+		const float dax = d.x * J.fringe, day = d.y * J.fringe;
+		S.V(0, p0.x + (lax - dax), p0.y + (lay - day), J.c0);
+		S.V(1, p0.x + lx, p0.y + ly, J.color);
+		S.V(2, p0.x - lx, p0.y - ly, J.color);
+		S.V(3, p0.x - (lax + dax), p0.y - (lay + day), J.c0);
+	} else {
+		/* square, stroker.cpp:1448-1474 */
+		const float dx = d.x * hsw, dy = d.y * hsw;
+		const float dax = d.x * hsw_aa, day = d.y * hsw_aa;
+		S.V(0, p0.x + (lax - dax), p0.y + (lay - day), J.c0);
+		S.V(1, p0.x + (lx - dx), p0.y + (ly - dy), J.color);
+		S.V(2, p0.x - (lx + dx), p0.y - (ly + dy), J.color);
+		S.V(3, p0.x - (lax + dax), p0.y - (lay + day), J.c0);
+	}
+	S.tri(0, F, F + 2, F + 1);
+	S.tri(3, F, F + 3, F + 2);
+}
+
+template<class IDX>
+__device__ __forceinline__ void emitCapEndAA(const JobCtx& J, const Piece& P, uint32_t C, uint4 prev, const Sink<IDX>& S)
+{
+	const float2 p1 = P.p, d = P.d01;
+	const float2 l = f2(-d.y, d.x);
+	const float hsw = J.hsw, hsw_aa = J.hsw_aa;
+	if (J.cap == VGB_CAP_ROUND) {
+		/* stroker.cpp:1917-1968 */
+		const uint32_t n = P.n;
+		const float startAngle = vgb_atan2(l.y, l.x);
+		for (uint32_t i = 0; i < n; ++i) {
+			const float a = startAngle - (float)i * VGB_PI / (float)(n - 1);
+			float sa, ca;
+			vgb_sincos(a, &sa, &ca);
+			S.V(2 * i, p1.x + ca * hsw, p1.y + sa * hsw, J.color);
+			S.V(2 * i + 1, p1.x + ca * hsw_aa, p1.y + sa * hsw_aa, J.c0);
+		}
+		const uint32_t e = C + 2 * (n - 1);
+		S.connect(0, prev, make_uint4(C + 1, C, e, e + 1));
+		uint32_t k = 18;
+		for (uint32_t i = 0; i < n - 2; ++i, k += 3) {
+			const uint32_t b = C + 2 * i;
+			S.tri(k, C, b + 4, b + 2);
+		}
+		for (uint32_t i = 0; i < n - 1; ++i, k += 6) {
+			const uint32_t b = C + 2 * i;
+			S.tri(k, b, b + 3, b + 1);
+			S.tri(k + 3, b, b + 2, b + 3);
+		}
+		return;
+	}
+	const float lx = l.x * hsw, ly = l.y * hsw;
+	const float lax = l.x * hsw_aa, lay = l.y * hsw_aa;
+	if (J.cap == VGB_CAP_BUTT) {
+		/* stroker.cpp:1858-1886 */
+		const float dax = d.x * J.fringe, day = d.y * J.fringe;
+		S.V(0, p1.x + (lax + dax), p1.y + (lay + day), J.c0);
+		S.V(1, p1.x + lx, p1.y + ly, J.color);
+		S.V(2, p1.x - lx, p1.y - ly, J.color);
+		S.V(3, p1.x - (lax - dax), p1.y - (lay - day), J.c0);
+	} else {
+		/* square, stroker.cpp:1887-1916 */
+		const float dx = d.x * hsw, dy = d.y * hsw;
+		const float dax = d.x * hsw_aa, day = d.y * hsw_aa;
+		S.V(0, p1.x + (lax + dax), p1.y + (lay + day), J.c0);
+		S.V(1, p1.x + (lx + dx), p1.y + (ly + dy), J.color);
+		S.V(2, p1.x - (lx - dx), p1.y - (ly - dy), J.color);
+		S.V(3, p1.x - (lax - dax), p1.y - (lay - day), J.c0);
+	}
+	S.connect(0, prev, make_uint4(C, C + 1, C + 2, C + 3));
+	S.tri(18, C, C + 1, C + 2);
+	S.tri(21, C, C + 2, C + 3);
+}
+
+/* stroker.cpp:1536-1847. firstLeft: side of the mesh's first join (closing connect only) */
+template<class IDX>
+__device__ __forceinline__ void emitJoinAA(const JobCtx& J, const Piece& P, uint32_t F, uint4 prev, bool firstLeft, const Sink<IDX>& S)
+{
+	const bool left = (P.flags & PF_LEFT) != 0;
+	const float hsw = J.hsw, hsw_aa = J.hsw_aa;
+	const float2 p1 = P.p;
+	/* right inner: every "+v" of the left case becomes "-v" (negation is exact) */
+	const float2 vs = left ? P.v : f2(-P.v.x, -P.v.y);
+	const float vax = vs.x * hsw_aa, vay = vs.y * hsw_aa;
+	const float vx = vs.x * hsw, vy = vs.y * hsw;
+	uint32_t k = 0;
+	if (J.join == VGB_JOIN_MITER) {
+		S.V(0, p1.x + vax, p1.y + vay, J.c0);
+		S.V(1, p1.x + vx, p1.y + vy, J.color);
+		S.V(2, p1.x - vx, p1.y - vy, J.color);
+		S.V(3, p1.x - vax, p1.y - vay, J.c0);
+		if (P.flags & PF_HAS_PREV) {
+			S.connect(0, prev, joinIn4(left, F));
+			k = 18;
+		}
+	} else {
+		const uint32_t n = P.n;
+		const float2 d01 = P.d01, d12 = P.d12;
+		const float2 s01 = left ? f2(d01.y, -d01.x) : f2(-d01.y, d01.x);
+		const float2 s12 = left ? f2(d12.y, -d12.x) : f2(-d12.y, d12.x);
+		S.V(0, p1.x + vax, p1.y + vay, J.c0);
+		S.V(1, p1.x + vx, p1.y + vy, J.color);
+		/* first arc vertex */
+		{
+			float ax = p1.x + s01.x * hsw, ay = p1.y + s01.y * hsw;
+			if (J.join == VGB_JOIN_BEVEL) {
+				const float cosAngle = fabsf(s01.x * s12.x + s01.y * s12.y);
+				const float t = cosAngle * J.fringe;
+				ax = ax - d01.x * t;
+				ay = ay - d01.y * t;
+			}
+			S.V(2, ax, ay, J.color);
+			S.V(3, p1.x + s01.x * hsw_aa, p1.y + s01.y * hsw_aa, J.c0);
+		}
+		/* middle arc vertices */
+		for (uint32_t i = 1; i < n; ++i) {
+			const float a = P.a01 + (float)i * P.arcDa;
+			float sa, ca;
+			vgb_sincos(a, &sa, &ca);
+			S.V(2 + 2 * i, p1.x + ca * hsw, p1.y + sa * hsw, J.color);
+			S.V(3 + 2 * i, p1.x + ca * hsw_aa, p1.y + sa * hsw_aa, J.c0);
+		}
+		/* last arc vertex */
+		{
+			float ax = p1.x + s12.x * hsw, ay = p1.y + s12.y * hsw;
+			if (J.join == VGB_JOIN_BEVEL) {
+				const float cosAngle = fabsf(s01.x * s12.x + s01.y * s12.y);
+				const float t = cosAngle * J.fringe;
+				ax = ax + d12.x * t;
+				ay = ay + d12.y * t;
+			}
+			S.V(2 + 2 * n, ax, ay, J.color);
+			S.V(3 + 2 * n, p1.x + s12.x * hsw_aa, p1.y + s12.y * hsw_aa, J.c0);
+		}
+		if (P.flags & PF_HAS_PREV) {
+			S.connect(0, prev, joinIn4(left, F));
+			k = 18;
+		}
+		uint32_t A = F + 2;
+		if (left) {
+			for (uint32_t i = 0; i < n; ++i, k += 9, A += 2) {
+				S.tri(k, F + 1, A, A + 2);
+				S.tri(k + 3, A, A + 1, A + 3);
+				S.tri(k + 6, A, A + 3, A + 2);
+			}
+		} else {
+			for (uint32_t i = 0; i < n; ++i, k += 9, A += 2) {
+				S.tri(k, F + 1, A + 2, A);
+				S.tri(k + 3, A, A + 3, A + 1);
+				S.tri(k + 6, A, A + 2, A + 3);
+			}
+		}
+	}
+	if (P.flags & PF_CLOSING) {
+		/* stroker.cpp:1970-1984: previous = this piece, first = piece 0 (its F is 0) */
+		S.connect(k, pieceOut4(J, P, F), joinIn4(firstLeft, 0));
+	}
+}
+
+/* side of join 0 of a closed polyline (needed by the closing connect) */
+__device__ __forceinline__ bool firstJoinLeft(const JobCtx& J, const float2* __restrict__ pts)
+{
+	const float2* v = pts + J.first;
+	const float2 d01 = vdir(v[J.N - 1], v[0]);
+	const float2 d12 = vdir(v[0], v[J.N == 1 ? 0 : 1]);
+	const float2 e = extrusion(d01, d12);
+	const float proj = d12.x * (e.x * J.hsw_aa) + d12.y * (e.y * J.hsw_aa);
+	return proj >= 0.0f;
+}
+
+/* ---- convex AA fill pieces (stroker.cpp:713-806) ---------------------------------------- */
+template<class IDX>
+__device__ __forceinline__ void emitFillFan(const Piece& P, const Sink<IDX>& S)
+{
+	S.tri(0, 0, 2 * P.li + 2, 2 * P.li + 4);
+}
+
+template<class IDX>
+__device__ __forceinline__ void emitFillVtx(const JobCtx& J, const Piece& P, const float2* __restrict__ pts, const Sink<IDX>& S)
+{
+	const float2* v = pts + J.first;
+	const float2 a = f2(v[1].x - v[0].x, v[1].y - v[0].y);
+	const float2 b = f2(v[2].x - v[0].x, v[2].y - v[0].y);
+	const float cross = a.x * b.y - b.x * a.y;
+	const float aa = J.fringe * 0.5f * vgb_sign(cross);
+	const float2 e = extrusion(P.d01, P.d12);
+	const float ex = e.x * aa, ey = e.y * aa;
+	S.V(0, P.p.x + ex, P.p.y + ey, J.color);
+	S.V(1, P.p.x - ex, P.p.y - ey, J.c0);
+	const uint32_t f = 2 * P.li;
+	if (P.li + 1 < J.N) {
+		S.tri(0, f, f + 1, f + 3);
+		S.tri(3, f, f + 3, f + 2);
+	} else {
+		S.tri(0, f, f + 1, 1);
+		S.tri(3, f, 1, 0);
+	}
+}
+} // namespace vgb
+
+#endif
