@@ -199,6 +199,11 @@ VGB_API int vgb_batch_execute(vgb_batch* b, uint32_t flags, float* pos, uint32_t
 /* elapsed device time (ms, CUDA events on the batch stream) of the kernels of the last run */
 VGB_API int vgb_batch_last_run_ms(vgb_batch* b, float* total_ms, float* flatten_ms, float* stroke_count_ms, float* emit_ms);
 
+/* user timing marks: cudaEventRecord on the batch stream into slot 0..7, and the elapsed device
+ * time between two recorded slots (synchronises on the later one) */
+VGB_API int vgb_batch_mark(vgb_batch* b, uint32_t slot);
+VGB_API int vgb_batch_elapsed_ms(vgb_batch* b, uint32_t slot_a, uint32_t slot_b, float* ms);
+
 /* pinned host memory helpers (cudaHostAlloc / cudaFreeHost) for the host-buffer path */
 VGB_API void* vgb_host_alloc(size_t bytes);
 VGB_API void vgb_host_free(void* p);

@@ -96,6 +96,8 @@ def load_library():
     L.vgb_batch_download_paths.argtypes = [vp, vp, u64, vp, u32]
     L.vgb_batch_execute.argtypes = [vp, u32, vp, vp, vp, u64, u64, vp, vp, C.POINTER(Sizes)]
     L.vgb_batch_last_run_ms.argtypes = [vp] + [C.POINTER(f)] * 4
+    L.vgb_batch_mark.argtypes = [vp, u32]
+    L.vgb_batch_elapsed_ms.argtypes = [vp, u32, u32, C.POINTER(f)]
     L.vgb_host_alloc.restype = vp
     L.vgb_host_alloc.argtypes = [C.c_size_t]
     L.vgb_host_free.argtypes = [vp]
@@ -241,6 +243,13 @@ class Batch:
         v = [C.c_float() for _ in range(4)]
         self._chk(self.L.vgb_batch_last_run_ms(self.h, *[C.byref(x) for x in v]))
         return dict(total=v[0].value, flatten=v[1].value, stroke_count=v[2].value, emit=v[3].value)
+
+    def mark(self, slot): return self._chk(self.L.vgb_batch_mark(self.h, slot))
+
+    def elapsed_ms(self, a, b):
+        v = C.c_float()
+        self._chk(self.L.vgb_batch_elapsed_ms(self.h, a, b, C.byref(v)))
+        return v.value
 
     def device_ptrs(self):
         p = [C.c_void_p() for _ in range(7)]

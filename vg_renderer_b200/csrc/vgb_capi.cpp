@@ -529,6 +529,24 @@ int vgb_batch_last_run_ms(vgb_batch* b, float* total, float* flatten, float* str
 	return 0;
 }
 
+int vgb_batch_mark(vgb_batch* b, uint32_t slot)
+{
+	if (!b) return fail(VGB_ERR_INVALID, "null batch");
+	std::string err;
+	const int rc = b->pipe->mark(slot, &err);
+	if (rc) return fail(rc, err.c_str());
+	return 0;
+}
+
+int vgb_batch_elapsed_ms(vgb_batch* b, uint32_t a, uint32_t c, float* ms)
+{
+	if (!b || !ms) return fail(VGB_ERR_INVALID, "null argument");
+	std::string err;
+	const int rc = b->pipe->elapsed(a, c, ms, &err);
+	if (rc) return fail(rc, err.c_str());
+	return 0;
+}
+
 void* vgb_host_alloc(size_t bytes) { return hostAlloc(bytes); }
 void vgb_host_free(void* p) { hostFree(p); }
 void* vgb_batch_stream(vgb_batch* b) { return b ? b->pipe->stream() : nullptr; }

@@ -564,6 +564,7 @@ public:
 	int dev = 0;
 	cudaStream_t st = nullptr;
 	cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+	cudaEvent_t userEv[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 	/* inputs */
 	DevBuf dSubRec, dCmd, dData, dScale, dTol, dXform, dDraws, dJobSub, dJobDraw;
 	/* intermediates */
@@ -588,6 +589,7 @@ public:
 		                 &dMeshTotals, &dMeshOff, &dScanTmp, &dPos, &dCol, &dIdx};
 		for (DevBuf* b : all) b->release();
 		for (auto& e : ev) if (e) cudaEventDestroy(e);
+		for (auto& e : userEv) if (e) cudaEventDestroy(e);
 		if (hPinned) cudaFreeHost(hPinned);
 		if (st) cudaStreamDestroy(st);
 	}
@@ -607,6 +609,7 @@ public:
 		VGB_CUDA(cudaSetDevice(dev));
 		VGB_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
 		for (auto& e : ev) VGB_CUDA(cudaEventCreate(&e));
+		for (auto& e : userEv) VGB_CUDA(cudaEventCreate(&e));
 		VGB_CUDA(cudaHostAlloc(&hPinned, 256, cudaHostAllocDefault));
 		memset(&sz, 0, sizeof(sz));
 		return 0;
@@ -813,6 +816,29 @@ public:
 			cudaEventElapsedTime(&rt.strokeCount, ev[1], ev[2]);
 			cudaEventElapsedTime(&rt.emit, ev[2], ev[3]);
 		}
+		return 0;
+	}
+
+	int mark(uint32_t slot, std::string* err) override
+	{
+		if (slot >= 8) {
+			if (err) *err = "event slot out of range";
+			return VGB_ERR_INVALID;
+		}
+		VGB_CUDA(cudaSetDevice(dev));
+		VGB_CUDA(cudaEventRecord(userEv[slot], st));
+		return 0;
+	}
+
+	int elapsed(uint32_t a, uint32_t b, float* ms, std::string* err) override
+	{
+		if (a >= 8 || b >= 8) {
+			if (err) *err = "event slot out of range";
+			return VGB_ERR_INVALID;
+		}
+		VGB_CUDA(cudaSetDevice(dev));
+		VGB_CUDA(cudaEventSynchronize(userEv[b]));
+		VGB_CUDA(cudaEventElapsedTime(ms, userEv[a], userEv[b]));
 		return 0;
 	}
 

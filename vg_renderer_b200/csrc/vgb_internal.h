@@ -85,6 +85,8 @@ public:
 	virtual int downloadPaths(float* pts, uint64_t ptsCap, vgb_subpath* subs, uint32_t subCap, std::string* err) = 0;
 	virtual RunTimes times() = 0;
 	virtual void* stream() = 0;
+	virtual int mark(uint32_t slot, std::string* err) = 0;
+	virtual int elapsed(uint32_t a, uint32_t b, float* ms, std::string* err) = 0;
 };
 
 int deviceCount();
