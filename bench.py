@@ -243,14 +243,11 @@ def main():
     vertex_base = 0
     if args.merged and dist is not None:
         # exclusive scan of per-rank vertex totals (16 B per rank over NCCL): SURVEY.md 8e
-        import torch
+        from vg_renderer_b200.dist import exclusive_bases
         b.run()
         b.sync()
         s0 = b.sizes()
-        mine = torch.tensor([int(s0.num_vertices), int(s0.num_indices)], dtype=torch.int64, device=f"cuda:{local}")
-        allv = [torch.zeros_like(mine) for _ in range(world)]
-        dist.all_gather(allv, mine)
-        vertex_base = int(sum(int(t[0]) for t in allv[:rank]))
+        vertex_base, _ib, _tv, _ti = exclusive_bases(int(s0.num_vertices), int(s0.num_indices), device=f"cuda:{local}")
 
     def step():
         b.run(index_u32=args.merged, vertex_base=vertex_base)

@@ -119,6 +119,9 @@ VGB_API int vgb_device_count(void);
 VGB_API const char* vgb_version(void);
 
 /* ---- batched path: record -> run -> read ------------------------------------------------ */
+/* device_ordinal >= 0: a CUDA device (fails with VGB_ERR_NOGPU if none is usable).
+ * device_ordinal == -1: record-only batch (host tables can be built and inspected; upload/run
+ * fail with VGB_ERR_NOGPU) -- used by the CPU-only host-logic tests. */
 VGB_API vgb_batch* vgb_batch_create(int device_ordinal);
 VGB_API void vgb_batch_destroy(vgb_batch* b);
 
@@ -166,6 +169,12 @@ VGB_API int vgb_batch_set_polylines(vgb_batch* b, const float* pts, uint32_t num
 VGB_API int vgb_batch_draw_polyline(vgb_batch* b, uint32_t subpath, uint32_t op, uint32_t color, float width, uint32_t cap, uint32_t join);
 /* the same draw for every polyline sub-path / every recorded path */
 VGB_API int vgb_batch_draw_all(vgb_batch* b, uint32_t op, uint32_t color, float width, uint32_t cap, uint32_t join);
+
+/* introspection of what was recorded: out6 = {paths, sub-paths, commands, data floats, draws, jobs};
+ * the arrays (each nullable) receive one entry per sub-path / per job */
+VGB_API int vgb_batch_recorded_counts(vgb_batch* b, uint32_t* out6);
+VGB_API int vgb_batch_recorded_subpaths(vgb_batch* b, uint32_t* cmd_begin, uint32_t* cmd_end, uint32_t* data_begin, uint32_t* path_id);
+VGB_API int vgb_batch_recorded_jobs(vgb_batch* b, uint32_t* job_subpath, uint32_t* job_draw);
 
 /* ---- execution ----------------------------------------------------------------------------
  * upload: host tables -> device (async on the batch stream).  run: all kernels; results stay in

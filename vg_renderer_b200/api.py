@@ -87,6 +87,9 @@ def load_library():
     L.vgb_batch_set_polylines.argtypes = [vp, vp, u32, vp, vp, vp, u32, f, f]
     L.vgb_batch_draw_polyline.argtypes = [vp, u32, u32, u32, f, u32, u32]
     L.vgb_batch_draw_all.argtypes = [vp, u32, u32, f, u32, u32]
+    L.vgb_batch_recorded_counts.argtypes = [vp, vp]
+    L.vgb_batch_recorded_subpaths.argtypes = [vp, vp, vp, vp, vp]
+    L.vgb_batch_recorded_jobs.argtypes = [vp, vp, vp]
     L.vgb_batch_upload.argtypes = [vp]
     L.vgb_batch_run.argtypes = [vp, u32, u64]
     L.vgb_batch_sync.argtypes = [vp]
@@ -224,6 +227,18 @@ class Batch:
 
     def draw_all(self, op=OP_STROKE_AA, color=0xFF0000FF, width=4.0, cap=CAP_BUTT, join=JOIN_MITER):
         return self._chk(self.L.vgb_batch_draw_all(self.h, op, color, width, cap, join))
+
+    def recorded(self):
+        """host tables as recorded (works on a record-only batch, device=-1)"""
+        c = np.zeros(6, np.uint32)
+        self._chk(self.L.vgb_batch_recorded_counts(self.h, _ptr(c)))
+        ns, nj = int(c[1]), int(c[5])
+        a = [np.zeros(max(ns, 1), np.uint32) for _ in range(4)]
+        self._chk(self.L.vgb_batch_recorded_subpaths(self.h, *[_ptr(x) for x in a]))
+        js, jd = np.zeros(max(nj, 1), np.uint32), np.zeros(max(nj, 1), np.uint32)
+        self._chk(self.L.vgb_batch_recorded_jobs(self.h, _ptr(js), _ptr(jd)))
+        return dict(num_paths=int(c[0]), num_subpaths=ns, num_cmds=int(c[2]), num_data=int(c[3]), num_draws=int(c[4]), num_jobs=nj,
+                    cmd_begin=a[0][:ns], cmd_end=a[1][:ns], data_begin=a[2][:ns], path_id=a[3][:ns], job_subpath=js[:nj], job_draw=jd[:nj])
 
     # ---- execution ----
     def upload(self): return self._chk(self.L.vgb_batch_upload(self.h))

@@ -28,6 +28,12 @@ static int fail(int code, const char* msg)
 	return code;
 }
 
+#define NEED_PIPE(b) \
+	do { \
+		if (!(b)) return fail(VGB_ERR_INVALID, "null batch"); \
+		if (!(b)->pipe) return fail(VGB_ERR_NOGPU, "record-only batch (device -1): no GPU pipeline, and there is no CPU fallback"); \
+	} while (0)
+
 static inline bool finite_all(const float* p, size_t n)
 {
 	/* a NaN/Inf coordinate makes the reference's pathCubicTo loop forever */
@@ -130,10 +136,13 @@ const char* vgb_version(void) { return "vgb200 0.1 (sm_100a)"; }
 vgb_batch* vgb_batch_create(int device)
 {
 	std::string err;
-	Pipeline* p = Pipeline::create(device, &err);
-	if (!p) {
-		t_err = err;
-		return nullptr;
+	Pipeline* p = nullptr;
+	if (device != -1) {
+		p = Pipeline::create(device, &err);
+		if (!p) {
+			t_err = err;
+			return nullptr;
+		}
 	}
 	vgb_batch* b = new (std::nothrow) vgb_batch();
 	if (!b) {
@@ -410,9 +419,46 @@ int vgb_batch_draw_all(vgb_batch* b, uint32_t op, uint32_t color, float width, u
 	return addDraw(b, op, color, width, cap, join, 0, 0, (uint32_t)b->subs.size());
 }
 
+int vgb_batch_recorded_counts(vgb_batch* b, uint32_t* out6)
+{
+	if (!b || !out6) return fail(VGB_ERR_INVALID, "null argument");
+	b->closeSub();
+	out6[0] = (uint32_t)b->pathScale.size();
+	out6[1] = (uint32_t)(b->rawMode ? b->rawFirst.size() : b->subs.size());
+	out6[2] = (uint32_t)b->cmd.size();
+	out6[3] = (uint32_t)b->data.size();
+	out6[4] = (uint32_t)b->draws.size();
+	out6[5] = (uint32_t)b->jobSub.size();
+	return 0;
+}
+
+int vgb_batch_recorded_subpaths(vgb_batch* b, uint32_t* cb, uint32_t* ce, uint32_t* db, uint32_t* pid)
+{
+	if (!b) return fail(VGB_ERR_INVALID, "null batch");
+	b->closeSub();
+	for (size_t i = 0; i < b->subs.size(); ++i) {
+		if (cb) cb[i] = b->subs[i].cmdBegin;
+		if (ce) ce[i] = b->subs[i].cmdEnd;
+		if (db) db[i] = b->subs[i].dataBegin;
+		if (pid) pid[i] = b->subs[i].pathId;
+	}
+	return 0;
+}
+
+int vgb_batch_recorded_jobs(vgb_batch* b, uint32_t* js, uint32_t* jd)
+{
+	if (!b) return fail(VGB_ERR_INVALID, "null batch");
+	for (size_t i = 0; i < b->jobSub.size(); ++i) {
+		if (js) js[i] = b->jobSub[i];
+		if (jd) jd[i] = b->jobDraw[i];
+	}
+	return 0;
+}
+
 int vgb_batch_upload(vgb_batch* b)
 {
 	if (!b) return fail(VGB_ERR_INVALID, "null batch");
+	if (!b->pipe) return fail(VGB_ERR_NOGPU, "record-only batch (device -1): no GPU pipeline, and there is no CPU fallback");
 	b->closeSub();
 	HostTables t;
 	t.fringe = b->fringe;
@@ -450,6 +496,7 @@ int vgb_batch_upload(vgb_batch* b)
 
 int vgb_batch_run(vgb_batch* b, uint32_t flags, uint64_t vertexBase)
 {
+	NEED_PIPE(b);
 	if (!b) return fail(VGB_ERR_INVALID, "null batch");
 	if (b->dirty) {
 		const int rc = vgb_batch_upload(b);
@@ -463,6 +510,7 @@ int vgb_batch_run(vgb_batch* b, uint32_t flags, uint64_t vertexBase)
 
 int vgb_batch_sync(vgb_batch* b)
 {
+	NEED_PIPE(b);
 	if (!b) return fail(VGB_ERR_INVALID, "null batch");
 	std::string err;
 	const int rc = b->pipe->sync(&err);
@@ -472,6 +520,7 @@ int vgb_batch_sync(vgb_batch* b)
 
 int vgb_batch_get_sizes(vgb_batch* b, vgb_sizes* out)
 {
+	NEED_PIPE(b);
 	if (!b || !out) return fail(VGB_ERR_INVALID, "null argument");
 	b->pipe->sizes(out);
 	return 0;
@@ -479,6 +528,7 @@ int vgb_batch_get_sizes(vgb_batch* b, vgb_sizes* out)
 
 int vgb_batch_device_ptrs(vgb_batch* b, void** pos, void** color, void** index, void** mvo, void** mio, void** pts, void** subs)
 {
+	NEED_PIPE(b);
 	if (!b) return fail(VGB_ERR_INVALID, "null batch");
 	b->pipe->devicePtrs(pos, color, index, mvo, mio, pts, subs);
 	return 0;
@@ -486,6 +536,7 @@ int vgb_batch_device_ptrs(vgb_batch* b, void** pos, void** color, void** index, 
 
 int vgb_batch_download(vgb_batch* b, float* pos, uint32_t* color, void* index, uint64_t vcap, uint64_t icap, uint64_t* mvo, uint64_t* mio)
 {
+	NEED_PIPE(b);
 	if (!b) return fail(VGB_ERR_INVALID, "null batch");
 	std::string err;
 	const int rc = b->pipe->download(pos, color, index, vcap, icap, mvo, mio, &err);
@@ -495,6 +546,7 @@ int vgb_batch_download(vgb_batch* b, float* pos, uint32_t* color, void* index, u
 
 int vgb_batch_download_paths(vgb_batch* b, float* pts, uint64_t ptsCap, vgb_subpath* subs, uint32_t subCap)
 {
+	NEED_PIPE(b);
 	if (!b) return fail(VGB_ERR_INVALID, "null batch");
 	std::string err;
 	const int rc = b->pipe->downloadPaths(pts, ptsCap, subs, subCap, &err);
@@ -518,6 +570,7 @@ int vgb_batch_execute(vgb_batch* b, uint32_t flags, float* pos, uint32_t* color,
 
 int vgb_batch_last_run_ms(vgb_batch* b, float* total, float* flatten, float* strokeCount, float* emit)
 {
+	NEED_PIPE(b);
 	if (!b) return fail(VGB_ERR_INVALID, "null batch");
 	std::string err;
 	b->pipe->sync(&err);
@@ -531,6 +584,7 @@ int vgb_batch_last_run_ms(vgb_batch* b, float* total, float* flatten, float* str
 
 int vgb_batch_mark(vgb_batch* b, uint32_t slot)
 {
+	NEED_PIPE(b);
 	if (!b) return fail(VGB_ERR_INVALID, "null batch");
 	std::string err;
 	const int rc = b->pipe->mark(slot, &err);
@@ -540,6 +594,7 @@ int vgb_batch_mark(vgb_batch* b, uint32_t slot)
 
 int vgb_batch_elapsed_ms(vgb_batch* b, uint32_t a, uint32_t c, float* ms)
 {
+	NEED_PIPE(b);
 	if (!b || !ms) return fail(VGB_ERR_INVALID, "null argument");
 	std::string err;
 	const int rc = b->pipe->elapsed(a, c, ms, &err);
@@ -549,7 +604,7 @@ int vgb_batch_elapsed_ms(vgb_batch* b, uint32_t a, uint32_t c, float* ms)
 
 void* vgb_host_alloc(size_t bytes) { return hostAlloc(bytes); }
 void vgb_host_free(void* p) { hostFree(p); }
-void* vgb_batch_stream(vgb_batch* b) { return b ? b->pipe->stream() : nullptr; }
+void* vgb_batch_stream(vgb_batch* b) { return (b && b->pipe) ? b->pipe->stream() : nullptr; }
 
 /* =========================================================================================
  * per-object API (include/vg/path.h:19-38, include/vg/stroker.h:11-70)
