@@ -45,3 +45,15 @@ show("ATAN", A)
 # asin(x) = x + x^3 * R(x^2), |x| <= 0.5
 R = fit(lambda z: (np.arcsin(np.sqrt(z)) - np.sqrt(z)) / np.sqrt(z) ** 3, LO, 0.25 * 1.02, 4)
 show("ASIN", R)
+
+# ---- round-1 revision: FMA-evaluated variants (every step is one IEEE fma, identical on CPU
+# (fmaf) and GPU (__fmaf_rn)).  atan: one odd polynomial over the whole [0,1] octant so that
+# atan2 needs a single division and no branch.
+A1 = fit(lambda z: (np.arctan(np.sqrt(z)) - np.sqrt(z)) / np.sqrt(z) ** 3, LO, 1.0, 8, n=20000)
+show("ATAN01", A1)
+t = np.linspace(0, 1, 2000001)
+z = t * t
+q = np.zeros_like(t)
+for c in A1[::-1].astype(np.float64):
+    q = q * z + c
+print("   atan01 max abs err (float64 eval):", np.max(np.abs(t + t ** 3 * q - np.arctan(t))))

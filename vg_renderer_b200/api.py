@@ -23,7 +23,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 
 
 def lib_path():
-    return os.path.join(_HERE, "lib", "libvgb200.so")
+    # VGB_LIB selects another build of the same library (tuning variants under lib/variants/)
+    return os.environ.get("VGB_LIB") or os.path.join(_HERE, "lib", "libvgb200.so")
 
 
 class VgbError(RuntimeError):

@@ -39,9 +39,21 @@ namespace vgb
 		}                                                                                     \
 	} while (0)
 
-static constexpr uint32_t PPB = 128;          /* pieces per block == threads per block        */
-static constexpr uint32_t CV = 2048;          /* staged vertices per round                    */
-static constexpr uint32_t CI_BYTES = 18432;   /* staged index bytes per round                 */
+#ifndef VGB_PPB
+#define VGB_PPB 128
+#endif
+#ifndef VGB_CV
+#define VGB_CV 1536
+#endif
+#ifndef VGB_CI_BYTES
+#define VGB_CI_BYTES 13312
+#endif
+#ifndef VGB_EMIT_MIN_BLOCKS
+#define VGB_EMIT_MIN_BLOCKS 6
+#endif
+static constexpr uint32_t PPB = VGB_PPB;           /* pieces per block == threads per block   */
+static constexpr uint32_t CV = VGB_CV;             /* staged vertices per round               */
+static constexpr uint32_t CI_BYTES = VGB_CI_BYTES; /* staged index bytes per round            */
 
 /* =========================================================================================
  * scans
@@ -67,6 +79,17 @@ template<> struct ScanOps<uint2>
 	{
 		return make_ulonglong2(__shfl_up_sync(0xffffffffu, a.x, d), __shfl_up_sync(0xffffffffu, a.y, d));
 	}
+};
+
+/* in-block variant: sums of one block fit 32 bits */
+struct ScanOpsU2
+{
+	typedef uint2 In;
+	typedef uint2 Acc;
+	__device__ static Acc zero() { return make_uint2(0u, 0u); }
+	__device__ static Acc cvt(In a) { return a; }
+	__device__ static Acc add(Acc a, Acc b) { return make_uint2(a.x + b.x, a.y + b.y); }
+	__device__ static Acc shflUp(Acc a, int d) { return make_uint2(__shfl_up_sync(0xffffffffu, a.x, d), __shfl_up_sync(0xffffffffu, a.y, d)); }
 };
 
 static constexpr uint32_t SCAN_THREADS = 256;
@@ -247,28 +270,54 @@ __global__ void k_job_pieces(const uint32_t* __restrict__ jobSub, const uint32_t
 	jobPieces[j] = pieceCount(draws[jobDraw[j]].ocj & 0xFF, subNum[jobSub[j]]);
 }
 
-__global__ void k_block_first_job(const uint32_t* __restrict__ pieceStart, uint32_t numJobs, uint32_t* __restrict__ blockFirstJob)
+/* per job: the 48-byte record the piece kernels read, and the job id of each of its pieces.
+ * One warp handles 32 jobs; for every job of the warp all 32 lanes write its piece range, so the
+ * pieceJob stores are coalesced whatever the job lengths are. */
+__global__ void __launch_bounds__(256) k_job_prep(const uint32_t* __restrict__ jobSub, const uint32_t* __restrict__ jobDraw, uint32_t numJobs,
+                                                  const uint32_t* __restrict__ subFirst, const uint32_t* __restrict__ subNum,
+                                                  const uint8_t* __restrict__ subClosed, const DrawDerived* __restrict__ dd,
+                                                  const uint32_t* __restrict__ pieceStart, JobRec* __restrict__ jobRec,
+                                                  uint32_t* __restrict__ pieceJob)
 {
 	const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
-	if (j >= numJobs) return;
-	const uint32_t s = pieceStart[j], e = pieceStart[j + 1];
-	if (e == s) return;
-	for (uint32_t b = (s + PPB - 1) / PPB; b * PPB < e; ++b) {
-		blockFirstJob[b] = j;
+	const uint32_t lane = threadIdx.x & 31;
+	uint32_t ps = 0, pe = 0;
+	if (j < numJobs) {
+		const uint32_t sp = jobSub[j];
+		const DrawDerived d = dd[jobDraw[j]];
+		JobRec r;
+		r.first = subFirst[sp];
+		r.N = subNum[sp];
+		const uint32_t op = d.ocj & 0xFF, cap = (d.ocj >> 8) & 0xFF, join = (d.ocj >> 16) & 0xFF;
+		r.flags = (uint32_t)subClosed[sp] | (op << 8) | (cap << 16) | (join << 24);
+		ps = pieceStart[j];
+		pe = pieceStart[j + 1];
+		r.pieceStart = ps;
+		r.hsw = d.hsw;
+		r.hsw_aa = d.hsw_aa;
+		r.da = d.da;
+		r.fringe = d.fringe;
+		r.nHC = d.nHC;
+		r.color = d.color;
+		r.c0 = d.c0;
+		r.pad = 0;
+		jobRec[j] = r;
+	}
+	const uint32_t jw = j - lane; /* first job of this warp */
+	for (uint32_t l = 0; l < 32; ++l) {
+		const uint32_t s0 = __shfl_sync(0xffffffffu, ps, l);
+		const uint32_t e0 = __shfl_sync(0xffffffffu, pe, l);
+		for (uint32_t k = s0 + lane; k < e0; k += 32) {
+			pieceJob[k] = jw + l;
+		}
 	}
 }
 
 struct PieceArgs
 {
 	uint32_t numPieces, numJobs;
-	const uint32_t* pieceStart;    /* numJobs + 1 */
-	const uint32_t* blockFirstJob; /* per block   */
-	const uint32_t* jobSub;
-	const uint32_t* jobDraw;
-	const uint32_t* subFirst;
-	const uint32_t* subNum;
-	const uint8_t* subClosed;
-	const DrawDerived* dd;
+	const uint32_t* pieceJob; /* per piece */
+	const JobRec* jobRec;     /* per job   */
 	const float2* pts;
 	/* count outputs */
 	uint2* blockTotals;
@@ -283,46 +332,25 @@ struct PieceArgs
 	void* idx;
 };
 
-/* job of global piece g: window of pieceStart staged in shared memory, global search fallback */
-__device__ __forceinline__ uint32_t findJob(const PieceArgs& a, const uint32_t* sStart, uint32_t j0, uint32_t win, uint32_t g)
+__device__ __forceinline__ JobCtx loadJob(const PieceArgs& a, uint32_t j, uint32_t* pieceStart)
 {
-	/* largest w in [0, win) with sStart[w] <= g  (sStart[0] <= g by construction) */
-	if (sStart[win] > g) {
-		uint32_t lo = 0, hi = win; /* invariant: sStart[lo] <= g < sStart[hi] */
-		while (hi - lo > 1) {
-			const uint32_t mid = (lo + hi) >> 1;
-			if (sStart[mid] <= g) lo = mid; else hi = mid;
-		}
-		return j0 + lo;
-	}
-	/* window exhausted (many empty jobs in a row): search the global table */
-	uint32_t lo = j0 + win, hi = a.numJobs; /* pieceStart[lo] <= g < pieceStart[hi] */
-	while (hi - lo > 1) {
-		const uint32_t mid = (lo + hi) >> 1;
-		if (a.pieceStart[mid] <= g) lo = mid; else hi = mid;
-	}
-	return lo;
-}
-
-__device__ __forceinline__ JobCtx loadJob(const PieceArgs& a, uint32_t j)
-{
-	const uint32_t s = a.jobSub[j];
-	const DrawDerived d = a.dd[a.jobDraw[j]];
+	const uint4* r = reinterpret_cast<const uint4*>(a.jobRec + j);
+	const uint4 r0 = __ldg(r), r1 = __ldg(r + 1), r2 = __ldg(r + 2);
 	JobCtx J;
-	J.first = a.subFirst[s];
-	J.N = a.subNum[s];
-	J.closed = a.subClosed[s];
-	J.op = d.ocj & 0xFF;
-	J.cap = (d.ocj >> 8) & 0xFF;
-	J.join = (d.ocj >> 16) & 0xFF;
-	J.hsw = d.hsw;
-	J.hsw_aa = d.hsw_aa;
-	J.da = d.da;
-	J.fringe = d.fringe;
-	J.nHC = d.nHC;
-	J.color = d.color;
-	J.c0 = d.c0;
-	/* closed paths ignore the cap (dispatch forces Butt, stroker.cpp:285-303) */
+	J.first = r0.x;
+	J.N = r0.y;
+	J.closed = r0.z & 0xFF;
+	J.op = (r0.z >> 8) & 0xFF;
+	J.cap = (r0.z >> 16) & 0xFF;
+	J.join = r0.z >> 24;
+	*pieceStart = r0.w;
+	J.hsw = __uint_as_float(r1.x);
+	J.hsw_aa = __uint_as_float(r1.y);
+	J.da = __uint_as_float(r1.z);
+	J.fringe = __uint_as_float(r1.w);
+	J.nHC = r2.x;
+	J.color = r2.y;
+	J.c0 = r2.z;
 	return J;
 }
 
@@ -333,34 +361,18 @@ struct Owner
 	bool valid;
 };
 
-__device__ __forceinline__ Owner findOwner(const PieceArgs& a, uint32_t* sStart)
-{
-	const uint32_t g0 = blockIdx.x * PPB;
-	const uint32_t g = g0 + threadIdx.x;
-	const uint32_t j0 = a.blockFirstJob[blockIdx.x];
-	const uint32_t win = min(PPB + 1, a.numJobs - j0); /* entries j0 .. j0+win (inclusive) exist */
-	for (uint32_t w = threadIdx.x; w <= win; w += blockDim.x) {
-		sStart[w] = a.pieceStart[j0 + w];
-	}
-	__syncthreads();
-	Owner o;
-	o.valid = g < a.numPieces;
-	o.j = 0;
-	o.q = 0;
-	if (o.valid) {
-		o.j = findJob(a, sStart, j0, win, g);
-		o.q = g - a.pieceStart[o.j];
-	}
-	return o;
-}
-
 __global__ void __launch_bounds__(PPB) k_piece_count(PieceArgs a)
 {
-	__shared__ uint32_t sStart[PPB + 2];
-	const Owner o = findOwner(a, sStart);
+	const uint32_t g = blockIdx.x * PPB + threadIdx.x;
+	Owner o;
+	o.valid = g < a.numPieces;
+	o.j = o.valid ? a.pieceJob[g] : 0;
+	o.q = 0;
 	uint32_t vc = 0, ic = 0;
 	if (o.valid) {
-		const JobCtx J = loadJob(a, o.j);
+		uint32_t ps;
+		const JobCtx J = loadJob(a, o.j, &ps);
+		o.q = g - ps;
 		const Piece P = classify(J, o.q, a.pts);
 		vc = P.vcount;
 		ic = P.icount;
@@ -376,42 +388,59 @@ __global__ void __launch_bounds__(PPB) k_piece_count(PieceArgs a)
 			atomicAdd(&a.meshTotals[o.j].y, si);
 		}
 	}
-	ulonglong2 total;
-	blockInclusive<ScanOps<uint2>>(make_ulonglong2(vc, ic), &total);
+	uint2 total;
+	blockInclusive<ScanOpsU2>(make_uint2(vc, ic), &total);
 	if (threadIdx.x == 0) {
-		a.blockTotals[blockIdx.x] = make_uint2((uint32_t)total.x, (uint32_t)total.y);
+		a.blockTotals[blockIdx.x] = total;
 	}
 }
 
-/* stream `count` elements of shared memory (image laid out so that element e sits at
- * sbuf[e - alignedBase]) to global memory starting at element gs: 16-byte stores for the
- * aligned body, element stores for the ragged head/tail. */
+/* ---- shared -> global copy-out through the TMA engine (1-D bulk copy, no tensor map) ----------
+ * The block's output image sits in shared memory laid out so that element e is at
+ * sbuf[e - alignedBase]: 16-byte chunks of the image line up with 16-byte chunks of HBM.  The
+ * aligned body goes out with ONE cp.async.bulk per stream issued by one thread (the copy runs
+ * asynchronously in the TMA unit: no LSU instructions, no registers); only the ragged head/tail
+ * (fewer than 16 bytes each) is stored by threads. */
+__device__ __forceinline__ void fenceProxyAsync()
+{
+	asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void bulkStore(void* gdst, const void* ssrc, uint32_t bytes)
+{
+	const uint32_t saddr = (uint32_t)__cvta_generic_to_shared(ssrc);
+	asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(saddr), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulkCommit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulkWaitRead() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulkWaitAll() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+/* lanes [laneBase, laneBase+16) of the block store the ragged ends; thread 0 issues the bulk body */
 template<class T>
-__device__ __forceinline__ void copyOut(T* __restrict__ gbase, uint64_t gs, uint32_t count, const T* sbuf)
+__device__ __forceinline__ void copyOut(T* __restrict__ gbase, uint64_t gs, uint32_t count, const T* sbuf, uint32_t laneBase)
 {
 	constexpr uint32_t K = 16 / sizeof(T);
 	const uint64_t ge = gs + count;
 	const uint64_t alignedBase = gs & ~(uint64_t)(K - 1);
-	const uint64_t bodyBegin = (gs + K - 1) & ~(uint64_t)(K - 1);
-	const uint64_t bodyEnd = ge & ~(uint64_t)(K - 1);
-	if (bodyEnd > bodyBegin) {
-		const uint32_t chunks = (uint32_t)((bodyEnd - bodyBegin) / K);
-		const uint4* s4 = reinterpret_cast<const uint4*>(sbuf + (bodyBegin - alignedBase));
-		uint4* g4 = reinterpret_cast<uint4*>(gbase + bodyBegin);
-		for (uint32_t c = threadIdx.x; c < chunks; c += blockDim.x) {
-			__stcs(g4 + c, s4[c]);
-		}
-		/* head and tail (fewer than K elements each) */
-		const uint32_t head = (uint32_t)(bodyBegin - gs);
-		const uint32_t tail = (uint32_t)(ge - bodyEnd);
-		if (threadIdx.x < head) {
-			gbase[gs + threadIdx.x] = sbuf[(gs - alignedBase) + threadIdx.x];
-		} else if (threadIdx.x >= 32 && threadIdx.x - 32 < tail) {
-			gbase[bodyEnd + (threadIdx.x - 32)] = sbuf[(bodyEnd - alignedBase) + (threadIdx.x - 32)];
-		}
-	} else {
-		for (uint32_t e = threadIdx.x; e < count; e += blockDim.x) {
-			gbase[gs + e] = sbuf[(gs - alignedBase) + e];
+	uint64_t bodyBegin = (gs + K - 1) & ~(uint64_t)(K - 1);
+	uint64_t bodyEnd = ge & ~(uint64_t)(K - 1);
+	if (bodyEnd <= bodyBegin) {
+		bodyBegin = bodyEnd = ge; /* everything is ragged */
+	}
+	if (threadIdx.x == 0 && bodyEnd > bodyBegin) {
+		bulkStore(gbase + bodyBegin, sbuf + (bodyBegin - alignedBase), (uint32_t)((bodyEnd - bodyBegin) * sizeof(T)));
+	}
+	const uint32_t head = (uint32_t)((bodyBegin < ge ? bodyBegin : ge) - gs);
+	const uint32_t tail = (uint32_t)(ge - bodyEnd);
+	const uint32_t l = threadIdx.x - laneBase;
+	if (l < head) {
+		gbase[gs + l] = sbuf[(gs - alignedBase) + l];
+	} else if (l >= 8 && l - 8 < tail) {
+		gbase[bodyEnd + (l - 8)] = sbuf[(bodyEnd - alignedBase) + (l - 8)];
+	}
+	if (bodyEnd == bodyBegin && count > head) {
+		/* short unaligned range (< 2 chunks): remaining elements by a strided loop */
+		for (uint32_t e = head + l; e < count; e += 16) {
+			if (l < 16) gbase[gs + e] = sbuf[(gs - alignedBase) + e];
 		}
 	}
 }
@@ -433,11 +462,10 @@ __device__ __forceinline__ void emitPiece(const PieceArgs& a, const JobCtx& J, c
 }
 
 template<class IDX>
-__global__ void __launch_bounds__(PPB) k_piece_emit(PieceArgs a)
+__global__ void __launch_bounds__(PPB, VGB_EMIT_MIN_BLOCKS) k_piece_emit(PieceArgs a)
 {
 	constexpr uint32_t CI = CI_BYTES / sizeof(IDX);
 	constexpr uint32_t KI = 16 / sizeof(IDX);
-	__shared__ uint32_t sStart[PPB + 2];
 	__shared__ uint32_t sVl[PPB + 1];
 	__shared__ uint32_t sIl[PPB + 1];
 	__shared__ uint4 sOut4[PPB];
@@ -446,25 +474,31 @@ __global__ void __launch_bounds__(PPB) k_piece_emit(PieceArgs a)
 	__shared__ __align__(16) IDX sIdx[CI + KI];
 
 	const uint32_t t = threadIdx.x;
-	const Owner o = findOwner(a, sStart);
+	const uint32_t g = blockIdx.x * PPB + t;
+	Owner o;
+	o.valid = g < a.numPieces;
+	o.j = o.valid ? a.pieceJob[g] : 0;
+	o.q = 0;
 	JobCtx J;
 	Piece P;
 	P.kind = PK_NONE;
 	P.vcount = P.icount = 0;
 	if (o.valid) {
-		J = loadJob(a, o.j);
+		uint32_t ps;
+		J = loadJob(a, o.j, &ps);
+		o.q = g - ps;
 		P = classify(J, o.q, a.pts);
 	}
 	/* local offsets */
-	ulonglong2 total;
-	const ulonglong2 inc = blockInclusive<ScanOps<uint2>>(make_ulonglong2(P.vcount, P.icount), &total);
-	const uint32_t vl = (uint32_t)inc.x - P.vcount;
-	const uint32_t il = (uint32_t)inc.y - P.icount;
+	uint2 total;
+	const uint2 inc = blockInclusive<ScanOpsU2>(make_uint2(P.vcount, P.icount), &total);
+	const uint32_t vl = inc.x - P.vcount;
+	const uint32_t il = inc.y - P.icount;
 	sVl[t] = vl;
 	sIl[t] = il;
 	if (t == 0) {
-		sVl[PPB] = (uint32_t)total.x;
-		sIl[PPB] = (uint32_t)total.y;
+		sVl[PPB] = total.x;
+		sIl[PPB] = total.y;
 	}
 	const ulonglong2 bb = a.blockBase[blockIdx.x];
 	/* mesh-local id of this piece's first vertex, and what it hands to the next piece */
@@ -521,13 +555,26 @@ __global__ void __launch_bounds__(PPB) k_piece_emit(PieceArgs a)
 			S.base = idxBase;
 			emitPiece(a, J, P, F, prev, S);
 		}
+		fenceProxyAsync(); /* generic-proxy writes above -> visible to the async (TMA) proxy */
 		__syncthreads();
 		const uint32_t nv = sVl[tb] - v0, ni = sIl[tb] - i0;
-		copyOut<float2>(a.pos, gv, nv, sPos);
-		copyOut<uint32_t>(a.col, gv, nv, sCol);
-		copyOut<IDX>(reinterpret_cast<IDX*>(a.idx), gi, ni, sIdx);
-		__syncthreads();
+		copyOut<float2>(a.pos, gv, nv, sPos, 32);
+		copyOut<uint32_t>(a.col, gv, nv, sCol, 64);
+		copyOut<IDX>(reinterpret_cast<IDX*>(a.idx), gi, ni, sIdx, 96);
+		if (t == 0) {
+			bulkCommit();
+		}
 		ta = tb;
+		if (ta < nThreads) {
+			/* another round reuses the staging buffers: wait until the TMA has read them */
+			if (t == 0) {
+				bulkWaitRead();
+			}
+			__syncthreads();
+		}
+	}
+	if (t == 0) {
+		bulkWaitAll();
 	}
 }
 
@@ -568,7 +615,7 @@ public:
 	/* inputs */
 	DevBuf dSubRec, dCmd, dData, dScale, dTol, dXform, dDraws, dJobSub, dJobDraw;
 	/* intermediates */
-	DevBuf dSubNum, dSubFirst, dSubClosed, dPts, dDD, dJobPieces, dPieceStart, dBlockFirstJob;
+	DevBuf dSubNum, dSubFirst, dSubClosed, dPts, dDD, dJobPieces, dPieceStart, dJobRec, dPieceJob;
 	DevBuf dBlockTotals, dBlockBase, dMeshTotals, dMeshOff, dScanTmp;
 	/* outputs */
 	DevBuf dPos, dCol, dIdx;
@@ -585,7 +632,7 @@ public:
 	{
 		cudaSetDevice(dev);
 		DevBuf* all[] = {&dSubRec, &dCmd, &dData, &dScale, &dTol, &dXform, &dDraws, &dJobSub, &dJobDraw, &dSubNum, &dSubFirst,
-		                 &dSubClosed, &dPts, &dDD, &dJobPieces, &dPieceStart, &dBlockFirstJob, &dBlockTotals, &dBlockBase,
+		                 &dSubClosed, &dPts, &dDD, &dJobPieces, &dPieceStart, &dJobRec, &dPieceJob, &dBlockTotals, &dBlockBase,
 		                 &dMeshTotals, &dMeshOff, &dScanTmp, &dPos, &dCol, &dIdx};
 		for (DevBuf* b : all) b->release();
 		for (auto& e : ev) if (e) cudaEventDestroy(e);
@@ -751,22 +798,19 @@ public:
 		PieceArgs pa;
 		memset(&pa, 0, sizeof(pa));
 		if (numPieces) {
-			if (dBlockFirstJob.ensure((size_t)numBlocks * 4, err) || dBlockTotals.ensure((size_t)numBlocks * 8, err) ||
-			    dBlockBase.ensure((size_t)(numBlocks + 1) * 16, err) || dMeshTotals.ensure((size_t)numJobs * 8, err))
+			if (dJobRec.ensure((size_t)numJobs * sizeof(JobRec), err) || dPieceJob.ensure((size_t)numPieces * 4, err) ||
+			    dBlockTotals.ensure((size_t)numBlocks * 8, err) || dBlockBase.ensure((size_t)(numBlocks + 1) * 16, err) ||
+			    dMeshTotals.ensure((size_t)numJobs * 8, err))
 				return VGB_ERR_CUDA;
-			k_block_first_job<<<(numJobs + 255) / 256, 256, 0, st>>>(dPieceStart.as<uint32_t>(), numJobs, dBlockFirstJob.as<uint32_t>());
+			k_job_prep<<<(numJobs + 255) / 256, 256, 0, st>>>(dJobSub.as<uint32_t>(), dJobDraw.as<uint32_t>(), numJobs, dSubFirst.as<uint32_t>(),
+			                                                   dSubNum.as<uint32_t>(), dSubClosed.as<uint8_t>(), dDD.as<DrawDerived>(),
+			                                                   dPieceStart.as<uint32_t>(), dJobRec.as<JobRec>(), dPieceJob.as<uint32_t>());
 			++launches;
 			VGB_CUDA(cudaMemsetAsync(dMeshTotals.p, 0, (size_t)numJobs * 8, st));
 			pa.numPieces = numPieces;
 			pa.numJobs = numJobs;
-			pa.pieceStart = dPieceStart.as<uint32_t>();
-			pa.blockFirstJob = dBlockFirstJob.as<uint32_t>();
-			pa.jobSub = dJobSub.as<uint32_t>();
-			pa.jobDraw = dJobDraw.as<uint32_t>();
-			pa.subFirst = dSubFirst.as<uint32_t>();
-			pa.subNum = dSubNum.as<uint32_t>();
-			pa.subClosed = dSubClosed.as<uint8_t>();
-			pa.dd = dDD.as<DrawDerived>();
+			pa.pieceJob = dPieceJob.as<uint32_t>();
+			pa.jobRec = dJobRec.as<JobRec>();
 			pa.pts = dPts.as<float2>();
 			pa.blockTotals = dBlockTotals.as<uint2>();
 			pa.meshTotals = dMeshTotals.as<uint2>();

@@ -35,6 +35,14 @@ struct DrawDerived
 	uint32_t nHC, color, c0, ocj;
 };
 
+/* one job (mesh) as the piece kernels read it: 48 bytes, three 16-byte loads */
+struct JobRec
+{
+	uint32_t first, N, flags, pieceStart; /* flags = closed | op << 8 | cap << 16 | join << 24 */
+	float hsw, hsw_aa, da, fringe;
+	uint32_t nHC, color, c0, pad;
+};
+
 /* everything the host hands to a run (all host pointers; sizes in elements) */
 struct HostTables
 {

@@ -10,10 +10,12 @@
  * vendored nor pinned, and these functions feed INTEGER decisions (ceil(pi/da),
  * (uint32)(dAngle/da)) that set vertex counts and therefore index buffers.  This build
  * therefore defines the functions itself, using only IEEE-754 binary32 add/sub/mul/div/sqrt
- * in a fixed order, so CPU oracle and GPU kernels agree to the last bit by construction.
+ * plus explicit fma in a fixed order, so CPU oracle and GPU kernels agree to the last bit by construction.
  * Coefficients: tools/fit_math.py (near-minimax fits; accuracy checked in tests/test_math.py).
  *
- * C99 / C++ / CUDA compatible.  No FMA anywhere: every product and sum is separately rounded.
+ * C99 / C++ / CUDA compatible.  The only fused operations are the EXPLICIT fma steps of the
+ * polynomial kernels below (IEEE fused multiply-add: exactly defined, so still reproducible);
+ * nothing is ever contracted implicitly.
  */
 #ifndef VGB_MATH_H
 #define VGB_MATH_H
@@ -33,14 +35,17 @@
 #define VGB_SUB(a, b) __fsub_rn((a), (b))
 #define VGB_DIV(a, b) __fdiv_rn((a), (b))
 #define VGB_SQRT(a) __fsqrt_rn((a))
+#define VGB_FMA(a, b, c) __fmaf_rn((a), (b), (c))
 #else
 /* host: plain operators; translation units including this header must be built with
- * -ffp-contract=off (and no -ffast-math) so nothing is fused or re-associated. */
+ * -ffp-contract=off (and no -ffast-math) so nothing is fused or re-associated behind our back.
+ * fmaf() is the exactly-rounded fused multiply-add of C99 (one vfmadd with -mfma). */
 #define VGB_MUL(a, b) ((a) * (b))
 #define VGB_ADD(a, b) ((a) + (b))
 #define VGB_SUB(a, b) ((a) - (b))
 #define VGB_DIV(a, b) ((a) / (b))
 #define VGB_SQRT(a) sqrtf((a))
+#define VGB_FMA(a, b, c) fmaf((a), (b), (c))
 #endif
 
 #define VGB_PI 3.1415926535897932384626433832795f
@@ -56,32 +61,34 @@ VGB_HD float vgb_ceil(float a) { return ceilf(a); }
 VGB_HD float vgb_floor(float a) { return floorf(a); }
 VGB_HD uint32_t vgb_umax(uint32_t a, uint32_t b) { return a > b ? a : b; }
 
-/* ---- sin / cos --------------------------------------------------------------------- */
+/* ---- sin / cos ---------------------------------------------------------------------
+ * Polynomials are Horner chains of explicit fused multiply-adds: each step is ONE IEEE-754
+ * fma, so the value is a pure function of the inputs on any conforming machine. */
 /* |r| <= pi/4 kernels */
 VGB_HD float vgb__sin_k(float r)
 {
 	const float z = VGB_MUL(r, r);
-	float p = VGB_ADD(VGB_MUL(-0x1.9aaefcp-13f, z), 0x1.110bf6p-7f);
-	p = VGB_ADD(VGB_MUL(p, z), -0x1.555552p-3f);
-	return VGB_ADD(r, VGB_MUL(VGB_MUL(r, z), p));
+	float p = VGB_FMA(-0x1.9aaefcp-13f, z, 0x1.110bf6p-7f);
+	p = VGB_FMA(p, z, -0x1.555552p-3f);
+	return VGB_FMA(VGB_MUL(r, z), p, r);
 }
 
 VGB_HD float vgb__cos_k(float r)
 {
 	const float z = VGB_MUL(r, r);
-	float p = VGB_ADD(VGB_MUL(0x1.9bc328p-16f, z), -0x1.6c12aap-10f);
-	p = VGB_ADD(VGB_MUL(p, z), 0x1.555554p-5f);
-	return VGB_ADD(VGB_SUB(1.0f, VGB_MUL(0.5f, z)), VGB_MUL(VGB_MUL(z, z), p));
+	float p = VGB_FMA(0x1.9bc328p-16f, z, -0x1.6c12aap-10f);
+	p = VGB_FMA(p, z, 0x1.555554p-5f);
+	return VGB_FMA(VGB_MUL(z, z), p, VGB_FMA(-0.5f, z, 1.0f));
 }
 
-/* Cody-Waite reduction by pi/2 = C1 + C2 + C3 (C1, C2 have trailing zero bits so k*C is
- * exact for |k| < 2^13); returns the quadrant in *q. Accurate for |x| up to a few thousand. */
+/* Cody-Waite reduction by pi/2 = C1 + C2 + C3, three fused steps; quadrant in *q.
+ * Accurate for |x| up to a few thousand (the path only produces |x| < 10). */
 VGB_HD float vgb__reduce(float x, int* q)
 {
 	const float kf = rintf(VGB_MUL(x, 0.63661977236758134308f));
-	float r = VGB_SUB(x, VGB_MUL(kf, 1.5703125f));
-	r = VGB_SUB(r, VGB_MUL(kf, 4.837512969970703125e-4f));
-	r = VGB_SUB(r, VGB_MUL(kf, 7.54978995489188216e-8f));
+	float r = VGB_FMA(kf, -1.5703125f, x);
+	r = VGB_FMA(kf, -4.837512969970703125e-4f, r);
+	r = VGB_FMA(kf, -7.54978995489188216e-8f, r);
 	*q = (int)kf;
 	return r;
 }
@@ -117,16 +124,21 @@ VGB_HD void vgb_sincos(float x, float* s, float* c)
 
 VGB_HD float vgb_tan(float x) { return VGB_DIV(vgb_sin(x), vgb_cos(x)); }
 
-/* ---- atan2 ------------------------------------------------------------------------- */
-/* atan(t) for |t| <= tan(pi/8) */
-VGB_HD float vgb__atan_k(float t)
+/* ---- atan2 -------------------------------------------------------------------------
+ * atan(t) on the whole first octant t in [0,1] with one odd polynomial (|err| < 2e-8), so
+ * atan2 costs a single division and no data-dependent branch. */
+VGB_HD float vgb__atan01(float t)
 {
 	const float z = VGB_MUL(t, t);
-	float p = VGB_ADD(VGB_MUL(-0x1.06a9dep-4f, z), 0x1.b791a6p-4f);
-	p = VGB_ADD(VGB_MUL(p, z), -0x1.241a1ep-3f);
-	p = VGB_ADD(VGB_MUL(p, z), 0x1.9996fep-3f);
-	p = VGB_ADD(VGB_MUL(p, z), -0x1.555554p-2f);
-	return VGB_ADD(t, VGB_MUL(VGB_MUL(t, z), p));
+	float p = VGB_FMA(-0x1.404d1cp-9f, z, 0x1.c21b1cp-7f);
+	p = VGB_FMA(p, z, -0x1.28ec28p-5f);
+	p = VGB_FMA(p, z, 0x1.01503p-4f);
+	p = VGB_FMA(p, z, -0x1.633408p-4f);
+	p = VGB_FMA(p, z, 0x1.c419eep-4f);
+	p = VGB_FMA(p, z, -0x1.246f5cp-3f);
+	p = VGB_FMA(p, z, 0x1.99985ap-3f);
+	p = VGB_FMA(p, z, -0x1.555554p-2f);
+	return VGB_FMA(VGB_MUL(t, z), p, t);
 }
 
 /* atan2(y, x) in (-pi, pi]; atan2(0, 0) is defined as 0 regardless of zero signs. */
@@ -139,14 +151,7 @@ VGB_HD float vgb_atan2(float y, float x)
 	if (mx == 0.0f) {
 		return 0.0f;
 	}
-	const float t = VGB_DIV(mn, mx); /* [0, 1] */
-	float a;
-	if (t > 0.41421356237309504880f) {
-		const float u = VGB_DIV(VGB_SUB(t, 1.0f), VGB_ADD(t, 1.0f));
-		a = VGB_ADD(0.78539816339744830962f, vgb__atan_k(u));
-	} else {
-		a = vgb__atan_k(t);
-	}
+	float a = vgb__atan01(VGB_DIV(mn, mx));
 	if (ay > ax) {
 		a = VGB_SUB(VGB_PI_HALF, a);
 	}
@@ -161,11 +166,11 @@ VGB_HD float vgb_atan2(float y, float x)
 VGB_HD float vgb__asin_k(float x)
 {
 	const float z = VGB_MUL(x, x);
-	float p = VGB_ADD(VGB_MUL(0x1.3cffcp-5f, z), 0x1.ae779ep-6f);
-	p = VGB_ADD(VGB_MUL(p, z), 0x1.70fb0ap-5f);
-	p = VGB_ADD(VGB_MUL(p, z), 0x1.33253ep-4f);
-	p = VGB_ADD(VGB_MUL(p, z), 0x1.55556p-3f);
-	return VGB_ADD(x, VGB_MUL(VGB_MUL(x, z), p));
+	float p = VGB_FMA(0x1.3cffcp-5f, z, 0x1.ae779ep-6f);
+	p = VGB_FMA(p, z, 0x1.70fb0ap-5f);
+	p = VGB_FMA(p, z, 0x1.33253ep-4f);
+	p = VGB_FMA(p, z, 0x1.55556p-3f);
+	return VGB_FMA(VGB_MUL(x, z), p, x);
 }
 
 /* acos(x), x clamped to [-1, 1] */

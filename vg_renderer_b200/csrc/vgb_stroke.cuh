@@ -237,6 +237,14 @@ struct Sink
 		pos[k] = make_float2(x, y);
 		col[k] = c;
 	}
+	/* two consecutive vertices starting at an EVEN k: one 128-bit and one 64-bit store.  Every AA
+	 * piece has an even vertex count, so every piece starts at an even vertex of its mesh and the
+	 * staging image keeps that parity. */
+	__device__ __forceinline__ void VP(uint32_t k, float x0, float y0, uint32_t c0_, float x1, float y1, uint32_t c1_) const
+	{
+		*reinterpret_cast<float4*>(pos + k) = make_float4(x0, y0, x1, y1);
+		*reinterpret_cast<uint2*>(col + k) = make_uint2(c0_, c1_);
+	}
 	__device__ __forceinline__ void I(uint32_t k, uint32_t v) const { idx[k] = (IDX)(v + base); }
 	__device__ __forceinline__ void tri(uint32_t k, uint32_t a, uint32_t b, uint32_t c) const
 	{
@@ -271,8 +279,7 @@ __device__ __forceinline__ void emitCapStartAA(const JobCtx& J, const Piece& P, 
 			const float a = startAngle + (float)i * VGB_PI / (float)(n - 1);
 			float sa, ca;
 			vgb_sincos(a, &sa, &ca);
-			S.V(2 * i, p0.x + ca * hsw, p0.y + sa * hsw, J.color);
-			S.V(2 * i + 1, p0.x + ca * hsw_aa, p0.y + sa * hsw_aa, J.c0);
+			S.VP(2 * i, p0.x + ca * hsw, p0.y + sa * hsw, J.color, p0.x + ca * hsw_aa, p0.y + sa * hsw_aa, J.c0);
 		}
 		uint32_t k = 0;
 		for (uint32_t i = 0; i < n - 2; ++i, k += 3) {
@@ -290,18 +297,14 @@ __device__ __forceinline__ void emitCapStartAA(const JobCtx& J, const Piece& P, 
 	if (J.cap == VGB_CAP_BUTT) {
 		/* stroker.cpp:1422-1447 */
 		const float dax = d.x * J.fringe, day = d.y * J.fringe;
-		S.V(0, p0.x + (lax - dax), p0.y + (lay - day), J.c0);
-		S.V(1, p0.x + lx, p0.y + ly, J.color);
-		S.V(2, p0.x - lx, p0.y - ly, J.color);
-		S.V(3, p0.x - (lax + dax), p0.y - (lay + day), J.c0);
+		S.VP(0, p0.x + (lax - dax), p0.y + (lay - day), J.c0, p0.x + lx, p0.y + ly, J.color);
+		S.VP(2, p0.x - lx, p0.y - ly, J.color, p0.x - (lax + dax), p0.y - (lay + day), J.c0);
 	} else {
 		/* square, stroker.cpp:1448-1474 */
 		const float dx = d.x * hsw, dy = d.y * hsw;
 		const float dax = d.x * hsw_aa, day = d.y * hsw_aa;
-		S.V(0, p0.x + (lax - dax), p0.y + (lay - day), J.c0);
-		S.V(1, p0.x + (lx - dx), p0.y + (ly - dy), J.color);
-		S.V(2, p0.x - (lx + dx), p0.y - (ly + dy), J.color);
-		S.V(3, p0.x - (lax + dax), p0.y - (lay + day), J.c0);
+		S.VP(0, p0.x + (lax - dax), p0.y + (lay - day), J.c0, p0.x + (lx - dx), p0.y + (ly - dy), J.color);
+		S.VP(2, p0.x - (lx + dx), p0.y - (ly + dy), J.color, p0.x - (lax + dax), p0.y - (lay + day), J.c0);
 	}
 	S.tri(0, F, F + 2, F + 1);
 	S.tri(3, F, F + 3, F + 2);
@@ -321,8 +324,7 @@ __device__ __forceinline__ void emitCapEndAA(const JobCtx& J, const Piece& P, ui
 			const float a = startAngle - (float)i * VGB_PI / (float)(n - 1);
 			float sa, ca;
 			vgb_sincos(a, &sa, &ca);
-			S.V(2 * i, p1.x + ca * hsw, p1.y + sa * hsw, J.color);
-			S.V(2 * i + 1, p1.x + ca * hsw_aa, p1.y + sa * hsw_aa, J.c0);
+			S.VP(2 * i, p1.x + ca * hsw, p1.y + sa * hsw, J.color, p1.x + ca * hsw_aa, p1.y + sa * hsw_aa, J.c0);
 		}
 		const uint32_t e = C + 2 * (n - 1);
 		S.connect(0, prev, make_uint4(C + 1, C, e, e + 1));
@@ -343,18 +345,14 @@ __device__ __forceinline__ void emitCapEndAA(const JobCtx& J, const Piece& P, ui
 	if (J.cap == VGB_CAP_BUTT) {
 		/* stroker.cpp:1858-1886 */
 		const float dax = d.x * J.fringe, day = d.y * J.fringe;
-		S.V(0, p1.x + (lax + dax), p1.y + (lay + day), J.c0);
-		S.V(1, p1.x + lx, p1.y + ly, J.color);
-		S.V(2, p1.x - lx, p1.y - ly, J.color);
-		S.V(3, p1.x - (lax - dax), p1.y - (lay - day), J.c0);
+		S.VP(0, p1.x + (lax + dax), p1.y + (lay + day), J.c0, p1.x + lx, p1.y + ly, J.color);
+		S.VP(2, p1.x - lx, p1.y - ly, J.color, p1.x - (lax - dax), p1.y - (lay - day), J.c0);
 	} else {
 		/* square, stroker.cpp:1887-1916 */
 		const float dx = d.x * hsw, dy = d.y * hsw;
 		const float dax = d.x * hsw_aa, day = d.y * hsw_aa;
-		S.V(0, p1.x + (lax + dax), p1.y + (lay + day), J.c0);
-		S.V(1, p1.x + (lx + dx), p1.y + (ly + dy), J.color);
-		S.V(2, p1.x - (lx - dx), p1.y - (ly - dy), J.color);
-		S.V(3, p1.x - (lax - dax), p1.y - (lay - day), J.c0);
+		S.VP(0, p1.x + (lax + dax), p1.y + (lay + day), J.c0, p1.x + (lx + dx), p1.y + (ly + dy), J.color);
+		S.VP(2, p1.x - (lx - dx), p1.y - (ly - dy), J.color, p1.x - (lax - dax), p1.y - (lay - day), J.c0);
 	}
 	S.connect(0, prev, make_uint4(C, C + 1, C + 2, C + 3));
 	S.tri(18, C, C + 1, C + 2);
@@ -374,10 +372,8 @@ __device__ __forceinline__ void emitJoinAA(const JobCtx& J, const Piece& P, uint
 	const float vx = vs.x * hsw, vy = vs.y * hsw;
 	uint32_t k = 0;
 	if (J.join == VGB_JOIN_MITER) {
-		S.V(0, p1.x + vax, p1.y + vay, J.c0);
-		S.V(1, p1.x + vx, p1.y + vy, J.color);
-		S.V(2, p1.x - vx, p1.y - vy, J.color);
-		S.V(3, p1.x - vax, p1.y - vay, J.c0);
+		S.VP(0, p1.x + vax, p1.y + vay, J.c0, p1.x + vx, p1.y + vy, J.color);
+		S.VP(2, p1.x - vx, p1.y - vy, J.color, p1.x - vax, p1.y - vay, J.c0);
 		if (P.flags & PF_HAS_PREV) {
 			S.connect(0, prev, joinIn4(left, F));
 			k = 18;
@@ -387,8 +383,7 @@ __device__ __forceinline__ void emitJoinAA(const JobCtx& J, const Piece& P, uint
 		const float2 d01 = P.d01, d12 = P.d12;
 		const float2 s01 = left ? f2(d01.y, -d01.x) : f2(-d01.y, d01.x);
 		const float2 s12 = left ? f2(d12.y, -d12.x) : f2(-d12.y, d12.x);
-		S.V(0, p1.x + vax, p1.y + vay, J.c0);
-		S.V(1, p1.x + vx, p1.y + vy, J.color);
+		S.VP(0, p1.x + vax, p1.y + vay, J.c0, p1.x + vx, p1.y + vy, J.color);
 		/* first arc vertex */
 		{
 			float ax = p1.x + s01.x * hsw, ay = p1.y + s01.y * hsw;
@@ -398,16 +393,14 @@ __device__ __forceinline__ void emitJoinAA(const JobCtx& J, const Piece& P, uint
 				ax = ax - d01.x * t;
 				ay = ay - d01.y * t;
 			}
-			S.V(2, ax, ay, J.color);
-			S.V(3, p1.x + s01.x * hsw_aa, p1.y + s01.y * hsw_aa, J.c0);
+			S.VP(2, ax, ay, J.color, p1.x + s01.x * hsw_aa, p1.y + s01.y * hsw_aa, J.c0);
 		}
 		/* middle arc vertices */
 		for (uint32_t i = 1; i < n; ++i) {
 			const float a = P.a01 + (float)i * P.arcDa;
 			float sa, ca;
 			vgb_sincos(a, &sa, &ca);
-			S.V(2 + 2 * i, p1.x + ca * hsw, p1.y + sa * hsw, J.color);
-			S.V(3 + 2 * i, p1.x + ca * hsw_aa, p1.y + sa * hsw_aa, J.c0);
+			S.VP(2 + 2 * i, p1.x + ca * hsw, p1.y + sa * hsw, J.color, p1.x + ca * hsw_aa, p1.y + sa * hsw_aa, J.c0);
 		}
 		/* last arc vertex */
 		{
@@ -418,8 +411,7 @@ __device__ __forceinline__ void emitJoinAA(const JobCtx& J, const Piece& P, uint
 				ax = ax + d12.x * t;
 				ay = ay + d12.y * t;
 			}
-			S.V(2 + 2 * n, ax, ay, J.color);
-			S.V(3 + 2 * n, p1.x + s12.x * hsw_aa, p1.y + s12.y * hsw_aa, J.c0);
+			S.VP(2 + 2 * n, ax, ay, J.color, p1.x + s12.x * hsw_aa, p1.y + s12.y * hsw_aa, J.c0);
 		}
 		if (P.flags & PF_HAS_PREV) {
 			S.connect(0, prev, joinIn4(left, F));
@@ -474,8 +466,7 @@ __device__ __forceinline__ void emitFillVtx(const JobCtx& J, const Piece& P, con
 	const float aa = J.fringe * 0.5f * vgb_sign(cross);
 	const float2 e = extrusion(P.d01, P.d12);
 	const float ex = e.x * aa, ey = e.y * aa;
-	S.V(0, P.p.x + ex, P.p.y + ey, J.color);
-	S.V(1, P.p.x - ex, P.p.y - ey, J.c0);
+	S.VP(0, P.p.x + ex, P.p.y + ey, J.color, P.p.x - ex, P.p.y - ey, J.c0);
 	const uint32_t f = 2 * P.li;
 	if (P.li + 1 < J.N) {
 		S.tri(0, f, f + 1, f + 3);
