@@ -49,7 +49,7 @@ namespace vgb
 #define VGB_CI_BYTES 13312
 #endif
 #ifndef VGB_EMIT_MIN_BLOCKS
-#define VGB_EMIT_MIN_BLOCKS 6
+#define VGB_EMIT_MIN_BLOCKS 5
 #endif
 static constexpr uint32_t PPB = VGB_PPB;           /* pieces per block == threads per block   */
 static constexpr uint32_t CV = VGB_CV;             /* staged vertices per round               */
@@ -97,7 +97,7 @@ static constexpr uint32_t SCAN_ITEMS = 4;
 static constexpr uint32_t SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
 
 /* inclusive block scan of one value per thread; returns inclusive value, *total = block sum */
-template<class O>
+template<class O, bool TRAILING_SYNC = true>
 __device__ __forceinline__ typename O::Acc blockInclusive(typename O::Acc v, typename O::Acc* total)
 {
 	typedef typename O::Acc Acc;
@@ -122,7 +122,9 @@ __device__ __forceinline__ typename O::Acc blockInclusive(typename O::Acc v, typ
 	__syncthreads();
 	if (warp > 0) v = O::add(v, warpSum[warp - 1]);
 	*total = warpSum[nw - 1];
-	__syncthreads();
+	if (TRAILING_SYNC) {
+		__syncthreads(); /* warpSum may be reused by a following call */
+	}
 	return v;
 }
 
@@ -321,7 +323,8 @@ struct PieceArgs
 	const float2* pts;
 	/* count outputs */
 	uint2* blockTotals;
-	uint2* meshTotals; /* zeroed before the count kernel */
+	uint2* meshTotals;    /* zeroed before the count kernel */
+	uint32_t* blockTail;  /* packTail() of each block's last piece (the next block's hand-over) */
 	/* emit inputs */
 	const ulonglong2* blockBase; /* numBlocks + 1 */
 	const ulonglong2* meshOff;   /* numJobs + 1   */
@@ -361,6 +364,7 @@ struct Owner
 	bool valid;
 };
 
+template<uint32_t OPS>
 __global__ void __launch_bounds__(PPB) k_piece_count(PieceArgs a)
 {
 	const uint32_t g = blockIdx.x * PPB + threadIdx.x;
@@ -373,9 +377,12 @@ __global__ void __launch_bounds__(PPB) k_piece_count(PieceArgs a)
 		uint32_t ps;
 		const JobCtx J = loadJob(a, o.j, &ps);
 		o.q = g - ps;
-		const Piece P = classify(J, o.q, a.pts);
+		const Piece P = classify<OPS>(J, o.q, a.pts);
 		vc = P.vcount;
 		ic = P.icount;
+		if (threadIdx.x == PPB - 1) {
+			a.blockTail[blockIdx.x] = packTail(P);
+		}
 	}
 	/* per-mesh totals: lanes of one warp owning the same job reduce first, one atomic per run */
 	{
@@ -389,7 +396,7 @@ __global__ void __launch_bounds__(PPB) k_piece_count(PieceArgs a)
 		}
 	}
 	uint2 total;
-	blockInclusive<ScanOpsU2>(make_uint2(vc, ic), &total);
+	blockInclusive<ScanOpsU2, false>(make_uint2(vc, ic), &total);
 	if (threadIdx.x == 0) {
 		a.blockTotals[blockIdx.x] = total;
 	}
@@ -437,44 +444,64 @@ __device__ __forceinline__ void copyOut(T* __restrict__ gbase, uint64_t gs, uint
 	} else if (l >= 8 && l - 8 < tail) {
 		gbase[bodyEnd + (l - 8)] = sbuf[(bodyEnd - alignedBase) + (l - 8)];
 	}
-	if (bodyEnd == bodyBegin && count > head) {
-		/* short unaligned range (< 2 chunks): remaining elements by a strided loop */
-		for (uint32_t e = head + l; e < count; e += 16) {
-			if (l < 16) gbase[gs + e] = sbuf[(gs - alignedBase) + e];
-		}
-	}
 }
 
-template<class IDX>
+__device__ __forceinline__ CapRec makeCapRec(const JobCtx& J, const Piece& P, uint32_t F, uint4 prev, uint32_t vl, uint32_t il, uint32_t base, uint32_t owner)
+{
+	CapRec R;
+	R.p = P.p;
+	R.d = P.d01;
+	R.hsw = J.hsw;
+	R.hsw_aa = J.hsw_aa;
+	R.fringe = J.fringe;
+	R.color = J.color;
+	R.c0 = J.c0;
+	R.n = P.n;
+	R.F = F;
+	R.prev = prev;
+	R.vl = vl;
+	R.il = il;
+	R.base = base;
+	R.info = owner | (J.cap << 16) | ((P.kind == PK_CAP_END ? 1u : 0u) << 24);
+	return R;
+}
+
+static constexpr uint32_t CAPMAX = 32; /* caps per block handed to warp 0; the rest are emitted in place */
+
+template<class IDX, uint32_t OPS>
 __device__ __forceinline__ void emitPiece(const PieceArgs& a, const JobCtx& J, const Piece& P, uint32_t F, uint4 prev, const Sink<IDX>& S)
 {
-	switch (P.kind) {
-	case PK_CAP_START: emitCapStartAA(J, P, F, S); break;
-	case PK_CAP_END: emitCapEndAA(J, P, F, prev, S); break;
-	case PK_JOIN: {
+	if ((OPS & OPS_STROKE_AA) && P.kind == PK_JOIN) {
 		const bool firstLeft = (P.flags & PF_CLOSING) ? firstJoinLeft(J, a.pts) : false;
 		emitJoinAA(J, P, F, prev, firstLeft, S);
-	} break;
-	case PK_FILL_FAN: emitFillFan(P, S); break;
-	case PK_FILL_VTX: emitFillVtx(J, P, a.pts, S); break;
-	default: break;
+	} else if ((OPS & OPS_STROKE_AA) && (P.kind == PK_CAP_START || P.kind == PK_CAP_END)) {
+		emitCapAA(makeCapRec(J, P, F, prev, 0, 0, S.base, 0), S);
+	} else if ((OPS & OPS_FILL_AA) && P.kind == PK_FILL_VTX) {
+		emitFillVtx(J, P, a.pts, S);
+	} else if ((OPS & OPS_FILL_AA) && P.kind == PK_FILL_FAN) {
+		emitFillFan(P, S);
 	}
 }
 
-template<class IDX>
+template<class IDX, uint32_t OPS>
 __global__ void __launch_bounds__(PPB, VGB_EMIT_MIN_BLOCKS) k_piece_emit(PieceArgs a)
 {
 	constexpr uint32_t CI = CI_BYTES / sizeof(IDX);
 	constexpr uint32_t KI = 16 / sizeof(IDX);
 	__shared__ uint32_t sVl[PPB + 1];
 	__shared__ uint32_t sIl[PPB + 1];
-	__shared__ uint4 sOut4[PPB];
+	__shared__ uint32_t sTail[PPB];
+	__shared__ CapRec sCap[CAPMAX];
+	__shared__ uint32_t sCapCount;
 	__shared__ __align__(16) float2 sPos[CV + 2];
 	__shared__ __align__(16) uint32_t sCol[CV + 4];
 	__shared__ __align__(16) IDX sIdx[CI + KI];
 
 	const uint32_t t = threadIdx.x;
 	const uint32_t g = blockIdx.x * PPB + t;
+	if (t == 0) {
+		sCapCount = 0;
+	}
 	Owner o;
 	o.valid = g < a.numPieces;
 	o.j = o.valid ? a.pieceJob[g] : 0;
@@ -487,11 +514,14 @@ __global__ void __launch_bounds__(PPB, VGB_EMIT_MIN_BLOCKS) k_piece_emit(PieceAr
 		uint32_t ps;
 		J = loadJob(a, o.j, &ps);
 		o.q = g - ps;
-		P = classify(J, o.q, a.pts);
+		P = classify<OPS>(J, o.q, a.pts);
+		sTail[t] = packTail(P);
 	}
-	/* local offsets */
+	/* hand-over of the previous block's last piece (written by the count kernel) */
+	const uint32_t tail0 = (t == 0 && blockIdx.x > 0) ? a.blockTail[blockIdx.x - 1] : 0u;
+	/* local offsets (the scan's two barriers also publish sTail) */
 	uint2 total;
-	const uint2 inc = blockInclusive<ScanOpsU2>(make_uint2(P.vcount, P.icount), &total);
+	const uint2 inc = blockInclusive<ScanOpsU2, false>(make_uint2(P.vcount, P.icount), &total);
 	const uint32_t vl = inc.x - P.vcount;
 	const uint32_t il = inc.y - P.icount;
 	sVl[t] = vl;
@@ -501,26 +531,29 @@ __global__ void __launch_bounds__(PPB, VGB_EMIT_MIN_BLOCKS) k_piece_emit(PieceAr
 		sIl[PPB] = total.y;
 	}
 	const ulonglong2 bb = a.blockBase[blockIdx.x];
-	/* mesh-local id of this piece's first vertex, and what it hands to the next piece */
+	/* mesh-local id of this piece's first vertex; what the previous piece handed over */
 	uint32_t F = 0;
 	ulonglong2 mo = make_ulonglong2(0, 0);
+	uint4 prev = make_uint4(0, 0, 0, 0);
 	if (o.valid) {
 		mo = a.meshOff[o.j];
 		F = (uint32_t)(bb.x + vl - mo.x);
-		sOut4[t] = pieceOut4(J, P, F);
-	}
-	__syncthreads();
-	uint4 prev = make_uint4(0, 0, 0, 0);
-	if (o.valid && (P.flags & PF_HAS_PREV)) {
-		if (t > 0) {
-			prev = sOut4[t - 1]; /* piece q-1 of the same job is owned by thread t-1 */
-		} else {
-			/* halo: the previous piece belongs to the previous block; recompute it */
-			const Piece H = classify(J, o.q - 1, a.pts);
-			prev = pieceOut4(J, H, F - H.vcount);
+		if (P.flags & PF_HAS_PREV) {
+			/* piece q-1 of the same job is owned by thread t-1 (or by the previous block's last thread) */
+			prev = out4FromTail(J.cap, J.join, t > 0 ? sTail[t - 1] : tail0, F);
 		}
 	}
 	const uint32_t idxBase = sizeof(IDX) == 2 ? 0u : (uint32_t)(mo.x + a.vertexBase);
+	/* caps (a few per block) are detached from their owners and emitted by the low lanes of warp 0:
+	 * every other warp then runs join code only, instead of join + start-cap + end-cap code */
+	bool deferred = false;
+	if (o.valid && (P.kind == PK_CAP_START || P.kind == PK_CAP_END)) {
+		const uint32_t slot = atomicAdd(&sCapCount, 1u);
+		if (slot < CAPMAX) {
+			sCap[slot] = makeCapRec(J, P, F, prev, vl, il, idxBase, t);
+			deferred = true;
+		}
+	}
 
 	/* rounds: as many consecutive pieces as fit the staging buffers */
 	const uint32_t nThreads = min(PPB, a.numPieces - blockIdx.x * PPB);
@@ -539,7 +572,7 @@ __global__ void __launch_bounds__(PPB, VGB_EMIT_MIN_BLOCKS) k_piece_emit(PieceAr
 				S.col = a.col + gv;
 				S.idx = reinterpret_cast<IDX*>(a.idx) + gi;
 				S.base = idxBase;
-				emitPiece(a, J, P, F, prev, S);
+				emitPiece<IDX, OPS>(a, J, P, F, prev, S);
 			}
 			ta += 1;
 			__syncthreads();
@@ -547,13 +580,25 @@ __global__ void __launch_bounds__(PPB, VGB_EMIT_MIN_BLOCKS) k_piece_emit(PieceAr
 		}
 		const uint32_t tb = ta + cnt;
 		const uint32_t shV2 = (uint32_t)(gv & 1), shV4 = (uint32_t)(gv & 3), shI = (uint32_t)(gi & (KI - 1));
-		if (t >= ta && t < tb) {
+		if (t >= ta && t < tb && !deferred) {
 			Sink<IDX> S;
 			S.pos = sPos + shV2 + (vl - v0);
 			S.col = sCol + shV4 + (vl - v0);
 			S.idx = sIdx + shI + (il - i0);
 			S.base = idxBase;
-			emitPiece(a, J, P, F, prev, S);
+			emitPiece<IDX, OPS>(a, J, P, F, prev, S);
+		}
+		if (t < min(sCapCount, CAPMAX)) {
+			const CapRec R = sCap[t];
+			const uint32_t owner = R.info & 0xFFFF;
+			if (owner >= ta && owner < tb) {
+				Sink<IDX> S;
+				S.pos = sPos + shV2 + (R.vl - v0);
+				S.col = sCol + shV4 + (R.vl - v0);
+				S.idx = sIdx + shI + (R.il - i0);
+				S.base = R.base;
+				emitCapAA(R, S);
+			}
 		}
 		fenceProxyAsync(); /* generic-proxy writes above -> visible to the async (TMA) proxy */
 		__syncthreads();
@@ -574,7 +619,9 @@ __global__ void __launch_bounds__(PPB, VGB_EMIT_MIN_BLOCKS) k_piece_emit(PieceAr
 		}
 	}
 	if (t == 0) {
-		bulkWaitAll();
+		/* the CTA may retire once the TMA has READ the staging buffers; the global writes complete
+		 * asynchronously and are ordered before kernel completion */
+		bulkWaitRead();
 	}
 }
 
@@ -616,7 +663,7 @@ public:
 	DevBuf dSubRec, dCmd, dData, dScale, dTol, dXform, dDraws, dJobSub, dJobDraw;
 	/* intermediates */
 	DevBuf dSubNum, dSubFirst, dSubClosed, dPts, dDD, dJobPieces, dPieceStart, dJobRec, dPieceJob;
-	DevBuf dBlockTotals, dBlockBase, dMeshTotals, dMeshOff, dScanTmp;
+	DevBuf dBlockTotals, dBlockBase, dMeshTotals, dMeshOff, dScanTmp, dBlockTail;
 	/* outputs */
 	DevBuf dPos, dCol, dIdx;
 	void* hPinned = nullptr; /* small pinned readback area */
@@ -624,6 +671,7 @@ public:
 	bool hasXform = false, rawMode = false, uploaded = false, ran = false;
 	uint32_t numSub = 0, numJobs = 0, numDraws = 0, numPaths = 0;
 	uint32_t idxBytes = 2;
+	uint32_t opsMask = OPS_ALL; /* which ops the uploaded draws contain */
 	vgb_sizes sz;
 	RunTimes rt;
 	uint32_t launches = 0;
@@ -633,7 +681,7 @@ public:
 		cudaSetDevice(dev);
 		DevBuf* all[] = {&dSubRec, &dCmd, &dData, &dScale, &dTol, &dXform, &dDraws, &dJobSub, &dJobDraw, &dSubNum, &dSubFirst,
 		                 &dSubClosed, &dPts, &dDD, &dJobPieces, &dPieceStart, &dJobRec, &dPieceJob, &dBlockTotals, &dBlockBase,
-		                 &dMeshTotals, &dMeshOff, &dScanTmp, &dPos, &dCol, &dIdx};
+		                 &dMeshTotals, &dMeshOff, &dScanTmp, &dBlockTail, &dPos, &dCol, &dIdx};
 		for (DevBuf* b : all) b->release();
 		for (auto& e : ev) if (e) cudaEventDestroy(e);
 		for (auto& e : userEv) if (e) cudaEventDestroy(e);
@@ -694,6 +742,12 @@ public:
 			rc |= up(dData, t.data, t.numData, err);
 			if (hasXform) rc |= up(dXform, t.pathXform, 6 * (size_t)t.numPaths, err);
 		}
+		opsMask = 0;
+		for (uint32_t d = 0; d < t.numDraws; ++d) {
+			const uint32_t op = t.draws[d].ocj & 0xFF;
+			opsMask |= (op == VGB_OP_STROKE_AA) ? OPS_STROKE_AA : (op == VGB_OP_CONVEX_FILL_AA ? OPS_FILL_AA : 0u);
+		}
+		if (opsMask == 0) opsMask = OPS_ALL;
 		rc |= up(dDraws, t.draws, t.numDraws, err);
 		rc |= up(dJobSub, t.jobSub, t.numJobs, err);
 		rc |= up(dJobDraw, t.jobDraw, t.numJobs, err);
@@ -800,7 +854,7 @@ public:
 		if (numPieces) {
 			if (dJobRec.ensure((size_t)numJobs * sizeof(JobRec), err) || dPieceJob.ensure((size_t)numPieces * 4, err) ||
 			    dBlockTotals.ensure((size_t)numBlocks * 8, err) || dBlockBase.ensure((size_t)(numBlocks + 1) * 16, err) ||
-			    dMeshTotals.ensure((size_t)numJobs * 8, err))
+			    dMeshTotals.ensure((size_t)numJobs * 8, err) || dBlockTail.ensure((size_t)numBlocks * 4, err))
 				return VGB_ERR_CUDA;
 			k_job_prep<<<(numJobs + 255) / 256, 256, 0, st>>>(dJobSub.as<uint32_t>(), dJobDraw.as<uint32_t>(), numJobs, dSubFirst.as<uint32_t>(),
 			                                                   dSubNum.as<uint32_t>(), dSubClosed.as<uint8_t>(), dDD.as<DrawDerived>(),
@@ -812,12 +866,15 @@ public:
 			pa.pieceJob = dPieceJob.as<uint32_t>();
 			pa.jobRec = dJobRec.as<JobRec>();
 			pa.pts = dPts.as<float2>();
+			pa.blockTail = dBlockTail.as<uint32_t>();
 			pa.blockTotals = dBlockTotals.as<uint2>();
 			pa.meshTotals = dMeshTotals.as<uint2>();
 			pa.blockBase = dBlockBase.as<ulonglong2>();
 			pa.meshOff = dMeshOff.as<ulonglong2>();
 			pa.vertexBase = vertexBase;
-			k_piece_count<<<numBlocks, PPB, 0, st>>>(pa);
+			if (opsMask == OPS_STROKE_AA) k_piece_count<OPS_STROKE_AA><<<numBlocks, PPB, 0, st>>>(pa);
+			else if (opsMask == OPS_FILL_AA) k_piece_count<OPS_FILL_AA><<<numBlocks, PPB, 0, st>>>(pa);
+			else k_piece_count<OPS_ALL><<<numBlocks, PPB, 0, st>>>(pa);
 			++launches;
 			if (scan<ScanOps<uint2>>(dBlockTotals.as<uint2>(), numBlocks, dBlockBase.as<ulonglong2>(), err)) return VGB_ERR_CUDA;
 			if (scan<ScanOps<uint2>>(dMeshTotals.as<uint2>(), numJobs, dMeshOff.as<ulonglong2>(), err)) return VGB_ERR_CUDA;
@@ -836,11 +893,18 @@ public:
 			pa.pos = dPos.as<float2>();
 			pa.col = dCol.as<uint32_t>();
 			pa.idx = dIdx.p;
+#define VGB_LAUNCH_EMIT(T)                                                                                  \
+	do {                                                                                                    \
+		if (opsMask == OPS_STROKE_AA) k_piece_emit<T, OPS_STROKE_AA><<<numBlocks, PPB, 0, st>>>(pa);        \
+		else if (opsMask == OPS_FILL_AA) k_piece_emit<T, OPS_FILL_AA><<<numBlocks, PPB, 0, st>>>(pa);       \
+		else k_piece_emit<T, OPS_ALL><<<numBlocks, PPB, 0, st>>>(pa);                                       \
+	} while (0)
 			if (idxBytes == 2) {
-				k_piece_emit<uint16_t><<<numBlocks, PPB, 0, st>>>(pa);
+				VGB_LAUNCH_EMIT(uint16_t);
 			} else {
-				k_piece_emit<uint32_t><<<numBlocks, PPB, 0, st>>>(pa);
+				VGB_LAUNCH_EMIT(uint32_t);
 			}
+#undef VGB_LAUNCH_EMIT
 			++launches;
 			VGB_CUDA(cudaGetLastError());
 		}

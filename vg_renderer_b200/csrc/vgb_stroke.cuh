@@ -124,7 +124,11 @@ __device__ __forceinline__ void classifyJoinAA(const JobCtx& J, Piece& P)
 	}
 }
 
+/* ops present in a batch (kernel template parameter: code for absent ops is compiled out) */
+enum { OPS_STROKE_AA = 1, OPS_FILL_AA = 2, OPS_ALL = 3 };
+
 /* the single source of every count decision: piece q of job J */
+template<uint32_t OPS>
 __device__ __forceinline__ Piece classify(const JobCtx& J, uint32_t q, const float2* __restrict__ pts)
 {
 	Piece P;
@@ -139,7 +143,7 @@ __device__ __forceinline__ Piece classify(const JobCtx& J, uint32_t q, const flo
 	P.p = P.d01 = P.d12 = P.v = f2(0.0f, 0.0f);
 	const float2* v = pts + J.first;
 	const uint32_t N = J.N;
-	if (J.op == VGB_OP_STROKE_AA) {
+	if ((OPS & OPS_STROKE_AA) && (!(OPS & ~OPS_STROKE_AA) || J.op == VGB_OP_STROKE_AA)) {
 		if (!J.closed && q == 0) {
 			P.kind = PK_CAP_START;
 			P.p = v[0];
@@ -180,7 +184,7 @@ __device__ __forceinline__ Piece classify(const JobCtx& J, uint32_t q, const flo
 			}
 			classifyJoinAA(J, P);
 		}
-	} else if (J.op == VGB_OP_CONVEX_FILL_AA) {
+	} else if ((OPS & OPS_FILL_AA) && (!(OPS & ~OPS_FILL_AA) || J.op == VGB_OP_CONVEX_FILL_AA)) {
 		if (q < N - 2) {
 			P.kind = PK_FILL_FAN;
 			P.icount = 3;
@@ -216,6 +220,31 @@ __device__ __forceinline__ uint4 pieceOut4(const JobCtx& J, const Piece& P, uint
 		return make_uint4(F, F + 1, F + 2 + n2, F + 3 + n2);
 	}
 	return make_uint4(F + 3 + n2, F + 2 + n2, F + 1, F);
+}
+
+/* A piece's hand-over to its successor packed in one word: kind | left << 3 | n << 4 | vcount << 16.
+ * The successor rebuilds pieceOut4 from it and its own F (F_prev = F - vcount_prev). */
+__device__ __forceinline__ uint32_t packTail(const Piece& P)
+{
+	return P.kind | ((P.flags & PF_LEFT) ? 8u : 0u) | ((P.n & 0xFFFu) << 4) | (P.vcount << 16);
+}
+
+__device__ __forceinline__ uint4 out4FromTail(uint32_t capType, uint32_t joinType, uint32_t tail, uint32_t F)
+{
+	const uint32_t kind = tail & 7u, n = (tail >> 4) & 0xFFFu;
+	const uint32_t Fp = F - (tail >> 16);
+	if (kind == PK_CAP_START) {
+		if (capType == VGB_CAP_ROUND) {
+			const uint32_t e = 2 * (n - 1);
+			return make_uint4(Fp + 1, Fp, Fp + e, Fp + e + 1);
+		}
+		return make_uint4(Fp, Fp + 1, Fp + 2, Fp + 3);
+	}
+	const uint32_t n2 = (joinType == VGB_JOIN_MITER) ? 0u : 2 * n;
+	if (tail & 8u) {
+		return make_uint4(Fp, Fp + 1, Fp + 2 + n2, Fp + 3 + n2);
+	}
+	return make_uint4(Fp + 3 + n2, Fp + 2 + n2, Fp + 1, Fp);
 }
 
 /* the 4 ids of a join's entry cross-section (what the previous piece connects to) */
@@ -265,98 +294,82 @@ struct Sink
 };
 
 /* ---- AA stroke pieces ---------------------------------------------------------------- */
-template<class IDX>
-__device__ __forceinline__ void emitCapStartAA(const JobCtx& J, const Piece& P, uint32_t F, const Sink<IDX>& S)
+/* everything a cap needs, detached from its owner thread (k_piece_emit hands caps to one warp so
+ * that the other warps never execute cap code) */
+struct CapRec
 {
-	const float2 p0 = P.p, d = P.d01;
+	float2 p, d;      /* end point and direction of the adjacent segment        */
+	float hsw, hsw_aa, fringe;
+	uint32_t color, c0;
+	uint32_t n;       /* nHC for round caps                                    */
+	uint32_t F;       /* mesh-local id of the cap's first vertex               */
+	uint4 prev;       /* cross-section before an end cap                       */
+	uint32_t vl, il;  /* block-local offsets of its vertices / indices         */
+	uint32_t base;    /* index base                                            */
+	uint32_t info;    /* owner thread | cap type << 16 | isEnd << 24          */
+};
+
+/* start cap: stroker.cpp:1422-1515; end cap: 1858-1968.  An end cap is the start cap mirrored:
+ * the along-segment offsets change sign (negation is exact) and every triangle swaps its 2nd
+ * and 3rd index. */
+template<class IDX>
+__device__ __forceinline__ void emitCapAA(const CapRec& R, const Sink<IDX>& S)
+{
+	const uint32_t capType = (R.info >> 16) & 0xFF;
+	const bool isEnd = (R.info >> 24) != 0;
+	const float2 p0 = R.p, d = R.d;
 	const float2 l = f2(-d.y, d.x);
-	const float hsw = J.hsw, hsw_aa = J.hsw_aa;
-	if (J.cap == VGB_CAP_ROUND) {
-		/* stroker.cpp:1475-1515 */
-		const uint32_t n = P.n;
+	const float hsw = R.hsw, hsw_aa = R.hsw_aa;
+	const uint32_t F = R.F;
+	uint32_t k = 0;
+	if (capType == VGB_CAP_ROUND) {
+		const uint32_t n = R.n;
 		const float startAngle = vgb_atan2(l.y, l.x);
 		for (uint32_t i = 0; i < n; ++i) {
-			const float a = startAngle + (float)i * VGB_PI / (float)(n - 1);
+			const float t = (float)i * VGB_PI / (float)(n - 1);
+			const float a = startAngle + (isEnd ? -t : t);
 			float sa, ca;
 			vgb_sincos(a, &sa, &ca);
-			S.VP(2 * i, p0.x + ca * hsw, p0.y + sa * hsw, J.color, p0.x + ca * hsw_aa, p0.y + sa * hsw_aa, J.c0);
+			S.VP(2 * i, p0.x + ca * hsw, p0.y + sa * hsw, R.color, p0.x + ca * hsw_aa, p0.y + sa * hsw_aa, R.c0);
 		}
-		uint32_t k = 0;
+		if (isEnd) {
+			const uint32_t e = F + 2 * (n - 1);
+			S.connect(0, R.prev, make_uint4(F + 1, F, e, e + 1));
+			k = 18;
+		}
+		const uint32_t o2 = isEnd ? 4u : 2u, o3 = isEnd ? 2u : 4u;
 		for (uint32_t i = 0; i < n - 2; ++i, k += 3) {
-			S.tri(k, F, F + 2 * i + 2, F + 2 * i + 4);
+			S.tri(k, F, F + 2 * i + o2, F + 2 * i + o3);
 		}
+		const uint32_t q2 = isEnd ? 3u : 1u, q3 = isEnd ? 1u : 3u, r2 = isEnd ? 2u : 3u, r3 = isEnd ? 3u : 2u;
 		for (uint32_t i = 0; i < n - 1; ++i, k += 6) {
 			const uint32_t b = F + 2 * i;
-			S.tri(k, b, b + 1, b + 3);
-			S.tri(k + 3, b, b + 3, b + 2);
+			S.tri(k, b, b + q2, b + q3);
+			S.tri(k + 3, b, b + r2, b + r3);
 		}
 		return;
 	}
+	const float2 ds = isEnd ? f2(-d.x, -d.y) : d; /* d-terms of the start-cap formulas */
 	const float lx = l.x * hsw, ly = l.y * hsw;
 	const float lax = l.x * hsw_aa, lay = l.y * hsw_aa;
-	if (J.cap == VGB_CAP_BUTT) {
-		/* stroker.cpp:1422-1447 */
-		const float dax = d.x * J.fringe, day = d.y * J.fringe;
-		S.VP(0, p0.x + (lax - dax), p0.y + (lay - day), J.c0, p0.x + lx, p0.y + ly, J.color);
-		S.VP(2, p0.x - lx, p0.y - ly, J.color, p0.x - (lax + dax), p0.y - (lay + day), J.c0);
+	if (capType == VGB_CAP_BUTT) {
+		const float dax = ds.x * R.fringe, day = ds.y * R.fringe;
+		S.VP(0, p0.x + (lax - dax), p0.y + (lay - day), R.c0, p0.x + lx, p0.y + ly, R.color);
+		S.VP(2, p0.x - lx, p0.y - ly, R.color, p0.x - (lax + dax), p0.y - (lay + day), R.c0);
 	} else {
-		/* square, stroker.cpp:1448-1474 */
-		const float dx = d.x * hsw, dy = d.y * hsw;
-		const float dax = d.x * hsw_aa, day = d.y * hsw_aa;
-		S.VP(0, p0.x + (lax - dax), p0.y + (lay - day), J.c0, p0.x + (lx - dx), p0.y + (ly - dy), J.color);
-		S.VP(2, p0.x - (lx + dx), p0.y - (ly + dy), J.color, p0.x - (lax + dax), p0.y - (lay + day), J.c0);
+		const float dx = ds.x * hsw, dy = ds.y * hsw;
+		const float dax = ds.x * hsw_aa, day = ds.y * hsw_aa;
+		S.VP(0, p0.x + (lax - dax), p0.y + (lay - day), R.c0, p0.x + (lx - dx), p0.y + (ly - dy), R.color);
+		S.VP(2, p0.x - (lx + dx), p0.y - (ly + dy), R.color, p0.x - (lax + dax), p0.y - (lay + day), R.c0);
 	}
-	S.tri(0, F, F + 2, F + 1);
-	S.tri(3, F, F + 3, F + 2);
-}
-
-template<class IDX>
-__device__ __forceinline__ void emitCapEndAA(const JobCtx& J, const Piece& P, uint32_t C, uint4 prev, const Sink<IDX>& S)
-{
-	const float2 p1 = P.p, d = P.d01;
-	const float2 l = f2(-d.y, d.x);
-	const float hsw = J.hsw, hsw_aa = J.hsw_aa;
-	if (J.cap == VGB_CAP_ROUND) {
-		/* stroker.cpp:1917-1968 */
-		const uint32_t n = P.n;
-		const float startAngle = vgb_atan2(l.y, l.x);
-		for (uint32_t i = 0; i < n; ++i) {
-			const float a = startAngle - (float)i * VGB_PI / (float)(n - 1);
-			float sa, ca;
-			vgb_sincos(a, &sa, &ca);
-			S.VP(2 * i, p1.x + ca * hsw, p1.y + sa * hsw, J.color, p1.x + ca * hsw_aa, p1.y + sa * hsw_aa, J.c0);
-		}
-		const uint32_t e = C + 2 * (n - 1);
-		S.connect(0, prev, make_uint4(C + 1, C, e, e + 1));
-		uint32_t k = 18;
-		for (uint32_t i = 0; i < n - 2; ++i, k += 3) {
-			const uint32_t b = C + 2 * i;
-			S.tri(k, C, b + 4, b + 2);
-		}
-		for (uint32_t i = 0; i < n - 1; ++i, k += 6) {
-			const uint32_t b = C + 2 * i;
-			S.tri(k, b, b + 3, b + 1);
-			S.tri(k + 3, b, b + 2, b + 3);
-		}
-		return;
-	}
-	const float lx = l.x * hsw, ly = l.y * hsw;
-	const float lax = l.x * hsw_aa, lay = l.y * hsw_aa;
-	if (J.cap == VGB_CAP_BUTT) {
-		/* stroker.cpp:1858-1886 */
-		const float dax = d.x * J.fringe, day = d.y * J.fringe;
-		S.VP(0, p1.x + (lax + dax), p1.y + (lay + day), J.c0, p1.x + lx, p1.y + ly, J.color);
-		S.VP(2, p1.x - lx, p1.y - ly, J.color, p1.x - (lax - dax), p1.y - (lay - day), J.c0);
+	if (isEnd) {
+		S.connect(0, R.prev, make_uint4(F, F + 1, F + 2, F + 3));
+		S.tri(18, F, F + 1, F + 2);
+		S.tri(21, F, F + 2, F + 3);
 	} else {
-		/* square, stroker.cpp:1887-1916 */
-		const float dx = d.x * hsw, dy = d.y * hsw;
-		const float dax = d.x * hsw_aa, day = d.y * hsw_aa;
-		S.VP(0, p1.x + (lax + dax), p1.y + (lay + day), J.c0, p1.x + (lx + dx), p1.y + (ly + dy), J.color);
-		S.VP(2, p1.x - (lx - dx), p1.y - (ly - dy), J.color, p1.x - (lax - dax), p1.y - (lay - day), J.c0);
+		S.tri(0, F, F + 2, F + 1);
+		S.tri(3, F, F + 3, F + 2);
 	}
-	S.connect(0, prev, make_uint4(C, C + 1, C + 2, C + 3));
-	S.tri(18, C, C + 1, C + 2);
-	S.tri(21, C, C + 2, C + 3);
 }
 
 /* stroker.cpp:1536-1847. firstLeft: side of the mesh's first join (closing connect only) */
@@ -417,19 +430,13 @@ __device__ __forceinline__ void emitJoinAA(const JobCtx& J, const Piece& P, uint
 			S.connect(0, prev, joinIn4(left, F));
 			k = 18;
 		}
+		/* slices (1673-1685 / 1828-1840): the right-inner case swaps the 2nd and 3rd index of each triangle */
 		uint32_t A = F + 2;
-		if (left) {
-			for (uint32_t i = 0; i < n; ++i, k += 9, A += 2) {
-				S.tri(k, F + 1, A, A + 2);
-				S.tri(k + 3, A, A + 1, A + 3);
-				S.tri(k + 6, A, A + 3, A + 2);
-			}
-		} else {
-			for (uint32_t i = 0; i < n; ++i, k += 9, A += 2) {
-				S.tri(k, F + 1, A + 2, A);
-				S.tri(k + 3, A, A + 3, A + 1);
-				S.tri(k + 6, A, A + 2, A + 3);
-			}
+		const uint32_t u2 = left ? 0u : 2u, u3 = left ? 2u : 0u, w2 = left ? 1u : 3u, w3 = left ? 3u : 1u, x2 = left ? 3u : 2u, x3 = left ? 2u : 3u;
+		for (uint32_t i = 0; i < n; ++i, k += 9, A += 2) {
+			S.tri(k, F + 1, A + u2, A + u3);
+			S.tri(k + 3, A, A + w2, A + w3);
+			S.tri(k + 6, A, A + x2, A + x3);
 		}
 	}
 	if (P.flags & PF_CLOSING) {
