@@ -282,3 +282,70 @@ def test_large_batch_properties(gpu_batch, ref):
     np.testing.assert_array_equal(out["index"][i0:i1], exp["index"])
     np.testing.assert_array_equal(out["pos"][v0:v1], exp["pos"])
     np.testing.assert_array_equal(out["color"][v0:v1], exp["color"])
+
+
+@pytest.mark.parametrize("op", [vgb.OP_STROKE, vgb.OP_STROKE_AA_THIN])
+@pytest.mark.parametrize("closed", [False, True])
+@pytest.mark.parametrize("cap,join", CAPJOIN)
+def test_polyline_edge_cases_plain_and_thin(gpu_batch, ref, op, cap, join, closed):
+    """strokerPolylineStroke (no AA) and strokerPolylineStrokeAAThin on raw polylines"""
+    cases = polyline_cases()
+    pts = np.concatenate([np.asarray(c[1], np.float32) for c in cases])
+    num = np.array([len(c[1]) for c in cases], np.uint32)
+    first = np.concatenate([[0], np.cumsum(num)[:-1]]).astype(np.uint32)
+    gpu_batch.reset(1.0)
+    gpu_batch.set_polylines(pts, first, num, np.full(len(cases), closed, np.uint8))
+    gpu_batch.draw_all(op, 0x80FF8040, 6.0, cap, join)
+    gpu_batch.run()
+    out = gpu_batch.download()
+    for m, (name, c) in enumerate(cases):
+        pos, col, idx = ref.mesh(op, c, closed, 0x80FF8040, 6.0, cap, join)
+        v0, v1 = int(out["mesh_vtx_off"][m]), int(out["mesh_vtx_off"][m + 1])
+        i0, i1 = int(out["mesh_idx_off"][m]), int(out["mesh_idx_off"][m + 1])
+        assert (v1 - v0, i1 - i0) == (len(pos), len(idx)), name
+        np.testing.assert_array_equal(out["index"][i0:i1], idx, err_msg=name)
+        np.testing.assert_array_equal(out["pos"][v0:v1], pos, err_msg=name)
+        if col is not None:
+            np.testing.assert_array_equal(out["color"][v0:v1], col, err_msg=name)
+        else:
+            assert np.all(out["color"][v0:v1] == 0x80FF8040)  # no per-vertex colour in the reference: the draw colour
+
+
+def test_fan_fill_and_mixed_ops_batch(gpu_batch, ref):
+    """all five ops in one batch (general kernel), incl. odd vertex counts before AA meshes"""
+    r = Recorder(fringe=1.0)
+    r.begin_path().move_to(0, 0).line_to(40, 5).line_to(60, 50).line_to(10, 70).close()
+    r.convex_fill(0xFF010203, False).stroke(2, 0xFFAABBCC, 5.0, 1, 1).stroke(0, 0xFF112233, 5.0, 1, 1)
+    r.stroke(3, 0xFF445566, 1.0, 2, 2).convex_fill(0xFF778899, True)
+    r.begin_path().move_to(5, 5).cubic_to(80, -40, 120, 90, 200, 20).stroke(2, 0xFFFFFFFF, 9.0, 0, 0).stroke(3, 0xFF00FF00, 1.0, 0, 0)
+    r.begin_path().circle(50, 50, 33).convex_fill(0xFF0000FF, False).stroke(2, 0xFF00FFFF, 3.0, 0, 2)
+    for cap, join in CAPJOIN:
+        r.begin_path().move_to(0, 0).cubic_to(30, 60, 90, -60, 120, 0).line_to(140, 40)
+        r.stroke(2, 0xFF101010, 7.0, cap, join).stroke(3, 0xFF202020, 1.0, cap, join).stroke(0, 0xFF303030, 7.0, cap, join)
+    r.replay(gpu_batch)
+    gpu_batch.run()
+    check_same(gpu_batch.download(), ref.run_batch(r.tables()))
+
+
+def test_per_object_plain_thin_fan(ref):
+    p = vgb.Path()
+    p.reset(1.0, 0.25)
+    p.move_to(0, 0)
+    p.cubic_to(40, 80, 90, -50, 130, 10)
+    v = p.vertices()
+    s = vgb.Stroker()
+    s.reset(1.0, 0.25, 1.0)
+    pos, col, idx = s.polyline_stroke(v, False, 6.0, vgb.CAP_ROUND, vgb.JOIN_ROUND)
+    rpos, rcol, ridx = ref.mesh(vgb.OP_STROKE, v, False, 0, 6.0, 1, 1)
+    assert col is None and rcol is None
+    np.testing.assert_array_equal(idx, ridx)
+    np.testing.assert_array_equal(pos, rpos)
+    pos, col, idx = s.polyline_stroke_aa_thin(v, True, 0xFF0000FF, vgb.CAP_ROUND, vgb.JOIN_ROUND)
+    rpos, rcol, ridx = ref.mesh(vgb.OP_STROKE_AA_THIN, v, True, 0xFF0000FF, 1.0, 1, 1)
+    np.testing.assert_array_equal(idx, ridx)
+    np.testing.assert_array_equal(col, rcol)
+    np.testing.assert_array_equal(pos, rpos)
+    pos, col, idx = s.convex_fill(v[:9])
+    rpos, rcol, ridx = ref.mesh(vgb.OP_CONVEX_FILL, v[:9], True, 0)
+    np.testing.assert_array_equal(idx, ridx)
+    np.testing.assert_array_equal(pos, v[:9])

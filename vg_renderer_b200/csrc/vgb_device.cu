@@ -260,6 +260,20 @@ __global__ void k_draw_prep(const DrawRec* __restrict__ draws, uint32_t n, const
 		o.hsw_aa = o.hsw + fringe;
 		o.da = vgb_acos((scale * o.hsw) / ((scale * o.hsw) + tol)) * 2.0f;
 		o.nHC = vgb_umax(2u, (uint32_t)vgb_ceil(VGB_PI / o.da));
+	} else if (op == VGB_OP_STROKE) {
+		/* stroker.cpp:1012-1014; hsw_aa carries the side-test scale (v * hsw, 1096-1099) */
+		o.hsw = r.width * 0.5f;
+		o.hsw_aa = o.hsw;
+		o.da = vgb_acos((scale * o.hsw) / ((scale * o.hsw) + tol)) * 2.0f;
+		o.nHC = vgb_umax(2u, (uint32_t)vgb_ceil(VGB_PI / o.da));
+	} else if (op == VGB_OP_STROKE_AA_THIN) {
+		/* stroker.cpp:1999 (half width = fringe) and the dispatch of 311-332: round cap -> square,
+		 * round join -> bevel */
+		o.hsw_aa = fringe;
+		uint32_t cap = (r.ocj >> 8) & 0xFF, join = (r.ocj >> 16) & 0xFF;
+		if (cap == VGB_CAP_ROUND) cap = VGB_CAP_SQUARE;
+		if (join == VGB_JOIN_ROUND) join = VGB_JOIN_BEVEL;
+		o.ocj = op | (cap << 8) | (join << 16);
 	}
 	out[d] = o;
 }
@@ -468,9 +482,26 @@ __device__ __forceinline__ CapRec makeCapRec(const JobCtx& J, const Piece& P, ui
 
 static constexpr uint32_t CAPMAX = 32; /* caps per block handed to warp 0; the rest are emitted in place */
 
-template<class IDX, uint32_t OPS>
-__device__ __forceinline__ void emitPiece(const PieceArgs& a, const JobCtx& J, const Piece& P, uint32_t F, uint4 prev, const Sink<IDX>& S)
+template<uint32_t OPS, class SINK>
+__device__ __forceinline__ void emitPiece(const PieceArgs& a, const JobCtx& J, const Piece& P, uint32_t F, uint4 prev, const SINK& S)
 {
+	if ((OPS & OPS_OTHER) && (J.op == VGB_OP_STROKE || J.op == VGB_OP_STROKE_AA_THIN)) {
+		if (P.kind == PK_JOIN) {
+			const bool firstLeft = (P.flags & PF_CLOSING) ? firstJoinLeft(J, a.pts) : false;
+			emitRibbonJoin(J, P, F, prev, firstLeft, S);
+		} else {
+			emitRibbonCap(J, P, F, prev, S);
+		}
+		return;
+	}
+	if ((OPS & OPS_OTHER) && P.kind == PK_FAN_TRI) {
+		S.tri(0, 0, P.li + 1, P.li + 2);
+		return;
+	}
+	if ((OPS & OPS_OTHER) && P.kind == PK_FAN_VTX) {
+		S.V(0, P.p.x, P.p.y, J.color);
+		return;
+	}
 	if ((OPS & OPS_STROKE_AA) && P.kind == PK_JOIN) {
 		const bool firstLeft = (P.flags & PF_CLOSING) ? firstJoinLeft(J, a.pts) : false;
 		emitJoinAA(J, P, F, prev, firstLeft, S);
@@ -540,14 +571,15 @@ __global__ void __launch_bounds__(PPB, VGB_EMIT_MIN_BLOCKS) k_piece_emit(PieceAr
 		F = (uint32_t)(bb.x + vl - mo.x);
 		if (P.flags & PF_HAS_PREV) {
 			/* piece q-1 of the same job is owned by thread t-1 (or by the previous block's last thread) */
-			prev = out4FromTail(J.cap, J.join, t > 0 ? sTail[t - 1] : tail0, F);
+			const uint32_t tw = t > 0 ? sTail[t - 1] : tail0;
+			prev = ((OPS & OPS_OTHER) && J.op != VGB_OP_STROKE_AA) ? ribbonOutFromTail(J, tw, F) : out4FromTail(J.cap, J.join, tw, F);
 		}
 	}
 	const uint32_t idxBase = sizeof(IDX) == 2 ? 0u : (uint32_t)(mo.x + a.vertexBase);
 	/* caps (a few per block) are detached from their owners and emitted by the low lanes of warp 0:
 	 * every other warp then runs join code only, instead of join + start-cap + end-cap code */
 	bool deferred = false;
-	if (o.valid && (P.kind == PK_CAP_START || P.kind == PK_CAP_END)) {
+	if (o.valid && (P.kind == PK_CAP_START || P.kind == PK_CAP_END) && (!(OPS & OPS_OTHER) || J.op == VGB_OP_STROKE_AA)) {
 		const uint32_t slot = atomicAdd(&sCapCount, 1u);
 		if (slot < CAPMAX) {
 			sCap[slot] = makeCapRec(J, P, F, prev, vl, il, idxBase, t);
@@ -567,12 +599,12 @@ __global__ void __launch_bounds__(PPB, VGB_EMIT_MIN_BLOCKS) k_piece_emit(PieceAr
 		if (cnt == 0) {
 			/* a single piece larger than the staging buffers: its owner writes it straight to HBM */
 			if (t == ta) {
-				Sink<IDX> S;
+				Sink<IDX, !(OPS & OPS_OTHER)> S;
 				S.pos = a.pos + gv;
 				S.col = a.col + gv;
 				S.idx = reinterpret_cast<IDX*>(a.idx) + gi;
 				S.base = idxBase;
-				emitPiece<IDX, OPS>(a, J, P, F, prev, S);
+				emitPiece<OPS>(a, J, P, F, prev, S);
 			}
 			ta += 1;
 			__syncthreads();
@@ -581,18 +613,18 @@ __global__ void __launch_bounds__(PPB, VGB_EMIT_MIN_BLOCKS) k_piece_emit(PieceAr
 		const uint32_t tb = ta + cnt;
 		const uint32_t shV2 = (uint32_t)(gv & 1), shV4 = (uint32_t)(gv & 3), shI = (uint32_t)(gi & (KI - 1));
 		if (t >= ta && t < tb && !deferred) {
-			Sink<IDX> S;
+			Sink<IDX, !(OPS & OPS_OTHER)> S;
 			S.pos = sPos + shV2 + (vl - v0);
 			S.col = sCol + shV4 + (vl - v0);
 			S.idx = sIdx + shI + (il - i0);
 			S.base = idxBase;
-			emitPiece<IDX, OPS>(a, J, P, F, prev, S);
+			emitPiece<OPS>(a, J, P, F, prev, S);
 		}
 		if (t < min(sCapCount, CAPMAX)) {
 			const CapRec R = sCap[t];
 			const uint32_t owner = R.info & 0xFFFF;
 			if (owner >= ta && owner < tb) {
-				Sink<IDX> S;
+				Sink<IDX, !(OPS & OPS_OTHER)> S;
 				S.pos = sPos + shV2 + (R.vl - v0);
 				S.col = sCol + shV4 + (R.vl - v0);
 				S.idx = sIdx + shI + (R.il - i0);
@@ -745,9 +777,9 @@ public:
 		opsMask = 0;
 		for (uint32_t d = 0; d < t.numDraws; ++d) {
 			const uint32_t op = t.draws[d].ocj & 0xFF;
-			opsMask |= (op == VGB_OP_STROKE_AA) ? OPS_STROKE_AA : (op == VGB_OP_CONVEX_FILL_AA ? OPS_FILL_AA : 0u);
+			opsMask |= (op == VGB_OP_STROKE_AA) ? OPS_STROKE_AA : (op == VGB_OP_CONVEX_FILL_AA ? OPS_FILL_AA : OPS_OTHER);
 		}
-		if (opsMask == 0) opsMask = OPS_ALL;
+		if (opsMask == 0 || (opsMask & (opsMask - 1))) opsMask = OPS_ALL; /* mixed batches use the general kernel */
 		rc |= up(dDraws, t.draws, t.numDraws, err);
 		rc |= up(dJobSub, t.jobSub, t.numJobs, err);
 		rc |= up(dJobDraw, t.jobDraw, t.numJobs, err);

@@ -24,7 +24,7 @@
 
 namespace vgb
 {
-enum { PK_NONE = 0, PK_CAP_START, PK_JOIN, PK_CAP_END, PK_FILL_FAN, PK_FILL_VTX };
+enum { PK_NONE = 0, PK_CAP_START, PK_JOIN, PK_CAP_END, PK_FILL_FAN, PK_FILL_VTX, PK_FAN_TRI, PK_FAN_VTX };
 enum { PF_LEFT = 1, PF_HAS_PREV = 2, PF_CLOSING = 4 };
 
 /* one job = one mesh: (draw, sub-path) */
@@ -71,8 +71,11 @@ __device__ __forceinline__ float2 extrusion(float2 d01, float2 d12)
 __host__ __device__ __forceinline__ uint32_t pieceCount(uint32_t op, uint32_t N)
 {
 	switch (op) {
-	case VGB_OP_STROKE_AA: return N >= 2 ? N : 0;
-	case VGB_OP_CONVEX_FILL_AA: return N >= 3 ? 2 * N - 2 : 0;
+	case VGB_OP_STROKE_AA:
+	case VGB_OP_STROKE:
+	case VGB_OP_STROKE_AA_THIN: return N >= 2 ? N : 0;
+	case VGB_OP_CONVEX_FILL_AA:
+	case VGB_OP_CONVEX_FILL: return N >= 3 ? 2 * N - 2 : 0;
 	default: return 0;
 	}
 }
@@ -124,8 +127,82 @@ __device__ __forceinline__ void classifyJoinAA(const JobCtx& J, Piece& P)
 	}
 }
 
+/* ---- plain (W=2) and thin AA (W=3) strokes: the same ribbon walk as the AA stroke with fewer ids
+ * per cross-section (stroker.cpp:1008-1388 and 1993-2314).  JobCtx carries the op-specific side-test
+ * scale in hsw_aa (plain: w/2, thin: fringe) and, for thin strokes, the already mapped cap/join
+ * (round cap -> square, round join -> bevel: stroker.cpp:318-327). */
+__device__ __forceinline__ void classifyRibbon(const JobCtx& J, uint32_t q, const float2* __restrict__ v, Piece& P)
+{
+	const uint32_t N = J.N;
+	const bool thin = J.op == VGB_OP_STROKE_AA_THIN;
+	const uint32_t W = thin ? 3u : 2u;
+	const uint32_t conn = 6 * (W - 1);
+	const uint32_t fanI = (J.cap == VGB_CAP_ROUND && !thin) ? 3 * (J.nHC - 2) : 0u;
+	if (!J.closed && (q == 0 || q == N - 1)) {
+		const bool end = q != 0;
+		P.kind = end ? PK_CAP_END : PK_CAP_START;
+		P.p = v[q];
+		P.d01 = end ? vdir(v[N - 2], P.p) : vdir(P.p, v[1]);
+		P.n = J.nHC;
+		P.vcount = thin ? 3u : (J.cap == VGB_CAP_ROUND ? J.nHC : 2u);
+		P.icount = end ? conn + fanI : fanI;
+		if (end) {
+			P.flags = PF_HAS_PREV;
+		}
+		return;
+	}
+	P.kind = PK_JOIN;
+	P.p = v[q];
+	P.d01 = vdir(v[q == 0 ? N - 1 : q - 1], P.p);
+	P.d12 = vdir(P.p, v[q == N - 1 ? 0 : q + 1]);
+	if (!(J.closed && q == 0)) {
+		P.flags |= PF_HAS_PREV;
+	}
+	if (J.closed && q == N - 1) {
+		P.flags |= PF_CLOSING;
+	}
+	P.v = extrusion(P.d01, P.d12);
+	const float proj = P.d12.x * (P.v.x * J.hsw_aa) + P.d12.y * (P.v.y * J.hsw_aa); /* 1099 / 2072 */
+	const bool left = proj >= 0.0f;
+	if (left) {
+		P.flags |= PF_LEFT;
+	}
+	const uint32_t c = (P.flags & PF_HAS_PREV) ? conn : 0u;
+	if (J.join == VGB_JOIN_MITER) {
+		P.vcount = W;
+		P.icount = c;
+	} else if (thin) {
+		P.n = 1;
+		P.vcount = 4;
+		P.icount = c + 3;
+	} else {
+		uint32_t n = 1;
+		if (J.join == VGB_JOIN_ROUND) {
+			const float2 s01 = left ? f2(P.d01.y, -P.d01.x) : f2(-P.d01.y, P.d01.x);
+			const float2 s12 = left ? f2(P.d12.y, -P.d12.x) : f2(-P.d12.y, P.d12.x);
+			const float a01 = vgb_atan2(s01.y, s01.x);
+			float a12 = vgb_atan2(s12.y, s12.x);
+			if (left) {
+				if (a12 < a01) a12 += VGB_PI2;
+				n = vgb_umax(2u, (uint32_t)((a12 - a01) / J.da));
+			} else {
+				if (a12 > a01) a12 -= VGB_PI2;
+				n = vgb_umax(2u, (uint32_t)((a01 - a12) / J.da));
+			}
+			P.a01 = a01;
+			P.arcDa = (a12 - a01) / (float)n;
+		}
+		P.n = n;
+		P.vcount = n + 2;
+		P.icount = c + 3 * n;
+	}
+	if (P.flags & PF_CLOSING) {
+		P.icount += conn;
+	}
+}
+
 /* ops present in a batch (kernel template parameter: code for absent ops is compiled out) */
-enum { OPS_STROKE_AA = 1, OPS_FILL_AA = 2, OPS_ALL = 3 };
+enum { OPS_STROKE_AA = 1, OPS_FILL_AA = 2, OPS_OTHER = 4, OPS_ALL = 7 };
 
 /* the single source of every count decision: piece q of job J */
 template<uint32_t OPS>
@@ -200,6 +277,19 @@ __device__ __forceinline__ Piece classify(const JobCtx& J, uint32_t q, const flo
 			P.d01 = vdir(pm, P.p);
 			P.d12 = vdir(P.p, pn);
 		}
+	} else if ((OPS & OPS_OTHER) && (J.op == VGB_OP_STROKE || J.op == VGB_OP_STROKE_AA_THIN)) {
+		classifyRibbon(J, q, v, P);
+	} else if ((OPS & OPS_OTHER) && J.op == VGB_OP_CONVEX_FILL) {
+		/* strokerConvexFill, stroker.cpp:334-365: indices (0,k,k+1); positions are the polygon itself */
+		if (q < N - 2) {
+			P.kind = PK_FAN_TRI;
+			P.icount = 3;
+		} else {
+			P.kind = PK_FAN_VTX;
+			P.li = q - (N - 2);
+			P.vcount = 1;
+			P.p = v[P.li];
+		}
 	}
 	return P;
 }
@@ -253,7 +343,7 @@ __device__ __forceinline__ uint4 joinIn4(bool left, uint32_t F)
 	return left ? make_uint4(F, F + 1, F + 2, F + 3) : make_uint4(F + 3, F + 2, F + 1, F);
 }
 
-template<class IDX>
+template<class IDX, bool ALIGNED = true>
 struct Sink
 {
 	float2* pos;
@@ -271,8 +361,27 @@ struct Sink
 	 * staging image keeps that parity. */
 	__device__ __forceinline__ void VP(uint32_t k, float x0, float y0, uint32_t c0_, float x1, float y1, uint32_t c1_) const
 	{
-		*reinterpret_cast<float4*>(pos + k) = make_float4(x0, y0, x1, y1);
-		*reinterpret_cast<uint2*>(col + k) = make_uint2(c0_, c1_);
+		if (ALIGNED) {
+			*reinterpret_cast<float4*>(pos + k) = make_float4(x0, y0, x1, y1);
+			*reinterpret_cast<uint2*>(col + k) = make_uint2(c0_, c1_);
+		} else {
+			/* batches mixing odd-vertex-count ops (plain / thin strokes, fan fills) lose the parity */
+			pos[k] = make_float2(x0, y0);
+			pos[k + 1] = make_float2(x1, y1);
+			col[k] = c0_;
+			col[k + 1] = c1_;
+		}
+	}
+	/* W-1 quads between two cross-sections of W ids (W=2: stroker.cpp:1118-1121, W=3: 2092-2097) */
+	template<int W>
+	__device__ __forceinline__ void bridge(uint32_t k, uint4 p, uint4 c) const
+	{
+		const uint32_t pa[4] = {p.x, p.y, p.z, p.w}, ca[4] = {c.x, c.y, c.z, c.w};
+#pragma unroll
+		for (int i = 0; i + 1 < W; ++i) {
+			tri(k + 6 * i, pa[i], pa[i + 1], ca[i + 1]);
+			tri(k + 6 * i + 3, pa[i], ca[i + 1], ca[i]);
+		}
 	}
 	__device__ __forceinline__ void I(uint32_t k, uint32_t v) const { idx[k] = (IDX)(v + base); }
 	__device__ __forceinline__ void tri(uint32_t k, uint32_t a, uint32_t b, uint32_t c) const
@@ -312,8 +421,8 @@ struct CapRec
 /* start cap: stroker.cpp:1422-1515; end cap: 1858-1968.  An end cap is the start cap mirrored:
  * the along-segment offsets change sign (negation is exact) and every triangle swaps its 2nd
  * and 3rd index. */
-template<class IDX>
-__device__ __forceinline__ void emitCapAA(const CapRec& R, const Sink<IDX>& S)
+template<class SINK>
+__device__ __forceinline__ void emitCapAA(const CapRec& R, const SINK& S)
 {
 	const uint32_t capType = (R.info >> 16) & 0xFF;
 	const bool isEnd = (R.info >> 24) != 0;
@@ -373,8 +482,8 @@ __device__ __forceinline__ void emitCapAA(const CapRec& R, const Sink<IDX>& S)
 }
 
 /* stroker.cpp:1536-1847. firstLeft: side of the mesh's first join (closing connect only) */
-template<class IDX>
-__device__ __forceinline__ void emitJoinAA(const JobCtx& J, const Piece& P, uint32_t F, uint4 prev, bool firstLeft, const Sink<IDX>& S)
+template<class SINK>
+__device__ __forceinline__ void emitJoinAA(const JobCtx& J, const Piece& P, uint32_t F, uint4 prev, bool firstLeft, const SINK& S)
 {
 	const bool left = (P.flags & PF_LEFT) != 0;
 	const float hsw = J.hsw, hsw_aa = J.hsw_aa;
@@ -457,14 +566,14 @@ __device__ __forceinline__ bool firstJoinLeft(const JobCtx& J, const float2* __r
 }
 
 /* ---- convex AA fill pieces (stroker.cpp:713-806) ---------------------------------------- */
-template<class IDX>
-__device__ __forceinline__ void emitFillFan(const Piece& P, const Sink<IDX>& S)
+template<class SINK>
+__device__ __forceinline__ void emitFillFan(const Piece& P, const SINK& S)
 {
 	S.tri(0, 0, 2 * P.li + 2, 2 * P.li + 4);
 }
 
-template<class IDX>
-__device__ __forceinline__ void emitFillVtx(const JobCtx& J, const Piece& P, const float2* __restrict__ pts, const Sink<IDX>& S)
+template<class SINK>
+__device__ __forceinline__ void emitFillVtx(const JobCtx& J, const Piece& P, const float2* __restrict__ pts, const SINK& S)
 {
 	const float2* v = pts + J.first;
 	const float2 a = f2(v[1].x - v[0].x, v[1].y - v[0].y);
@@ -483,6 +592,161 @@ __device__ __forceinline__ void emitFillVtx(const JobCtx& J, const Piece& P, con
 		S.tri(3, f, 1, 0);
 	}
 }
+/* ---- plain / thin ribbons: hand-over and emission ------------------------------------------ */
+/* ids (left .. right) a plain/thin piece hands to its successor, rebuilt from its tail word */
+__device__ __forceinline__ uint4 ribbonOutFromTail(const JobCtx& J, uint32_t tail, uint32_t F)
+{
+	const uint32_t kind = tail & 7u, n = (tail >> 4) & 0xFFFu;
+	const uint32_t Fp = F - (tail >> 16);
+	const bool left = (tail & 8u) != 0;
+	if (J.op == VGB_OP_STROKE_AA_THIN) {
+		if (kind == PK_CAP_START || J.join == VGB_JOIN_MITER) {
+			return (kind == PK_CAP_START || left) ? make_uint4(Fp, Fp + 1, Fp + 2, 0) : make_uint4(Fp + 2, Fp + 1, Fp, 0);
+		}
+		return left ? make_uint4(Fp, Fp + 1, Fp + 3, 0) : make_uint4(Fp + 3, Fp + 1, Fp, 0); /* 2152-2154 / 2232-2234 */
+	}
+	if (kind == PK_CAP_START) {
+		return make_uint4(Fp, J.cap == VGB_CAP_ROUND ? Fp + n - 1 : Fp + 1, 0, 0); /* 1043-1044, 1079-1080 */
+	}
+	const uint32_t e = (J.join == VGB_JOIN_MITER) ? 1u : n + 1;
+	return left ? make_uint4(Fp, Fp + e, 0, 0) : make_uint4(Fp + e, Fp, 0, 0); /* 1130-1131, 1195-1196, 1228-1229, 1289-1290 */
+}
+
+template<class SINK>
+__device__ __forceinline__ void emitRibbonCap(const JobCtx& J, const Piece& P, uint32_t F, uint4 prev, const SINK& S)
+{
+	const bool end = P.kind == PK_CAP_END;
+	const float2 p0 = P.p, d = P.d01;
+	const float2 ds = end ? f2(-d.x, -d.y) : d; /* an end cap mirrors the along-segment offsets */
+	const float2 l = f2(-d.y, d.x);
+	if (J.op == VGB_OP_STROKE_AA_THIN) {
+		/* 2021-2051, 2247-2291 */
+		const float h = J.hsw_aa;
+		const float lax = l.x * h, lay = l.y * h;
+		if (J.cap == VGB_CAP_BUTT) {
+			S.V(0, p0.x + lax, p0.y + lay, J.c0);
+			S.V(1, p0.x, p0.y, J.color);
+			S.V(2, p0.x - lax, p0.y - lay, J.c0);
+		} else {
+			const float dax = ds.x * h, day = ds.y * h;
+			S.V(0, p0.x + (lax - dax), p0.y + (lay - day), J.c0);
+			S.V(1, p0.x, p0.y, J.color);
+			S.V(2, p0.x - (lax + dax), p0.y - (lay + day), J.c0);
+		}
+		if (end) {
+			S.template bridge<3>(0, prev, make_uint4(F, F + 1, F + 2, 0));
+		}
+		return;
+	}
+	const float hsw = J.hsw;
+	uint32_t k = 0;
+	if (J.cap == VGB_CAP_ROUND) {
+		/* 1059-1080, 1342-1371 */
+		const uint32_t n = P.n;
+		const float startAngle = vgb_atan2(l.y, l.x);
+		for (uint32_t i = 0; i < n; ++i) {
+			const float t = (float)i * VGB_PI / (float)(n - 1);
+			const float a = startAngle + (end ? -t : t);
+			S.V(i, p0.x + vgb_cos(a) * hsw, p0.y + vgb_sin(a) * hsw, J.color);
+		}
+		if (end) {
+			S.template bridge<2>(0, prev, make_uint4(F, F + n - 1, 0, 0));
+			k = 6;
+		}
+		for (uint32_t i = 0; i + 2 < n; ++i, k += 3) {
+			if (end) S.tri(k, F, F + i + 2, F + i + 1);
+			else S.tri(k, F, F + i + 1, F + i + 2);
+		}
+		return;
+	}
+	const float lx = l.x * hsw, ly = l.y * hsw;
+	if (J.cap == VGB_CAP_BUTT) {
+		S.V(0, p0.x + lx, p0.y + ly, J.color);
+		S.V(1, p0.x - lx, p0.y - ly, J.color);
+	} else {
+		const float dx = ds.x * hsw, dy = ds.y * hsw;
+		S.V(0, p0.x + (lx - dx), p0.y + (ly - dy), J.color);
+		S.V(1, p0.x - (lx + dx), p0.y - (ly + dy), J.color);
+	}
+	if (end) {
+		S.template bridge<2>(0, prev, make_uint4(F, F + 1, 0, 0));
+	}
+}
+
+template<class SINK>
+__device__ __forceinline__ void emitRibbonJoin(const JobCtx& J, const Piece& P, uint32_t F, uint4 prev, bool firstLeft, const SINK& S)
+{
+	const bool left = (P.flags & PF_LEFT) != 0;
+	const bool thin = J.op == VGB_OP_STROKE_AA_THIN;
+	const float2 p1 = P.p;
+	const float2 vs = left ? P.v : f2(-P.v.x, -P.v.y);
+	const float2 d01 = P.d01, d12 = P.d12;
+	const float2 s01 = left ? f2(d01.y, -d01.x) : f2(-d01.y, d01.x);
+	const float2 s12 = left ? f2(d12.y, -d12.x) : f2(-d12.y, d12.x);
+	uint32_t k = 0;
+	uint4 out;
+	if (thin) {
+		const float h = J.hsw_aa;
+		const float vax = vs.x * h, vay = vs.y * h;
+		const uint4 in = left ? make_uint4(F, F + 1, F + 2, 0) : make_uint4(F + 2, F + 1, F, 0);
+		S.V(0, p1.x + vax, p1.y + vay, J.c0);
+		S.V(1, p1.x, p1.y, J.color);
+		if (J.join == VGB_JOIN_MITER) {
+			S.V(2, p1.x - vax, p1.y - vay, J.c0);
+			out = in;
+		} else {
+			S.V(2, p1.x + s01.x * h, p1.y + s01.y * h, J.c0);
+			S.V(3, p1.x + s12.x * h, p1.y + s12.y * h, J.c0);
+			out = left ? make_uint4(F, F + 1, F + 3, 0) : make_uint4(F + 3, F + 1, F, 0);
+		}
+		if (P.flags & PF_HAS_PREV) {
+			S.template bridge<3>(0, prev, in);
+			k = 12;
+		}
+		if (J.join != VGB_JOIN_MITER) {
+			if (left) S.tri(k, F + 1, F + 2, F + 3);
+			else S.tri(k, F + 1, F + 3, F + 2);
+			k += 3;
+		}
+		if (P.flags & PF_CLOSING) {
+			S.template bridge<3>(k, out, firstLeft ? make_uint4(0, 1, 2, 0) : make_uint4(2, 1, 0, 0));
+		}
+		return;
+	}
+	const float hsw = J.hsw;
+	const float vx = vs.x * hsw, vy = vs.y * hsw;
+	const uint4 in = left ? make_uint4(F, F + 1, 0, 0) : make_uint4(F + 1, F, 0, 0);
+	S.V(0, p1.x + vx, p1.y + vy, J.color);
+	if (J.join == VGB_JOIN_MITER) {
+		S.V(1, p1.x - vx, p1.y - vy, J.color);
+		out = in;
+		if (P.flags & PF_HAS_PREV) {
+			S.template bridge<2>(0, prev, in);
+			k = 6;
+		}
+	} else {
+		const uint32_t n = P.n;
+		S.V(1, p1.x + s01.x * hsw, p1.y + s01.y * hsw, J.color);
+		for (uint32_t i = 1; i < n; ++i) {
+			const float a = P.a01 + (float)i * P.arcDa;
+			S.V(1 + i, p1.x + hsw * vgb_cos(a), p1.y + hsw * vgb_sin(a), J.color);
+		}
+		S.V(1 + n, p1.x + s12.x * hsw, p1.y + s12.y * hsw, J.color);
+		if (P.flags & PF_HAS_PREV) {
+			S.template bridge<2>(0, prev, in);
+			k = 6;
+		}
+		for (uint32_t i = 0; i < n; ++i, k += 3) {
+			if (left) S.tri(k, F, F + i + 1, F + i + 2);
+			else S.tri(k, F, F + i + 2, F + i + 1);
+		}
+		out = left ? make_uint4(F, F + n + 1, 0, 0) : make_uint4(F + n + 1, F, 0, 0);
+	}
+	if (P.flags & PF_CLOSING) {
+		S.template bridge<2>(k, out, firstLeft ? make_uint4(0, 1, 0, 0) : make_uint4(1, 0, 0, 0));
+	}
+}
+
 } // namespace vgb
 
 #endif
