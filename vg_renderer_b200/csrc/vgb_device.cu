@@ -49,7 +49,7 @@ namespace vgb
 #define VGB_CI_BYTES 13312
 #endif
 #ifndef VGB_EMIT_MIN_BLOCKS
-#define VGB_EMIT_MIN_BLOCKS 5
+#define VGB_EMIT_MIN_BLOCKS 6
 #endif
 static constexpr uint32_t PPB = VGB_PPB;           /* pieces per block == threads per block   */
 static constexpr uint32_t CV = VGB_CV;             /* staged vertices per round               */
@@ -378,7 +378,7 @@ struct Owner
 	bool valid;
 };
 
-template<uint32_t OPS>
+template<uint32_t OPS, int JT, int CT>
 __global__ void __launch_bounds__(PPB) k_piece_count(PieceArgs a)
 {
 	const uint32_t g = blockIdx.x * PPB + threadIdx.x;
@@ -391,7 +391,7 @@ __global__ void __launch_bounds__(PPB) k_piece_count(PieceArgs a)
 		uint32_t ps;
 		const JobCtx J = loadJob(a, o.j, &ps);
 		o.q = g - ps;
-		const Piece P = classify<OPS>(J, o.q, a.pts);
+		const Piece P = classify<OPS, JT, CT>(J, o.q, a.pts);
 		vc = P.vcount;
 		ic = P.icount;
 		if (threadIdx.x == PPB - 1) {
@@ -482,7 +482,7 @@ __device__ __forceinline__ CapRec makeCapRec(const JobCtx& J, const Piece& P, ui
 
 static constexpr uint32_t CAPMAX = 32; /* caps per block handed to warp 0; the rest are emitted in place */
 
-template<uint32_t OPS, class SINK>
+template<uint32_t OPS, int JT, int CT, class SINK>
 __device__ __forceinline__ void emitPiece(const PieceArgs& a, const JobCtx& J, const Piece& P, uint32_t F, uint4 prev, const SINK& S)
 {
 	if ((OPS & OPS_OTHER) && (J.op == VGB_OP_STROKE || J.op == VGB_OP_STROKE_AA_THIN)) {
@@ -504,9 +504,9 @@ __device__ __forceinline__ void emitPiece(const PieceArgs& a, const JobCtx& J, c
 	}
 	if ((OPS & OPS_STROKE_AA) && P.kind == PK_JOIN) {
 		const bool firstLeft = (P.flags & PF_CLOSING) ? firstJoinLeft(J, a.pts) : false;
-		emitJoinAA(J, P, F, prev, firstLeft, S);
+		emitJoinAA<JT>(J, P, F, prev, firstLeft, S);
 	} else if ((OPS & OPS_STROKE_AA) && (P.kind == PK_CAP_START || P.kind == PK_CAP_END)) {
-		emitCapAA(makeCapRec(J, P, F, prev, 0, 0, S.base, 0), S);
+		emitCapAA<CT>(makeCapRec(J, P, F, prev, 0, 0, S.base, 0), S);
 	} else if ((OPS & OPS_FILL_AA) && P.kind == PK_FILL_VTX) {
 		emitFillVtx(J, P, a.pts, S);
 	} else if ((OPS & OPS_FILL_AA) && P.kind == PK_FILL_FAN) {
@@ -514,7 +514,7 @@ __device__ __forceinline__ void emitPiece(const PieceArgs& a, const JobCtx& J, c
 	}
 }
 
-template<class IDX, uint32_t OPS>
+template<class IDX, uint32_t OPS, int JT, int CT>
 __global__ void __launch_bounds__(PPB, VGB_EMIT_MIN_BLOCKS) k_piece_emit(PieceArgs a)
 {
 	constexpr uint32_t CI = CI_BYTES / sizeof(IDX);
@@ -545,7 +545,7 @@ __global__ void __launch_bounds__(PPB, VGB_EMIT_MIN_BLOCKS) k_piece_emit(PieceAr
 		uint32_t ps;
 		J = loadJob(a, o.j, &ps);
 		o.q = g - ps;
-		P = classify<OPS>(J, o.q, a.pts);
+		P = classify<OPS, JT, CT>(J, o.q, a.pts);
 		sTail[t] = packTail(P);
 	}
 	/* hand-over of the previous block's last piece (written by the count kernel) */
@@ -572,7 +572,8 @@ __global__ void __launch_bounds__(PPB, VGB_EMIT_MIN_BLOCKS) k_piece_emit(PieceAr
 		if (P.flags & PF_HAS_PREV) {
 			/* piece q-1 of the same job is owned by thread t-1 (or by the previous block's last thread) */
 			const uint32_t tw = t > 0 ? sTail[t - 1] : tail0;
-			prev = ((OPS & OPS_OTHER) && J.op != VGB_OP_STROKE_AA) ? ribbonOutFromTail(J, tw, F) : out4FromTail(J.cap, J.join, tw, F);
+			prev = ((OPS & OPS_OTHER) && J.op != VGB_OP_STROKE_AA) ? ribbonOutFromTail(J, tw, F)
+			                                                        : out4FromTail(CT < 3 ? (uint32_t)CT : J.cap, JT < 3 ? (uint32_t)JT : J.join, tw, F);
 		}
 	}
 	const uint32_t idxBase = sizeof(IDX) == 2 ? 0u : (uint32_t)(mo.x + a.vertexBase);
@@ -604,7 +605,7 @@ __global__ void __launch_bounds__(PPB, VGB_EMIT_MIN_BLOCKS) k_piece_emit(PieceAr
 				S.col = a.col + gv;
 				S.idx = reinterpret_cast<IDX*>(a.idx) + gi;
 				S.base = idxBase;
-				emitPiece<OPS>(a, J, P, F, prev, S);
+				emitPiece<OPS, JT, CT>(a, J, P, F, prev, S);
 			}
 			ta += 1;
 			__syncthreads();
@@ -618,7 +619,7 @@ __global__ void __launch_bounds__(PPB, VGB_EMIT_MIN_BLOCKS) k_piece_emit(PieceAr
 			S.col = sCol + shV4 + (vl - v0);
 			S.idx = sIdx + shI + (il - i0);
 			S.base = idxBase;
-			emitPiece<OPS>(a, J, P, F, prev, S);
+			emitPiece<OPS, JT, CT>(a, J, P, F, prev, S);
 		}
 		if (t < min(sCapCount, CAPMAX)) {
 			const CapRec R = sCap[t];
@@ -629,7 +630,7 @@ __global__ void __launch_bounds__(PPB, VGB_EMIT_MIN_BLOCKS) k_piece_emit(PieceAr
 				S.col = sCol + shV4 + (R.vl - v0);
 				S.idx = sIdx + shI + (R.il - i0);
 				S.base = R.base;
-				emitCapAA(R, S);
+				emitCapAA<CT>(R, S);
 			}
 		}
 		fenceProxyAsync(); /* generic-proxy writes above -> visible to the async (TMA) proxy */
@@ -704,6 +705,7 @@ public:
 	uint32_t numSub = 0, numJobs = 0, numDraws = 0, numPaths = 0;
 	uint32_t idxBytes = 2;
 	uint32_t opsMask = OPS_ALL; /* which ops the uploaded draws contain */
+	uint32_t uniCap = 3, uniJoin = 3; /* cap / join shared by every draw (3 = mixed): selects a specialised kernel */
 	vgb_sizes sz;
 	RunTimes rt;
 	uint32_t launches = 0;
@@ -775,8 +777,12 @@ public:
 			if (hasXform) rc |= up(dXform, t.pathXform, 6 * (size_t)t.numPaths, err);
 		}
 		opsMask = 0;
+		uniCap = uniJoin = 3;
 		for (uint32_t d = 0; d < t.numDraws; ++d) {
 			const uint32_t op = t.draws[d].ocj & 0xFF;
+			const uint32_t cap = (t.draws[d].ocj >> 8) & 0xFF, join = (t.draws[d].ocj >> 16) & 0xFF;
+			uniCap = d == 0 ? cap : (uniCap == cap ? cap : 3u);
+			uniJoin = d == 0 ? join : (uniJoin == join ? join : 3u);
 			opsMask |= (op == VGB_OP_STROKE_AA) ? OPS_STROKE_AA : (op == VGB_OP_CONVEX_FILL_AA ? OPS_FILL_AA : OPS_OTHER);
 		}
 		if (opsMask == 0 || (opsMask & (opsMask - 1))) opsMask = OPS_ALL; /* mixed batches use the general kernel */
@@ -904,9 +910,11 @@ public:
 			pa.blockBase = dBlockBase.as<ulonglong2>();
 			pa.meshOff = dMeshOff.as<ulonglong2>();
 			pa.vertexBase = vertexBase;
-			if (opsMask == OPS_STROKE_AA) k_piece_count<OPS_STROKE_AA><<<numBlocks, PPB, 0, st>>>(pa);
-			else if (opsMask == OPS_FILL_AA) k_piece_count<OPS_FILL_AA><<<numBlocks, PPB, 0, st>>>(pa);
-			else k_piece_count<OPS_ALL><<<numBlocks, PPB, 0, st>>>(pa);
+			if (opsMask == OPS_STROKE_AA && uniJoin == VGB_JOIN_ROUND && uniCap == VGB_CAP_ROUND) k_piece_count<OPS_STROKE_AA, 1, 1><<<numBlocks, PPB, 0, st>>>(pa);
+			else if (opsMask == OPS_STROKE_AA && uniJoin == VGB_JOIN_MITER && uniCap == VGB_CAP_BUTT) k_piece_count<OPS_STROKE_AA, 0, 0><<<numBlocks, PPB, 0, st>>>(pa);
+			else if (opsMask == OPS_STROKE_AA) k_piece_count<OPS_STROKE_AA, 3, 3><<<numBlocks, PPB, 0, st>>>(pa);
+			else if (opsMask == OPS_FILL_AA) k_piece_count<OPS_FILL_AA, 3, 3><<<numBlocks, PPB, 0, st>>>(pa);
+			else k_piece_count<OPS_ALL, 3, 3><<<numBlocks, PPB, 0, st>>>(pa);
 			++launches;
 			if (scan<ScanOps<uint2>>(dBlockTotals.as<uint2>(), numBlocks, dBlockBase.as<ulonglong2>(), err)) return VGB_ERR_CUDA;
 			if (scan<ScanOps<uint2>>(dMeshTotals.as<uint2>(), numJobs, dMeshOff.as<ulonglong2>(), err)) return VGB_ERR_CUDA;
@@ -927,9 +935,11 @@ public:
 			pa.idx = dIdx.p;
 #define VGB_LAUNCH_EMIT(T)                                                                                  \
 	do {                                                                                                    \
-		if (opsMask == OPS_STROKE_AA) k_piece_emit<T, OPS_STROKE_AA><<<numBlocks, PPB, 0, st>>>(pa);        \
-		else if (opsMask == OPS_FILL_AA) k_piece_emit<T, OPS_FILL_AA><<<numBlocks, PPB, 0, st>>>(pa);       \
-		else k_piece_emit<T, OPS_ALL><<<numBlocks, PPB, 0, st>>>(pa);                                       \
+		if (opsMask == OPS_STROKE_AA && uniJoin == VGB_JOIN_ROUND && uniCap == VGB_CAP_ROUND) k_piece_emit<T, OPS_STROKE_AA, 1, 1><<<numBlocks, PPB, 0, st>>>(pa); \
+		else if (opsMask == OPS_STROKE_AA && uniJoin == VGB_JOIN_MITER && uniCap == VGB_CAP_BUTT) k_piece_emit<T, OPS_STROKE_AA, 0, 0><<<numBlocks, PPB, 0, st>>>(pa); \
+		else if (opsMask == OPS_STROKE_AA) k_piece_emit<T, OPS_STROKE_AA, 3, 3><<<numBlocks, PPB, 0, st>>>(pa); \
+		else if (opsMask == OPS_FILL_AA) k_piece_emit<T, OPS_FILL_AA, 3, 3><<<numBlocks, PPB, 0, st>>>(pa); \
+		else k_piece_emit<T, OPS_ALL, 3, 3><<<numBlocks, PPB, 0, st>>>(pa);                                 \
 	} while (0)
 			if (idxBytes == 2) {
 				VGB_LAUNCH_EMIT(uint16_t);

@@ -81,8 +81,10 @@ __host__ __device__ __forceinline__ uint32_t pieceCount(uint32_t op, uint32_t N)
 }
 
 /* side test + arc subdivision of one join (stroker.cpp:1528-1535, 1581-1596, 1737-1752) */
+template<int JT>
 __device__ __forceinline__ void classifyJoinAA(const JobCtx& J, Piece& P)
 {
+	const uint32_t jt = JT < 3 ? (uint32_t)JT : J.join; /* compile-time join type when the whole batch shares it */
 	P.v = extrusion(P.d01, P.d12);
 	const float vx = P.v.x * J.hsw_aa;
 	const float vy = P.v.y * J.hsw_aa;
@@ -92,13 +94,13 @@ __device__ __forceinline__ void classifyJoinAA(const JobCtx& J, Piece& P)
 		P.flags |= PF_LEFT;
 	}
 	const uint32_t conn = (P.flags & PF_HAS_PREV) ? 18u : 0u;
-	if (J.join == VGB_JOIN_MITER) {
+	if (jt == VGB_JOIN_MITER) {
 		P.n = 0;
 		P.vcount = 4;
 		P.icount = conn;
 	} else {
 		uint32_t n = 1;
-		if (J.join == VGB_JOIN_ROUND) {
+		if (jt == VGB_JOIN_ROUND) {
 			/* left inner: r = perpCW(d), right inner: l = perpCCW(d) */
 			const float2 s01 = left ? f2(P.d01.y, -P.d01.x) : f2(-P.d01.y, P.d01.x);
 			const float2 s12 = left ? f2(P.d12.y, -P.d12.x) : f2(-P.d12.y, P.d12.x);
@@ -205,7 +207,7 @@ __device__ __forceinline__ void classifyRibbon(const JobCtx& J, uint32_t q, cons
 enum { OPS_STROKE_AA = 1, OPS_FILL_AA = 2, OPS_OTHER = 4, OPS_ALL = 7 };
 
 /* the single source of every count decision: piece q of job J */
-template<uint32_t OPS>
+template<uint32_t OPS, int JT = 3, int CT = 3>
 __device__ __forceinline__ Piece classify(const JobCtx& J, uint32_t q, const float2* __restrict__ pts)
 {
 	Piece P;
@@ -221,45 +223,39 @@ __device__ __forceinline__ Piece classify(const JobCtx& J, uint32_t q, const flo
 	const float2* v = pts + J.first;
 	const uint32_t N = J.N;
 	if ((OPS & OPS_STROKE_AA) && (!(OPS & ~OPS_STROKE_AA) || J.op == VGB_OP_STROKE_AA)) {
-		if (!J.closed && q == 0) {
-			P.kind = PK_CAP_START;
-			P.p = v[0];
-			P.d01 = vdir(P.p, v[1]);
-			if (J.cap == VGB_CAP_ROUND) {
+		/* one code path for the loads and both segment directions, whatever the piece is: a start
+		 * cap uses the outgoing direction, an end cap the incoming one (its other neighbour index is
+		 * clamped onto itself and gives the zero vector) */
+		const uint32_t ct = CT < 3 ? (uint32_t)CT : J.cap;
+		const bool open = !J.closed;
+		const bool isStart = open && q == 0, isEnd = open && q == N - 1;
+		const float2 pm = v[q > 0 ? q - 1 : (open ? 0u : N - 1)];
+		const float2 pn = v[q < N - 1 ? q + 1 : (open ? q : 0u)];
+		P.p = v[q];
+		const float2 dA = vdir(pm, P.p), dB = vdir(P.p, pn);
+		if (isStart || isEnd) {
+			P.kind = isStart ? PK_CAP_START : PK_CAP_END;
+			P.d01 = isStart ? dB : dA;
+			P.flags = isEnd ? PF_HAS_PREV : 0u;
+			if (ct == VGB_CAP_ROUND) {
 				P.n = J.nHC;
 				P.vcount = 2 * J.nHC;
-				P.icount = 9 * J.nHC - 12;
+				P.icount = isStart ? 9 * J.nHC - 12 : 9 * J.nHC + 6;
 			} else {
 				P.vcount = 4;
-				P.icount = 6;
-			}
-		} else if (!J.closed && q == N - 1) {
-			P.kind = PK_CAP_END;
-			P.p = v[N - 1];
-			P.d01 = vdir(v[N - 2], P.p);
-			P.flags = PF_HAS_PREV;
-			if (J.cap == VGB_CAP_ROUND) {
-				P.n = J.nHC;
-				P.vcount = 2 * J.nHC;
-				P.icount = 9 * J.nHC + 6;
-			} else {
-				P.vcount = 4;
-				P.icount = 24;
+				P.icount = isStart ? 6u : 24u;
 			}
 		} else {
 			P.kind = PK_JOIN;
-			const float2 pm = v[q == 0 ? N - 1 : q - 1];
-			const float2 pn = v[q == N - 1 ? 0 : q + 1];
-			P.p = v[q];
-			P.d01 = vdir(pm, P.p);
-			P.d12 = vdir(P.p, pn);
+			P.d01 = dA;
+			P.d12 = dB;
 			if (!(J.closed && q == 0)) {
 				P.flags |= PF_HAS_PREV;
 			}
 			if (J.closed && q == N - 1) {
 				P.flags |= PF_CLOSING;
 			}
-			classifyJoinAA(J, P);
+			classifyJoinAA<JT>(J, P);
 		}
 	} else if ((OPS & OPS_FILL_AA) && (!(OPS & ~OPS_FILL_AA) || J.op == VGB_OP_CONVEX_FILL_AA)) {
 		if (q < N - 2) {
@@ -421,10 +417,10 @@ struct CapRec
 /* start cap: stroker.cpp:1422-1515; end cap: 1858-1968.  An end cap is the start cap mirrored:
  * the along-segment offsets change sign (negation is exact) and every triangle swaps its 2nd
  * and 3rd index. */
-template<class SINK>
+template<int CT = 3, class SINK>
 __device__ __forceinline__ void emitCapAA(const CapRec& R, const SINK& S)
 {
-	const uint32_t capType = (R.info >> 16) & 0xFF;
+	const uint32_t capType = CT < 3 ? (uint32_t)CT : ((R.info >> 16) & 0xFF);
 	const bool isEnd = (R.info >> 24) != 0;
 	const float2 p0 = R.p, d = R.d;
 	const float2 l = f2(-d.y, d.x);
@@ -482,9 +478,10 @@ __device__ __forceinline__ void emitCapAA(const CapRec& R, const SINK& S)
 }
 
 /* stroker.cpp:1536-1847. firstLeft: side of the mesh's first join (closing connect only) */
-template<class SINK>
+template<int JT = 3, class SINK>
 __device__ __forceinline__ void emitJoinAA(const JobCtx& J, const Piece& P, uint32_t F, uint4 prev, bool firstLeft, const SINK& S)
 {
+	const uint32_t jt = JT < 3 ? (uint32_t)JT : J.join;
 	const bool left = (P.flags & PF_LEFT) != 0;
 	const float hsw = J.hsw, hsw_aa = J.hsw_aa;
 	const float2 p1 = P.p;
@@ -493,7 +490,7 @@ __device__ __forceinline__ void emitJoinAA(const JobCtx& J, const Piece& P, uint
 	const float vax = vs.x * hsw_aa, vay = vs.y * hsw_aa;
 	const float vx = vs.x * hsw, vy = vs.y * hsw;
 	uint32_t k = 0;
-	if (J.join == VGB_JOIN_MITER) {
+	if (jt == VGB_JOIN_MITER) {
 		S.VP(0, p1.x + vax, p1.y + vay, J.c0, p1.x + vx, p1.y + vy, J.color);
 		S.VP(2, p1.x - vx, p1.y - vy, J.color, p1.x - vax, p1.y - vay, J.c0);
 		if (P.flags & PF_HAS_PREV) {
@@ -509,7 +506,7 @@ __device__ __forceinline__ void emitJoinAA(const JobCtx& J, const Piece& P, uint
 		/* first arc vertex */
 		{
 			float ax = p1.x + s01.x * hsw, ay = p1.y + s01.y * hsw;
-			if (J.join == VGB_JOIN_BEVEL) {
+			if (jt == VGB_JOIN_BEVEL) {
 				const float cosAngle = fabsf(s01.x * s12.x + s01.y * s12.y);
 				const float t = cosAngle * J.fringe;
 				ax = ax - d01.x * t;
@@ -527,7 +524,7 @@ __device__ __forceinline__ void emitJoinAA(const JobCtx& J, const Piece& P, uint
 		/* last arc vertex */
 		{
 			float ax = p1.x + s12.x * hsw, ay = p1.y + s12.y * hsw;
-			if (J.join == VGB_JOIN_BEVEL) {
+			if (jt == VGB_JOIN_BEVEL) {
 				const float cosAngle = fabsf(s01.x * s12.x + s01.y * s12.y);
 				const float t = cosAngle * J.fringe;
 				ax = ax + d12.x * t;
@@ -550,7 +547,7 @@ __device__ __forceinline__ void emitJoinAA(const JobCtx& J, const Piece& P, uint
 	}
 	if (P.flags & PF_CLOSING) {
 		/* stroker.cpp:1970-1984: previous = this piece, first = piece 0 (its F is 0) */
-		S.connect(k, pieceOut4(J, P, F), joinIn4(firstLeft, 0));
+		S.connect(k, out4FromTail(0, jt, packTail(P), F + P.vcount), joinIn4(firstLeft, 0));
 	}
 }
 
