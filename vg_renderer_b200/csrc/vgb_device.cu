@@ -215,6 +215,7 @@ struct FlattenArgs
 template<bool EMIT>
 __global__ void __launch_bounds__(128) k_flatten(FlattenArgs a)
 {
+	__shared__ float sStack[10 * 6 * 128];
 	const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
 	if (s >= a.numSub) return;
 	const SubRec r = a.subRec[s];
@@ -227,6 +228,8 @@ __global__ void __launch_bounds__(128) k_flatten(FlattenArgs a)
 	w.m = (EMIT && a.pathXform) ? a.pathXform + 6 * (size_t)r.pathId : nullptr;
 	w.out = EMIT ? a.pts + a.subFirst[s] : nullptr;
 	w.limit = EMIT ? a.subNum[s] : 0u;
+	w.stk = sStack + threadIdx.x;
+	w.stride = 128;
 	w.run(a.cmd, r.cmdBegin, r.cmdEnd, a.data + r.dataBegin);
 	if (EMIT) {
 		a.subClosed[s] = w.closed ? 1 : 0;

@@ -83,13 +83,20 @@ struct SubPathWalker
 	}
 
 	/* pathCubicTo, src/path.cpp:86-182: left-first subdivision, at most 10 pending right
-	 * siblings; a non-flat node met with a full stack is dropped without a vertex. */
+	 * siblings; a non-flat node met with a full stack is dropped without a vertex.
+	 * The pending siblings live in SHARED memory, laid out [level][component][thread] so that a
+	 * warp's accesses are conflict-free (a per-thread local array would spill 320 B x 1M threads
+	 * through L1 into L2).  Consecutive pending siblings share an end point (P4 of entry k is P1
+	 * of entry k-1, the deepest entry ends at the curve's end point), so an entry stores 6 floats. */
+	float* stk;      /* this thread's column: stk[(level * 6 + c) * STRIDE] */
+	uint32_t stride;
+
 	__device__ void cubic(float c1x, float c1y, float c2x, float c2y, float x, float y)
 	{
-		float stack[10 * 8];
 		int sp = 0;
 		float x1 = lx, y1 = ly, x2 = c1x, y2 = c1y, x3 = c2x, y3 = c2y, x4 = x, y4 = y;
 		const float tessTol = tol / (scale * scale);
+		const uint32_t S = stride;
 		for (;;) {
 			const float dx = x4 - x1;
 			const float dy = y4 - y1;
@@ -100,28 +107,37 @@ struct SubPathWalker
 			if (flat) {
 				add(x4, y4);
 			}
-			if (!flat && sp < 80) {
+			if (!flat && sp < 10) {
 				const float x12 = (x1 + x2) * 0.5f, y12 = (y1 + y2) * 0.5f;
 				const float x23 = (x2 + x3) * 0.5f, y23 = (y2 + y3) * 0.5f;
 				const float x34 = (x3 + x4) * 0.5f, y34 = (y3 + y4) * 0.5f;
 				const float x123 = (x12 + x23) * 0.5f, y123 = (y12 + y23) * 0.5f;
 				const float x234 = (x23 + x34) * 0.5f, y234 = (y23 + y34) * 0.5f;
 				const float x1234 = (x123 + x234) * 0.5f, y1234 = (y123 + y234) * 0.5f;
-				stack[sp + 0] = x1234; stack[sp + 1] = y1234;
-				stack[sp + 2] = x234;  stack[sp + 3] = y234;
-				stack[sp + 4] = x34;   stack[sp + 5] = y34;
-				stack[sp + 6] = x4;    stack[sp + 7] = y4;
-				sp += 8;
+				/* pending right half (P1234, P234, P34, [P4 = current P4]) */
+				float* e = stk + (uint32_t)sp * 6u * S;
+				e[0] = x1234; e[S] = y1234;
+				e[2 * S] = x234; e[3 * S] = y234;
+				e[4 * S] = x34;  e[5 * S] = y34;
+				++sp;
 				x2 = x12; y2 = y12; x3 = x123; y3 = y123; x4 = x1234; y4 = y1234;
 			} else {
 				if (sp == 0) {
-					break; /* only reachable from a flat node: a non-flat root always has sp<80 */
+					break; /* only reachable from a flat node: a non-flat root always has sp<10 */
 				}
-				sp -= 8;
-				x1 = stack[sp + 0]; y1 = stack[sp + 1];
-				x2 = stack[sp + 2]; y2 = stack[sp + 3];
-				x3 = stack[sp + 4]; y3 = stack[sp + 5];
-				x4 = stack[sp + 6]; y4 = stack[sp + 7];
+				--sp;
+				const float* e = stk + (uint32_t)sp * 6u * S;
+				/* the popped sibling ends where the entry below it starts, or at the curve's end */
+				if (sp > 0) {
+					x4 = e[-6 * (int)S];
+					y4 = e[-5 * (int)S];
+				} else {
+					x4 = x;
+					y4 = y;
+				}
+				x1 = e[0]; y1 = e[S];
+				x2 = e[2 * S]; y2 = e[3 * S];
+				x3 = e[4 * S]; y3 = e[5 * S];
 			}
 		}
 	}
