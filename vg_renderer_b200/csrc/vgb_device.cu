@@ -438,9 +438,10 @@ __device__ __forceinline__ void bulkCommit() { asm volatile("cp.async.bulk.commi
 __device__ __forceinline__ void bulkWaitRead() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulkWaitAll() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
-/* lanes [laneBase, laneBase+16) of the block store the ragged ends; thread 0 issues the bulk body */
+/* one WARP streams one array: lane 0 issues (and later waits for) the bulk copy of the 16-byte
+ * aligned body, lanes 1..16 store the ragged head/tail (fewer than 16 bytes each) */
 template<class T>
-__device__ __forceinline__ void copyOut(T* __restrict__ gbase, uint64_t gs, uint32_t count, const T* sbuf, uint32_t laneBase)
+__device__ __forceinline__ void copyOutWarp(T* __restrict__ gbase, uint64_t gs, uint32_t count, const T* sbuf, uint32_t lane)
 {
 	constexpr uint32_t K = 16 / sizeof(T);
 	const uint64_t ge = gs + count;
@@ -448,18 +449,21 @@ __device__ __forceinline__ void copyOut(T* __restrict__ gbase, uint64_t gs, uint
 	uint64_t bodyBegin = (gs + K - 1) & ~(uint64_t)(K - 1);
 	uint64_t bodyEnd = ge & ~(uint64_t)(K - 1);
 	if (bodyEnd <= bodyBegin) {
-		bodyBegin = bodyEnd = ge; /* everything is ragged */
+		bodyBegin = bodyEnd = ge; /* everything is ragged (count < 2K) */
 	}
-	if (threadIdx.x == 0 && bodyEnd > bodyBegin) {
-		bulkStore(gbase + bodyBegin, sbuf + (bodyBegin - alignedBase), (uint32_t)((bodyEnd - bodyBegin) * sizeof(T)));
+	if (lane == 0) {
+		if (bodyEnd > bodyBegin) {
+			bulkStore(gbase + bodyBegin, sbuf + (bodyBegin - alignedBase), (uint32_t)((bodyEnd - bodyBegin) * sizeof(T)));
+		}
+		bulkCommit();
 	}
-	const uint32_t head = (uint32_t)((bodyBegin < ge ? bodyBegin : ge) - gs);
+	const uint32_t head = (uint32_t)(bodyBegin - gs);
 	const uint32_t tail = (uint32_t)(ge - bodyEnd);
-	const uint32_t l = threadIdx.x - laneBase;
+	const uint32_t l = lane - 1;
 	if (l < head) {
 		gbase[gs + l] = sbuf[(gs - alignedBase) + l];
-	} else if (l >= 8 && l - 8 < tail) {
-		gbase[bodyEnd + (l - 8)] = sbuf[(bodyEnd - alignedBase) + (l - 8)];
+	} else if (l >= 16 && l - 16 < tail) {
+		gbase[bodyEnd + (l - 16)] = sbuf[(bodyEnd - alignedBase) + (l - 16)];
 	}
 }
 
@@ -591,16 +595,25 @@ __global__ void __launch_bounds__(PPB, VGB_EMIT_MIN_BLOCKS) k_piece_emit(PieceAr
 		}
 	}
 
-	/* rounds: as many consecutive pieces as fit the staging buffers */
+	/* rounds: as many consecutive pieces as fit the staging buffers (one round in the common case) */
+	static_assert(PPB >= 128, "copy-out uses warps 1..3");
 	const uint32_t nThreads = min(PPB, a.numPieces - blockIdx.x * PPB);
+	const uint32_t warp = t >> 5, lane = t & 31;
+	const bool single = total.x <= CV && total.y <= CI; /* block-uniform */
 	uint32_t ta = 0;
 	while (ta < nThreads) {
 		const uint32_t v0 = sVl[ta], i0 = sIl[ta];
-		const bool fits = t >= ta && t < nThreads && (sVl[t + 1] - v0) <= CV && (sIl[t + 1] - i0) <= CI;
-		const uint32_t cnt = __syncthreads_count(fits);
+		uint32_t tb;
+		if (single) {
+			__syncthreads(); /* cap records written above -> readable by warp 0 */
+			tb = nThreads;
+		} else {
+			const bool fits = t >= ta && t < nThreads && (sVl[t + 1] - v0) <= CV && (sIl[t + 1] - i0) <= CI;
+			tb = ta + __syncthreads_count(fits);
+		}
 		const uint64_t gv = bb.x + v0; /* global element offsets of the round */
 		const uint64_t gi = bb.y + i0;
-		if (cnt == 0) {
+		if (tb == ta) {
 			/* a single piece larger than the staging buffers: its owner writes it straight to HBM */
 			if (t == ta) {
 				Sink<IDX, !(OPS & OPS_OTHER)> S;
@@ -614,7 +627,6 @@ __global__ void __launch_bounds__(PPB, VGB_EMIT_MIN_BLOCKS) k_piece_emit(PieceAr
 			__syncthreads();
 			continue;
 		}
-		const uint32_t tb = ta + cnt;
 		const uint32_t shV2 = (uint32_t)(gv & 1), shV4 = (uint32_t)(gv & 3), shI = (uint32_t)(gi & (KI - 1));
 		if (t >= ta && t < tb && !deferred) {
 			Sink<IDX, !(OPS & OPS_OTHER)> S;
@@ -639,22 +651,23 @@ __global__ void __launch_bounds__(PPB, VGB_EMIT_MIN_BLOCKS) k_piece_emit(PieceAr
 		fenceProxyAsync(); /* generic-proxy writes above -> visible to the async (TMA) proxy */
 		__syncthreads();
 		const uint32_t nv = sVl[tb] - v0, ni = sIl[tb] - i0;
-		copyOut<float2>(a.pos, gv, nv, sPos, 32);
-		copyOut<uint32_t>(a.col, gv, nv, sCol, 64);
-		copyOut<IDX>(reinterpret_cast<IDX*>(a.idx), gi, ni, sIdx, 96);
-		if (t == 0) {
-			bulkCommit();
+		if (warp == 1) {
+			copyOutWarp<float2>(a.pos, gv, nv, sPos, lane);
+		} else if (warp == 2) {
+			copyOutWarp<uint32_t>(a.col, gv, nv, sCol, lane);
+		} else if (warp == 3) {
+			copyOutWarp<IDX>(reinterpret_cast<IDX*>(a.idx), gi, ni, sIdx, lane);
 		}
 		ta = tb;
 		if (ta < nThreads) {
 			/* another round reuses the staging buffers: wait until the TMA has read them */
-			if (t == 0) {
+			if (warp >= 1 && lane == 0) {
 				bulkWaitRead();
 			}
 			__syncthreads();
 		}
 	}
-	if (t == 0) {
+	if (warp >= 1 && lane == 0) {
 		/* the CTA may retire once the TMA has READ the staging buffers; the global writes complete
 		 * asynchronously and are ordered before kernel completion */
 		bulkWaitRead();
