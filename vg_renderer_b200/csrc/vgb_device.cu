@@ -49,7 +49,7 @@ namespace vgb
 #define VGB_CI_BYTES 13312
 #endif
 #ifndef VGB_EMIT_MIN_BLOCKS
-#define VGB_EMIT_MIN_BLOCKS 6
+#define VGB_EMIT_MIN_BLOCKS 9
 #endif
 static constexpr uint32_t PPB = VGB_PPB;           /* pieces per block == threads per block   */
 static constexpr uint32_t CV = VGB_CV;             /* staged vertices per round               */
@@ -675,6 +675,166 @@ __global__ void __launch_bounds__(PPB, VGB_EMIT_MIN_BLOCKS) k_piece_emit(PieceAr
 }
 
 /* =========================================================================================
+ * warp-autonomous variants (VGB_GROUP32): the unit that owns a contiguous output range is a WARP
+ * (32 pieces) instead of a 128-thread block.  Offsets come from a shuffle scan, the hand-over
+ * from the previous lane (or the previous warp's tail word), the staging image is private to
+ * the warp and leaves through the warp's own bulk copies -- there is not a single block barrier,
+ * so a warp waiting on memory never holds its three siblings.
+ * ======================================================================================= */
+#ifndef VGB_GROUP32
+#define VGB_GROUP32 1
+#endif
+#ifndef VGB_CVW
+#define VGB_CVW 288
+#endif
+#ifndef VGB_CIW_BYTES
+#define VGB_CIW_BYTES 2560
+#endif
+static constexpr uint32_t GRP = VGB_GROUP32 ? 32u : PPB; /* pieces per offset group */
+static constexpr uint32_t CVW = VGB_CVW;                 /* staged vertices per warp */
+static constexpr uint32_t CIW_BYTES = VGB_CIW_BYTES;     /* staged index bytes per warp */
+
+__device__ __forceinline__ uint2 warpInclusive(uint2 v, uint32_t lane)
+{
+#pragma unroll
+	for (int d = 1; d < 32; d <<= 1) {
+		const uint32_t x = __shfl_up_sync(0xffffffffu, v.x, d);
+		const uint32_t y = __shfl_up_sync(0xffffffffu, v.y, d);
+		if (lane >= (uint32_t)d) {
+			v.x += x;
+			v.y += y;
+		}
+	}
+	return v;
+}
+
+template<uint32_t OPS, int JT, int CT>
+__global__ void __launch_bounds__(128) k_group_count(PieceArgs a)
+{
+	const uint32_t lane = threadIdx.x & 31;
+	const uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+	const uint32_t g = w * 32 + lane;
+	const bool valid = g < a.numPieces;
+	const uint32_t j = valid ? a.pieceJob[g] : 0;
+	uint32_t vc = 0, ic = 0, tail = 0;
+	if (valid) {
+		uint32_t ps;
+		const JobCtx J = loadJob(a, j, &ps);
+		const Piece P = classify<OPS, JT, CT>(J, g - ps, a.pts);
+		vc = P.vcount;
+		ic = P.icount;
+		tail = packTail(P);
+	}
+	{
+		const uint32_t key = valid ? j : 0xFFFFFFFFu;
+		const uint32_t m = __match_any_sync(0xffffffffu, key);
+		const uint32_t sv = __reduce_add_sync(m, vc);
+		const uint32_t si = __reduce_add_sync(m, ic);
+		if (valid && lane == (uint32_t)(__ffs(m) - 1)) {
+			atomicAdd(&a.meshTotals[j].x, sv);
+			atomicAdd(&a.meshTotals[j].y, si);
+		}
+	}
+	const uint32_t tv = __reduce_add_sync(0xffffffffu, vc);
+	const uint32_t ti = __reduce_add_sync(0xffffffffu, ic);
+	if (w * 32 < a.numPieces) {
+		if (lane == 0) {
+			a.blockTotals[w] = make_uint2(tv, ti);
+		}
+		if (lane == 31) {
+			a.blockTail[w] = tail;
+		}
+	}
+}
+
+template<class IDX, uint32_t OPS, int JT, int CT>
+__global__ void __launch_bounds__(128, VGB_EMIT_MIN_BLOCKS) k_group_emit(PieceArgs a)
+{
+	constexpr uint32_t CIW = CIW_BYTES / sizeof(IDX);
+	constexpr uint32_t KI = 16 / sizeof(IDX);
+	constexpr uint32_t POS_BYTES = (CVW + 2) * 8, COL_BYTES = (CVW + 4) * 4, IDX_BYTES = (CIW + KI) * sizeof(IDX);
+	constexpr uint32_t WBYTES = POS_BYTES + COL_BYTES + IDX_BYTES;
+	static_assert(POS_BYTES % 16 == 0 && COL_BYTES % 16 == 0 && IDX_BYTES % 16 == 0, "16-byte aligned staging streams");
+	__shared__ __align__(16) uint8_t sStage[4 * WBYTES];
+
+	const uint32_t lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+	const uint32_t w = blockIdx.x * 4 + wib;
+	const uint32_t g = w * 32 + lane;
+	if (w * 32 >= a.numPieces) {
+		return; /* whole warp out of range */
+	}
+	const bool valid = g < a.numPieces;
+	const uint32_t j = valid ? a.pieceJob[g] : 0;
+	JobCtx J;
+	Piece P;
+	P.kind = PK_NONE;
+	P.vcount = P.icount = 0;
+	P.flags = 0;
+	uint32_t q = 0;
+	if (valid) {
+		uint32_t ps;
+		J = loadJob(a, j, &ps);
+		q = g - ps;
+		P = classify<OPS, JT, CT>(J, q, a.pts);
+	}
+	const uint32_t myTail = valid ? packTail(P) : 0u;
+	uint32_t tw = __shfl_up_sync(0xffffffffu, myTail, 1);
+	if (lane == 0) {
+		tw = w > 0 ? a.blockTail[w - 1] : 0u;
+	}
+	const uint2 inc = warpInclusive(make_uint2(P.vcount, P.icount), lane);
+	const uint32_t vl = inc.x - P.vcount, il = inc.y - P.icount;
+	const uint32_t totV = __shfl_sync(0xffffffffu, inc.x, 31), totI = __shfl_sync(0xffffffffu, inc.y, 31);
+	const ulonglong2 bb = a.blockBase[w];
+	uint32_t F = 0;
+	ulonglong2 mo = make_ulonglong2(0, 0);
+	uint4 prev = make_uint4(0, 0, 0, 0);
+	if (valid) {
+		mo = a.meshOff[j];
+		F = (uint32_t)(bb.x + vl - mo.x);
+		if (P.flags & PF_HAS_PREV) {
+			prev = ((OPS & OPS_OTHER) && J.op != VGB_OP_STROKE_AA) ? ribbonOutFromTail(J, tw, F)
+			                                                        : out4FromTail(CT < 3 ? (uint32_t)CT : J.cap, JT < 3 ? (uint32_t)JT : J.join, tw, F);
+		}
+	}
+	const uint32_t idxBase = sizeof(IDX) == 2 ? 0u : (uint32_t)(mo.x + a.vertexBase);
+	const bool fits = totV <= CVW && totI <= CIW; /* warp-uniform */
+	uint8_t* stage = sStage + wib * WBYTES;
+	float2* sPos = reinterpret_cast<float2*>(stage);
+	uint32_t* sCol = reinterpret_cast<uint32_t*>(stage + POS_BYTES);
+	IDX* sIdx = reinterpret_cast<IDX*>(stage + POS_BYTES + COL_BYTES);
+	Sink<IDX, !(OPS & OPS_OTHER)> S;
+	S.base = idxBase;
+	if (fits) {
+		S.pos = sPos + (uint32_t)(bb.x & 1) + vl;
+		S.col = sCol + (uint32_t)(bb.x & 3) + vl;
+		S.idx = sIdx + (uint32_t)(bb.y & (KI - 1)) + il;
+	} else {
+		/* a warp whose pieces exceed the staging image writes straight to HBM */
+		S.pos = a.pos + bb.x + vl;
+		S.col = a.col + bb.x + vl;
+		S.idx = reinterpret_cast<IDX*>(a.idx) + bb.y + il;
+	}
+	const bool isCap = P.kind == PK_CAP_START || P.kind == PK_CAP_END;
+	if (valid && !isCap) {
+		emitPiece<OPS, JT, CT>(a, J, P, F, prev, S);
+	}
+	if (valid && isCap) {
+		emitPiece<OPS, JT, CT>(a, J, P, F, prev, S); /* the few cap lanes of the warp, after the joins */
+	}
+	if (fits) {
+		fenceProxyAsync();
+		__syncwarp();
+		copyOutWarp<float2>(a.pos, bb.x, totV, sPos, lane);
+		copyOutWarp<uint32_t>(a.col, bb.x, totV, sCol, lane);
+		copyOutWarp<IDX>(reinterpret_cast<IDX*>(a.idx), bb.y, totI, sIdx, lane);
+		if (lane == 0) {
+			bulkWaitRead();
+		}
+	}
+}
+
+/* =========================================================================================
  * host side
  * ======================================================================================= */
 struct DevBuf
@@ -900,7 +1060,8 @@ public:
 			if (scan<ScanOps<uint32_t>>(dJobPieces.as<uint32_t>(), numJobs, dPieceStart.as<uint32_t>(), err)) return VGB_ERR_CUDA;
 			if (readback(&numPieces, dPieceStart.as<uint32_t>() + numJobs, 4, err)) return VGB_ERR_CUDA;
 		}
-		const uint32_t numBlocks = (numPieces + PPB - 1) / PPB;
+		const uint32_t numBlocks = (numPieces + GRP - 1) / GRP;          /* offset groups (warps or blocks) */
+		const uint32_t gridBlocks = (numPieces + PPB - 1) / PPB;         /* 128-thread launch blocks      */
 		uint64_t totals[2] = {0, 0};
 		if (dMeshOff.ensure((size_t)(numJobs + 1) * 16, err)) return VGB_ERR_CUDA;
 		PieceArgs pa;
@@ -926,11 +1087,17 @@ public:
 			pa.blockBase = dBlockBase.as<ulonglong2>();
 			pa.meshOff = dMeshOff.as<ulonglong2>();
 			pa.vertexBase = vertexBase;
-			if (opsMask == OPS_STROKE_AA && uniJoin == VGB_JOIN_ROUND && uniCap == VGB_CAP_ROUND) k_piece_count<OPS_STROKE_AA, 1, 1><<<numBlocks, PPB, 0, st>>>(pa);
-			else if (opsMask == OPS_STROKE_AA && uniJoin == VGB_JOIN_MITER && uniCap == VGB_CAP_BUTT) k_piece_count<OPS_STROKE_AA, 0, 0><<<numBlocks, PPB, 0, st>>>(pa);
-			else if (opsMask == OPS_STROKE_AA) k_piece_count<OPS_STROKE_AA, 3, 3><<<numBlocks, PPB, 0, st>>>(pa);
-			else if (opsMask == OPS_FILL_AA) k_piece_count<OPS_FILL_AA, 3, 3><<<numBlocks, PPB, 0, st>>>(pa);
-			else k_piece_count<OPS_ALL, 3, 3><<<numBlocks, PPB, 0, st>>>(pa);
+#if VGB_GROUP32
+#define VGB_COUNT_K k_group_count
+#else
+#define VGB_COUNT_K k_piece_count
+#endif
+			if (opsMask == OPS_STROKE_AA && uniJoin == VGB_JOIN_ROUND && uniCap == VGB_CAP_ROUND) VGB_COUNT_K<OPS_STROKE_AA, 1, 1><<<gridBlocks, PPB, 0, st>>>(pa);
+			else if (opsMask == OPS_STROKE_AA && uniJoin == VGB_JOIN_MITER && uniCap == VGB_CAP_BUTT) VGB_COUNT_K<OPS_STROKE_AA, 0, 0><<<gridBlocks, PPB, 0, st>>>(pa);
+			else if (opsMask == OPS_STROKE_AA) VGB_COUNT_K<OPS_STROKE_AA, 3, 3><<<gridBlocks, PPB, 0, st>>>(pa);
+			else if (opsMask == OPS_FILL_AA) VGB_COUNT_K<OPS_FILL_AA, 3, 3><<<gridBlocks, PPB, 0, st>>>(pa);
+			else VGB_COUNT_K<OPS_ALL, 3, 3><<<gridBlocks, PPB, 0, st>>>(pa);
+#undef VGB_COUNT_K
 			++launches;
 			if (scan<ScanOps<uint2>>(dBlockTotals.as<uint2>(), numBlocks, dBlockBase.as<ulonglong2>(), err)) return VGB_ERR_CUDA;
 			if (scan<ScanOps<uint2>>(dMeshTotals.as<uint2>(), numJobs, dMeshOff.as<ulonglong2>(), err)) return VGB_ERR_CUDA;
@@ -949,13 +1116,18 @@ public:
 			pa.pos = dPos.as<float2>();
 			pa.col = dCol.as<uint32_t>();
 			pa.idx = dIdx.p;
+#if VGB_GROUP32
+#define VGB_EMIT_K k_group_emit
+#else
+#define VGB_EMIT_K k_piece_emit
+#endif
 #define VGB_LAUNCH_EMIT(T)                                                                                  \
 	do {                                                                                                    \
-		if (opsMask == OPS_STROKE_AA && uniJoin == VGB_JOIN_ROUND && uniCap == VGB_CAP_ROUND) k_piece_emit<T, OPS_STROKE_AA, 1, 1><<<numBlocks, PPB, 0, st>>>(pa); \
-		else if (opsMask == OPS_STROKE_AA && uniJoin == VGB_JOIN_MITER && uniCap == VGB_CAP_BUTT) k_piece_emit<T, OPS_STROKE_AA, 0, 0><<<numBlocks, PPB, 0, st>>>(pa); \
-		else if (opsMask == OPS_STROKE_AA) k_piece_emit<T, OPS_STROKE_AA, 3, 3><<<numBlocks, PPB, 0, st>>>(pa); \
-		else if (opsMask == OPS_FILL_AA) k_piece_emit<T, OPS_FILL_AA, 3, 3><<<numBlocks, PPB, 0, st>>>(pa); \
-		else k_piece_emit<T, OPS_ALL, 3, 3><<<numBlocks, PPB, 0, st>>>(pa);                                 \
+		if (opsMask == OPS_STROKE_AA && uniJoin == VGB_JOIN_ROUND && uniCap == VGB_CAP_ROUND) VGB_EMIT_K<T, OPS_STROKE_AA, 1, 1><<<gridBlocks, PPB, 0, st>>>(pa); \
+		else if (opsMask == OPS_STROKE_AA && uniJoin == VGB_JOIN_MITER && uniCap == VGB_CAP_BUTT) VGB_EMIT_K<T, OPS_STROKE_AA, 0, 0><<<gridBlocks, PPB, 0, st>>>(pa); \
+		else if (opsMask == OPS_STROKE_AA) VGB_EMIT_K<T, OPS_STROKE_AA, 3, 3><<<gridBlocks, PPB, 0, st>>>(pa); \
+		else if (opsMask == OPS_FILL_AA) VGB_EMIT_K<T, OPS_FILL_AA, 3, 3><<<gridBlocks, PPB, 0, st>>>(pa); \
+		else VGB_EMIT_K<T, OPS_ALL, 3, 3><<<gridBlocks, PPB, 0, st>>>(pa);                                 \
 	} while (0)
 			if (idxBytes == 2) {
 				VGB_LAUNCH_EMIT(uint16_t);
@@ -963,6 +1135,7 @@ public:
 				VGB_LAUNCH_EMIT(uint32_t);
 			}
 #undef VGB_LAUNCH_EMIT
+#undef VGB_EMIT_K
 			++launches;
 			VGB_CUDA(cudaGetLastError());
 		}
