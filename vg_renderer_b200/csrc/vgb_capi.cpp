@@ -55,6 +55,7 @@ struct vgb_batch
 	std::vector<uint8_t> cmd;
 	std::vector<float> data;
 	std::vector<SubRec> subs;
+	std::vector<uint32_t> slotFirst; /* built at upload: point-slot prefix per sub-path */
 	std::vector<float> pathScale, pathTol, pathXform;
 	bool anyXform = false;
 	std::vector<DrawRec> draws;
@@ -474,6 +475,35 @@ int vgb_batch_upload(vgb_batch* b)
 		t.rawClosed = b->rawClosed.data();
 		t.numSub = (uint32_t)b->rawFirst.size();
 	} else {
+		/* point slots for the single-pass flatten: a generous per-command estimate; a sub-path that
+		 * outgrows its slot is re-flattened into an overflow arena on the device, so the estimate
+		 * only affects memory and speed, never results */
+		static const uint32_t kSlot[VGB_CMD__COUNT] = {1, 1, 48, 48, 80, 4, 200, 200, 160, 160, 80, 0, 0};
+		const size_t ns = b->subs.size();
+		b->slotFirst.resize(ns + 1);
+		uint64_t acc = 0;
+		for (size_t i = 0; i < ns; ++i) {
+			b->slotFirst[i] = (uint32_t)acc;
+			const SubRec& r = b->subs[i];
+			uint32_t cap = 2;
+			const float* d = b->data.data() + r.dataBegin;
+			for (uint32_t c = r.cmdBegin; c < r.cmdEnd; ++c) {
+				const uint8_t ty = b->cmd[c];
+				if (ty == VGB_CMD_POLYLINE) {
+					uint32_t np;
+					memcpy(&np, d, 4);
+					cap += np;
+					d += 1 + 2 * (size_t)np;
+				} else {
+					cap += kSlot[ty];
+					static const uint8_t kArity[VGB_CMD__COUNT] = {2, 2, 6, 4, 5, 4, 5, 8, 3, 4, 6, 0, 0};
+					d += kArity[ty];
+				}
+			}
+			acc += cap;
+		}
+		b->slotFirst[ns] = (uint32_t)acc;
+		t.subSlotFirst = acc < 0xE0000000ull ? b->slotFirst.data() : nullptr;
 		t.subRec = b->subs.data();
 		t.numSub = (uint32_t)b->subs.size();
 		t.cmd = b->cmd.data();

@@ -26,6 +26,7 @@
 
 #include <cuda_runtime.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 namespace vgb
@@ -235,6 +236,80 @@ __global__ void __launch_bounds__(128) k_flatten(FlattenArgs a)
 		a.subClosed[s] = w.closed ? 1 : 0;
 	} else {
 		a.subNum[s] = w.n;
+	}
+}
+
+/* Single-pass flatten: every sub-path owns a slot of the point buffer sized by the recorder, so
+ * one walk both counts and stores -- no count pass, no scan, no size read-back.  A sub-path that
+ * outgrows its slot (the walk keeps counting past the slot's end) claims space in an overflow
+ * arena with one atomicAdd and walks again; the point buffer is therefore not dense, which is
+ * fine because everything downstream addresses points through (subFirst, subNum). */
+struct SlotArgs
+{
+	FlattenArgs f;
+	const uint32_t* slotFirst; /* numSub + 1 */
+	uint32_t* subFirstOut;
+	uint32_t arenaBase, arenaCap;
+	uint32_t* counters; /* [0] arena cursor, [1] overflow-error flag, [2] total points */
+};
+
+__global__ void __launch_bounds__(128) k_flatten_slots(SlotArgs a)
+{
+	__shared__ float sStack[10 * 6 * 128];
+	const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+	uint32_t n = 0;
+	if (s < a.f.numSub) {
+		const SubRec r = a.f.subRec[s];
+		uint32_t first = a.slotFirst[s];
+		uint32_t cap = a.slotFirst[s + 1] - first;
+		bool closed = false;
+		for (int pass = 0; pass < 2; ++pass) {
+			SubPathWalker<true> w;
+			w.lx = w.ly = w.px = w.py = w.fx = w.fy = 0.0f;
+			w.n = 0;
+			w.closed = false;
+			w.scale = a.f.pathScale[r.pathId];
+			w.tol = a.f.pathTol[r.pathId];
+			w.m = a.f.pathXform ? a.f.pathXform + 6 * (size_t)r.pathId : nullptr;
+			w.out = a.f.pts + first;
+			w.limit = cap;
+			w.stk = sStack + threadIdx.x;
+			w.stride = 128;
+			w.run(a.f.cmd, r.cmdBegin, r.cmdEnd, a.f.data + r.dataBegin);
+			n = w.n;
+			closed = w.closed;
+			if (n <= cap) {
+				break;
+			}
+			/* slot too small: claim n points of the arena and walk once more */
+			const uint32_t base = atomicAdd(&a.counters[0], n);
+			if (pass == 1 || base + n > a.arenaCap) {
+				atomicOr(&a.counters[1], 1u);
+				n = 0;
+				break;
+			}
+			first = a.arenaBase + base;
+			cap = n;
+		}
+		a.subFirstOut[s] = first;
+		a.f.subNum[s] = n;
+		a.f.subClosed[s] = closed ? 1 : 0;
+	}
+	const uint32_t tot = __reduce_add_sync(0xffffffffu, n);
+	if ((threadIdx.x & 31) == 0 && tot) {
+		atomicAdd(&a.counters[2], tot);
+	}
+}
+
+/* dense copy of a slotted point buffer (only for reading paths back: download_paths) */
+__global__ void k_gather_points(const float2* __restrict__ pts, const uint32_t* __restrict__ subFirst, const uint32_t* __restrict__ subNum,
+                                const uint32_t* __restrict__ denseFirst, uint32_t numSub, float2* __restrict__ out)
+{
+	const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+	if (s >= numSub) return;
+	const uint32_t f = subFirst[s], n = subNum[s], d = denseFirst[s];
+	for (uint32_t i = 0; i < n; ++i) {
+		out[d + i] = pts[f + i];
 	}
 }
 
@@ -873,6 +948,10 @@ public:
 	/* intermediates */
 	DevBuf dSubNum, dSubFirst, dSubClosed, dPts, dDD, dJobPieces, dPieceStart, dJobRec, dPieceJob;
 	DevBuf dBlockTotals, dBlockBase, dMeshTotals, dMeshOff, dScanTmp, dBlockTail;
+	DevBuf dSlotFirst, dCounters, dDenseFirst, dDensePts;
+	bool slotMode = false;   /* single-pass flatten into recorder-sized slots */
+	bool slotsUsed = false;  /* the last run's point buffer is slotted (not dense) */
+	uint32_t totalSlots = 0;
 	/* outputs */
 	DevBuf dPos, dCol, dIdx;
 	void* hPinned = nullptr; /* small pinned readback area */
@@ -891,7 +970,7 @@ public:
 		cudaSetDevice(dev);
 		DevBuf* all[] = {&dSubRec, &dCmd, &dData, &dScale, &dTol, &dXform, &dDraws, &dJobSub, &dJobDraw, &dSubNum, &dSubFirst,
 		                 &dSubClosed, &dPts, &dDD, &dJobPieces, &dPieceStart, &dJobRec, &dPieceJob, &dBlockTotals, &dBlockBase,
-		                 &dMeshTotals, &dMeshOff, &dScanTmp, &dBlockTail, &dPos, &dCol, &dIdx};
+		                 &dMeshTotals, &dMeshOff, &dScanTmp, &dBlockTail, &dSlotFirst, &dCounters, &dDenseFirst, &dDensePts, &dPos, &dCol, &dIdx};
 		for (DevBuf* b : all) b->release();
 		for (auto& e : ev) if (e) cudaEventDestroy(e);
 		for (auto& e : userEv) if (e) cudaEventDestroy(e);
@@ -933,6 +1012,7 @@ public:
 		VGB_CUDA(cudaSetDevice(dev));
 		ht = t;
 		rawMode = t.rawPts != nullptr;
+		slotMode = false;
 		numSub = t.numSub;
 		numJobs = t.numJobs;
 		numDraws = t.numDraws;
@@ -951,6 +1031,11 @@ public:
 			rc |= up(dCmd, t.cmd, t.numCmd, err);
 			rc |= up(dData, t.data, t.numData, err);
 			if (hasXform) rc |= up(dXform, t.pathXform, 6 * (size_t)t.numPaths, err);
+			slotMode = t.subSlotFirst != nullptr && t.numSub > 0 && getenv("VGB_TWO_PASS_FLATTEN") == nullptr;
+			if (slotMode) {
+				totalSlots = t.subSlotFirst[t.numSub];
+				rc |= up(dSlotFirst, t.subSlotFirst, (size_t)t.numSub + 1, err);
+			}
 		}
 		opsMask = 0;
 		uniCap = uniJoin = 3;
@@ -1033,15 +1118,35 @@ public:
 			fa.subClosed = dSubClosed.as<uint8_t>();
 			fa.pts = nullptr;
 			const uint32_t fb = (numSub + 127) / 128;
-			k_flatten<false><<<fb, 128, 0, st>>>(fa);
-			++launches;
-			if (scan<ScanOps<uint32_t>>(dSubNum.as<uint32_t>(), numSub, dSubFirst.as<uint32_t>(), err)) return VGB_ERR_CUDA;
-			if (readback(&numPts, dSubFirst.as<uint32_t>() + numSub, 4, err)) return VGB_ERR_CUDA;
-			if (dPts.ensure((size_t)numPts * 8 + 16, err)) return VGB_ERR_CUDA;
-			fa.pts = dPts.as<float2>();
-			k_flatten<true><<<fb, 128, 0, st>>>(fa);
-			++launches;
-			VGB_CUDA(cudaGetLastError());
+			slotsUsed = false;
+			if (slotMode) {
+				const uint32_t arenaCap = totalSlots / 2 + (1u << 20);
+				if (dPts.ensure(((size_t)totalSlots + arenaCap) * 8 + 16, err) || dCounters.ensure(16, err)) return VGB_ERR_CUDA;
+				VGB_CUDA(cudaMemsetAsync(dCounters.p, 0, 16, st));
+				SlotArgs sa;
+				fa.pts = dPts.as<float2>();
+				sa.f = fa;
+				sa.slotFirst = dSlotFirst.as<uint32_t>();
+				sa.subFirstOut = dSubFirst.as<uint32_t>();
+				sa.arenaBase = totalSlots;
+				sa.arenaCap = arenaCap;
+				sa.counters = dCounters.as<uint32_t>();
+				k_flatten_slots<<<fb, 128, 0, st>>>(sa);
+				++launches;
+				VGB_CUDA(cudaGetLastError());
+				slotsUsed = true;
+				numPts = 0xFFFFFFFFu; /* read back later together with the piece count */
+			} else {
+				k_flatten<false><<<fb, 128, 0, st>>>(fa);
+				++launches;
+				if (scan<ScanOps<uint32_t>>(dSubNum.as<uint32_t>(), numSub, dSubFirst.as<uint32_t>(), err)) return VGB_ERR_CUDA;
+				if (readback(&numPts, dSubFirst.as<uint32_t>() + numSub, 4, err)) return VGB_ERR_CUDA;
+				if (dPts.ensure((size_t)numPts * 8 + 16, err)) return VGB_ERR_CUDA;
+				fa.pts = dPts.as<float2>();
+				k_flatten<true><<<fb, 128, 0, st>>>(fa);
+				++launches;
+				VGB_CUDA(cudaGetLastError());
+			}
 		}
 		sz.num_points = numPts;
 		VGB_CUDA(cudaEventRecord(ev[1], st));
@@ -1059,6 +1164,18 @@ public:
 			launches += 2;
 			if (scan<ScanOps<uint32_t>>(dJobPieces.as<uint32_t>(), numJobs, dPieceStart.as<uint32_t>(), err)) return VGB_ERR_CUDA;
 			if (readback(&numPieces, dPieceStart.as<uint32_t>() + numJobs, 4, err)) return VGB_ERR_CUDA;
+		}
+		if (slotsUsed) {
+			uint32_t c[4];
+			if (readback(c, dCounters.p, 16, err)) return VGB_ERR_CUDA;
+			if (c[1]) {
+				/* the overflow arena was too small: redo this run with the two-pass flatten */
+				slotMode = false;
+				const int rc = run(flags, vertexBase, err);
+				return rc;
+			}
+			numPts = c[2];
+			sz.num_points = numPts;
 		}
 		const uint32_t numBlocks = (numPieces + GRP - 1) / GRP;          /* offset groups (warps or blocks) */
 		const uint32_t gridBlocks = (numPieces + PPB - 1) / PPB;         /* 128-thread launch blocks      */
@@ -1238,11 +1355,23 @@ public:
 			if (err) *err = "capacity too small";
 			return VGB_ERR_CAPACITY;
 		}
-		if (pts && sz.num_points) VGB_CUDA(cudaMemcpyAsync(pts, dPts.p, sz.num_points * 8, cudaMemcpyDeviceToHost, st));
+		const void* srcPts = dPts.p;
+		const void* srcFirst = dSubFirst.p;
+		if (slotsUsed && numSub) {
+			/* the run used the slotted (non-dense) point buffer: hand out a dense copy, in sub-path order */
+			if (dDenseFirst.ensure((size_t)(numSub + 1) * 4, err) || dDensePts.ensure(sz.num_points * 8 + 16, err)) return VGB_ERR_CUDA;
+			if (scan<ScanOps<uint32_t>>(dSubNum.as<uint32_t>(), numSub, dDenseFirst.as<uint32_t>(), err)) return VGB_ERR_CUDA;
+			k_gather_points<<<(numSub + 127) / 128, 128, 0, st>>>(dPts.as<float2>(), dSubFirst.as<uint32_t>(), dSubNum.as<uint32_t>(),
+			                                                       dDenseFirst.as<uint32_t>(), numSub, dDensePts.as<float2>());
+			VGB_CUDA(cudaGetLastError());
+			srcPts = dDensePts.p;
+			srcFirst = dDenseFirst.p;
+		}
+		if (pts && sz.num_points) VGB_CUDA(cudaMemcpyAsync(pts, srcPts, sz.num_points * 8, cudaMemcpyDeviceToHost, st));
 		if (subs && numSub) {
 			std::vector<uint32_t> f(numSub), n(numSub);
 			std::vector<uint8_t> c(numSub);
-			VGB_CUDA(cudaMemcpyAsync(f.data(), dSubFirst.p, (size_t)numSub * 4, cudaMemcpyDeviceToHost, st));
+			VGB_CUDA(cudaMemcpyAsync(f.data(), srcFirst, (size_t)numSub * 4, cudaMemcpyDeviceToHost, st));
 			VGB_CUDA(cudaMemcpyAsync(n.data(), dSubNum.p, (size_t)numSub * 4, cudaMemcpyDeviceToHost, st));
 			VGB_CUDA(cudaMemcpyAsync(c.data(), dSubClosed.p, (size_t)numSub, cudaMemcpyDeviceToHost, st));
 			VGB_CUDA(cudaStreamSynchronize(st));

@@ -57,6 +57,9 @@ struct HostTables
 	const float* pathTol = nullptr;
 	const float* pathXform = nullptr; /* nullable: identity for every path */
 	uint32_t numPaths = 0;
+	/* single-pass flatten: sub-path s owns point slots [subSlotFirst[s], subSlotFirst[s+1]) sized from
+	 * its commands by the recorder (numSub+1 entries; nullptr = always use the two-pass flatten) */
+	const uint32_t* subSlotFirst = nullptr;
 	/* raw-polyline mode (strokerXXX on caller polylines): replaces the flatten stage */
 	const float* rawPts = nullptr;
 	uint32_t numRawPts = 0;
