@@ -107,9 +107,10 @@ def test_config4_rounded_rect_fills(gpu_batch, ref, r):
     check_same(out, exp)
 
 
+@pytest.mark.parametrize("width", [6.0, 3.0])  # 3.0: 3*da > pi, the count kernel's geometry-free shortcut and its fallbacks
 @pytest.mark.parametrize("closed", [False, True])
 @pytest.mark.parametrize("cap,join", CAPJOIN)
-def test_polyline_edge_cases_stroke_aa(gpu_batch, ref, cap, join, closed):
+def test_polyline_edge_cases_stroke_aa(gpu_batch, ref, cap, join, closed, width):
     """raw polylines straight into the stroker (strokerPolylineStrokeAA), per-mesh compare"""
     cases = polyline_cases()
     pts = np.concatenate([np.asarray(c[1], np.float32) for c in cases])
@@ -117,11 +118,11 @@ def test_polyline_edge_cases_stroke_aa(gpu_batch, ref, cap, join, closed):
     first = np.concatenate([[0], np.cumsum(num)[:-1]]).astype(np.uint32)
     gpu_batch.reset(1.0)
     gpu_batch.set_polylines(pts, first, num, np.full(len(cases), closed, np.uint8))
-    gpu_batch.draw_all(vgb.OP_STROKE_AA, 0x80FF8040, 6.0, cap, join)
+    gpu_batch.draw_all(vgb.OP_STROKE_AA, 0x80FF8040, width, cap, join)
     gpu_batch.run()
     out = gpu_batch.download()
     for m, (name, c) in enumerate(cases):
-        pos, col, idx = ref.mesh(vgb.OP_STROKE_AA, c, closed, 0x80FF8040, 6.0, cap, join)
+        pos, col, idx = ref.mesh(vgb.OP_STROKE_AA, c, closed, 0x80FF8040, width, cap, join)
         v0, v1 = int(out["mesh_vtx_off"][m]), int(out["mesh_vtx_off"][m + 1])
         i0, i1 = int(out["mesh_idx_off"][m]), int(out["mesh_idx_off"][m + 1])
         assert (v1 - v0, i1 - i0) == (len(pos), len(idx)), name

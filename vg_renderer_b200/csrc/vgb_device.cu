@@ -338,6 +338,9 @@ __global__ void k_draw_prep(const DrawRec* __restrict__ draws, uint32_t n, const
 		o.hsw_aa = o.hsw + fringe;
 		o.da = vgb_acos((scale * o.hsw) / ((scale * o.hsw) + tol)) * 2.0f;
 		o.nHC = vgb_umax(2u, (uint32_t)vgb_ceil(VGB_PI / o.da));
+		if (3.0f * o.da > VGB_PI + 1e-3f) {
+			o.ocj |= 1u << 24; /* nfix: see quickCountAA */
+		}
 	} else if (op == VGB_OP_STROKE) {
 		/* stroker.cpp:1012-1014; hsw_aa carries the side-test scale (v * hsw, 1096-1099) */
 		o.hsw = r.width * 0.5f;
@@ -383,7 +386,7 @@ __global__ void __launch_bounds__(256) k_job_prep(const uint32_t* __restrict__ j
 		r.first = subFirst[sp];
 		r.N = subNum[sp];
 		const uint32_t op = d.ocj & 0xFF, cap = (d.ocj >> 8) & 0xFF, join = (d.ocj >> 16) & 0xFF;
-		r.flags = (uint32_t)subClosed[sp] | (op << 8) | (cap << 16) | (join << 24);
+		r.flags = (uint32_t)(subClosed[sp] & 1) | (((d.ocj >> 24) & 1u) << 1) | (op << 8) | (cap << 16) | (join << 24);
 		ps = pieceStart[j];
 		pe = pieceStart[j + 1];
 		r.pieceStart = ps;
@@ -434,7 +437,8 @@ __device__ __forceinline__ JobCtx loadJob(const PieceArgs& a, uint32_t j, uint32
 	JobCtx J;
 	J.first = r0.x;
 	J.N = r0.y;
-	J.closed = r0.z & 0xFF;
+	J.closed = r0.z & 1u;
+	J.nfix = (r0.z >> 1) & 1u;
 	J.op = (r0.z >> 8) & 0xFF;
 	J.cap = (r0.z >> 16) & 0xFF;
 	J.join = r0.z >> 24;
@@ -795,7 +799,10 @@ __global__ void __launch_bounds__(128) k_group_count(PieceArgs a)
 	if (valid) {
 		uint32_t ps;
 		const JobCtx J = loadJob(a, j, &ps);
-		const Piece P = classify<OPS, JT, CT>(J, g - ps, a.pts);
+		Piece P;
+		if (!((OPS & OPS_STROKE_AA) && (!(OPS & ~OPS_STROKE_AA) || J.op == VGB_OP_STROKE_AA) && quickCountAA<JT, CT>(J, g - ps, a.pts, lane == 31, P))) {
+			P = classify<OPS, JT, CT>(J, g - ps, a.pts);
+		}
 		vc = P.vcount;
 		ic = P.icount;
 		tail = packTail(P);

@@ -31,6 +31,7 @@ enum { PF_LEFT = 1, PF_HAS_PREV = 2, PF_CLOSING = 4 };
 struct JobCtx
 {
 	uint32_t first, N, closed;
+	uint32_t nfix; /* round joins of this job always have n == 2 when the turn is unambiguous (3*da > pi) */
 	uint32_t op, cap, join;
 	float hsw, hsw_aa, da, fringe;
 	uint32_t nHC, color, c0;
@@ -205,6 +206,72 @@ __device__ __forceinline__ void classifyRibbon(const JobCtx& J, uint32_t q, cons
 
 /* ops present in a batch (kernel template parameter: code for absent ops is compiled out) */
 enum { OPS_STROKE_AA = 1, OPS_FILL_AA = 2, OPS_OTHER = 4, OPS_ALL = 7 };
+
+/*
+ * Count-only shortcut for AA strokes (k_group_count).  Sizes of caps, miter and bevel joins do not
+ * depend on geometry; a round join has n = max(2, uint(theta / da)) with theta the turning angle
+ * <= pi, so when 3*da > pi (J.nfix, decided in k_draw_prep: strokes thinner than ~4.2 px at the
+ * default tolerance) n == 2 -- PROVIDED the reference's side test and its atan2 ordering agree,
+ * which is certain when the turn is unambiguous: |sin(theta)| > 1e-3 and both segments longer than
+ * the epsilon below which vec2Dir returns zero.  Then the side is the sign of the raw cross
+ * product as well.  Anything else (near-collinear, hairpin, degenerate) returns false and takes
+ * the full classify(), so counts stay bit-exact.  needSide: the caller needs PF_LEFT (the warp's
+ * last lane publishes the hand-over word).
+ */
+template<int JT, int CT>
+__device__ __forceinline__ bool quickCountAA(const JobCtx& J, uint32_t q, const float2* __restrict__ pts, bool needSide, Piece& P)
+{
+	const uint32_t jt = JT < 3 ? (uint32_t)JT : J.join;
+	const uint32_t ct = CT < 3 ? (uint32_t)CT : J.cap;
+	if (jt == VGB_JOIN_ROUND && !J.nfix) {
+		return false;
+	}
+	const uint32_t N = J.N;
+	const bool open = !J.closed;
+	const bool isStart = open && q == 0, isEnd = open && q == N - 1;
+	P.kind = PK_JOIN;
+	P.flags = 0;
+	P.li = q;
+	if (isStart || isEnd) {
+		P.kind = isStart ? PK_CAP_START : PK_CAP_END;
+		P.flags = isEnd ? PF_HAS_PREV : 0u;
+		if (ct == VGB_CAP_ROUND) {
+			P.n = J.nHC;
+			P.vcount = 2 * J.nHC;
+			P.icount = isStart ? 9 * J.nHC - 12 : 9 * J.nHC + 6;
+		} else {
+			P.n = 0;
+			P.vcount = 4;
+			P.icount = isStart ? 6u : 24u;
+		}
+		return true;
+	}
+	if (!(J.closed && q == 0)) {
+		P.flags |= PF_HAS_PREV;
+	}
+	if (J.closed && q == N - 1) {
+		P.flags |= PF_CLOSING;
+	}
+	if (jt == VGB_JOIN_ROUND || needSide) {
+		const float2* v = pts + J.first;
+		const float2 pm = v[q > 0 ? q - 1 : N - 1], p = v[q], pn = v[q < N - 1 ? q + 1 : 0u];
+		const float ax = p.x - pm.x, ay = p.y - pm.y, bx = pn.x - p.x, by = pn.y - p.y;
+		const float la = ax * ax + ay * ay, lb = bx * bx + by * by;
+		const float cr = ax * by - ay * bx;
+		if (!(la > 2e-5f && lb > 2e-5f && cr * cr > 1e-6f * (la * lb))) {
+			return false;
+		}
+		if (cr > 0.0f) {
+			P.flags |= PF_LEFT;
+		}
+	}
+	const uint32_t conn = (P.flags & PF_HAS_PREV) ? 18u : 0u;
+	const uint32_t n = jt == VGB_JOIN_MITER ? 0u : (jt == VGB_JOIN_BEVEL ? 1u : 2u);
+	P.n = n;
+	P.vcount = jt == VGB_JOIN_MITER ? 4u : 2 * n + 4;
+	P.icount = conn + 9 * n + ((P.flags & PF_CLOSING) ? 18u : 0u);
+	return true;
+}
 
 /* the single source of every count decision: piece q of job J */
 template<uint32_t OPS, int JT = 3, int CT = 3>
