@@ -787,44 +787,94 @@ __device__ __forceinline__ uint2 warpInclusive(uint2 v, uint32_t lane)
 	return v;
 }
 
+/* mesh table: (first vertex, first index) of job j = base of the group holding its first piece +
+ * the within-group offset recorded by k_group_count; an empty job starts where the next piece starts */
+__global__ void k_mesh_off(const uint32_t* __restrict__ pieceStart, const uint32_t* __restrict__ pieceJob, uint32_t numJobs, uint32_t numPieces,
+                           uint32_t numGroups, const ulonglong2* __restrict__ groupBase, const uint2* __restrict__ meshLocal,
+                           ulonglong2* __restrict__ meshOff)
+{
+	const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+	if (j > numJobs) return;
+	const uint32_t g = j < numJobs ? pieceStart[j] : numPieces;
+	ulonglong2 o;
+	if (g >= numPieces) {
+		o = groupBase[numGroups];
+	} else {
+		const uint2 l = meshLocal[pieceJob[g]];
+		o = groupBase[g >> 5];
+		o.x += l.x;
+		o.y += l.y;
+	}
+	meshOff[j] = o;
+}
+
+/* each warp counts GC consecutive groups; the loads of all of them are issued before any is used
+ * (the kernel is a chain of dependent loads: piece -> job record -> points) */
+static constexpr uint32_t GC = 4;
+
 template<uint32_t OPS, int JT, int CT>
 __global__ void __launch_bounds__(128) k_group_count(PieceArgs a)
 {
 	const uint32_t lane = threadIdx.x & 31;
-	const uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-	const uint32_t g = w * 32 + lane;
-	const bool valid = g < a.numPieces;
-	const uint32_t j = valid ? a.pieceJob[g] : 0;
-	uint32_t vc = 0, ic = 0, tail = 0;
-	if (valid) {
-		uint32_t ps;
-		const JobCtx J = loadJob(a, j, &ps);
-		Piece P;
-		if (!((OPS & OPS_STROKE_AA) && (!(OPS & ~OPS_STROKE_AA) || J.op == VGB_OP_STROKE_AA) && quickCountAA<JT, CT>(J, g - ps, a.pts, lane == 31, P))) {
-			P = classify<OPS, JT, CT>(J, g - ps, a.pts);
-		}
-		vc = P.vcount;
-		ic = P.icount;
-		tail = packTail(P);
+	const uint32_t w0 = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * GC;
+	uint32_t g[GC], j[GC], ps[GC];
+	bool valid[GC];
+	JobCtx J[GC];
+	float2 pm[GC], pc[GC], pn[GC];
+#pragma unroll
+	for (uint32_t k = 0; k < GC; ++k) {
+		g[k] = (w0 + k) * 32 + lane;
+		valid[k] = g[k] < a.numPieces;
+		j[k] = valid[k] ? a.pieceJob[g[k]] : 0u;
 	}
-	{
-		const uint32_t key = valid ? j : 0xFFFFFFFFu;
-		const uint32_t m = __match_any_sync(0xffffffffu, key);
-		const uint32_t sv = __reduce_add_sync(m, vc);
-		const uint32_t si = __reduce_add_sync(m, ic);
-		if (valid && lane == (uint32_t)(__ffs(m) - 1)) {
-			atomicAdd(&a.meshTotals[j].x, sv);
-			atomicAdd(&a.meshTotals[j].y, si);
+#pragma unroll
+	for (uint32_t k = 0; k < GC; ++k) {
+		ps[k] = 0;
+		if (valid[k]) {
+			J[k] = loadJob(a, j[k], &ps[k]);
 		}
 	}
-	const uint32_t tv = __reduce_add_sync(0xffffffffu, vc);
-	const uint32_t ti = __reduce_add_sync(0xffffffffu, ic);
-	if (w * 32 < a.numPieces) {
-		if (lane == 0) {
-			a.blockTotals[w] = make_uint2(tv, ti);
+#pragma unroll
+	for (uint32_t k = 0; k < GC; ++k) {
+		pm[k] = pc[k] = pn[k] = make_float2(0.0f, 0.0f);
+		if (valid[k] && ((OPS & OPS_STROKE_AA) && (!(OPS & ~OPS_STROKE_AA) || J[k].op == VGB_OP_STROKE_AA))) {
+			const uint32_t q = g[k] - ps[k], N = J[k].N;
+			const float2* v = a.pts + J[k].first;
+			pm[k] = v[q > 0 ? q - 1 : N - 1];
+			pc[k] = v[q];
+			pn[k] = v[q < N - 1 ? q + 1 : 0u];
 		}
-		if (lane == 31) {
-			a.blockTail[w] = tail;
+	}
+#pragma unroll
+	for (uint32_t k = 0; k < GC; ++k) {
+		const uint32_t w = w0 + k;
+		uint32_t vc = 0, ic = 0, tail = 0;
+		if (valid[k]) {
+			Piece P;
+			const uint32_t q = g[k] - ps[k];
+			if (!((OPS & OPS_STROKE_AA) && (!(OPS & ~OPS_STROKE_AA) || J[k].op == VGB_OP_STROKE_AA) &&
+			      quickCountAA<JT, CT>(J[k], q, pm[k], pc[k], pn[k], lane == 31, P))) {
+				P = classify<OPS, JT, CT>(J[k], q, a.pts);
+			}
+			vc = P.vcount;
+			ic = P.icount;
+			tail = packTail(P);
+		}
+		/* within-group offsets: the lane owning a mesh's first piece records where that mesh starts
+		 * inside its group; k_mesh_off adds the group base after the scan (no atomics, no per-mesh scan) */
+		const uint2 inc = warpInclusive(make_uint2(vc, ic), lane);
+		if (valid[k] && g[k] == ps[k]) {
+			a.meshTotals[j[k]] = make_uint2(inc.x - vc, inc.y - ic);
+		}
+		const uint32_t tv = __shfl_sync(0xffffffffu, inc.x, 31);
+		const uint32_t ti = __shfl_sync(0xffffffffu, inc.y, 31);
+		if (w * 32 < a.numPieces) {
+			if (lane == 0) {
+				a.blockTotals[w] = make_uint2(tv, ti);
+			}
+			if (lane == 31) {
+				a.blockTail[w] = tail;
+			}
 		}
 	}
 }
@@ -1199,7 +1249,9 @@ public:
 			                                                   dSubNum.as<uint32_t>(), dSubClosed.as<uint8_t>(), dDD.as<DrawDerived>(),
 			                                                   dPieceStart.as<uint32_t>(), dJobRec.as<JobRec>(), dPieceJob.as<uint32_t>());
 			++launches;
+#if !VGB_GROUP32
 			VGB_CUDA(cudaMemsetAsync(dMeshTotals.p, 0, (size_t)numJobs * 8, st));
+#endif
 			pa.numPieces = numPieces;
 			pa.numJobs = numJobs;
 			pa.pieceJob = dPieceJob.as<uint32_t>();
@@ -1213,18 +1265,26 @@ public:
 			pa.vertexBase = vertexBase;
 #if VGB_GROUP32
 #define VGB_COUNT_K k_group_count
+			const uint32_t countBlocks = (numBlocks + 4 * GC - 1) / (4 * GC); /* 4 warps per block, GC groups per warp */
 #else
 #define VGB_COUNT_K k_piece_count
+			const uint32_t countBlocks = gridBlocks;
 #endif
-			if (opsMask == OPS_STROKE_AA && uniJoin == VGB_JOIN_ROUND && uniCap == VGB_CAP_ROUND) VGB_COUNT_K<OPS_STROKE_AA, 1, 1><<<gridBlocks, PPB, 0, st>>>(pa);
-			else if (opsMask == OPS_STROKE_AA && uniJoin == VGB_JOIN_MITER && uniCap == VGB_CAP_BUTT) VGB_COUNT_K<OPS_STROKE_AA, 0, 0><<<gridBlocks, PPB, 0, st>>>(pa);
-			else if (opsMask == OPS_STROKE_AA) VGB_COUNT_K<OPS_STROKE_AA, 3, 3><<<gridBlocks, PPB, 0, st>>>(pa);
-			else if (opsMask == OPS_FILL_AA) VGB_COUNT_K<OPS_FILL_AA, 3, 3><<<gridBlocks, PPB, 0, st>>>(pa);
-			else VGB_COUNT_K<OPS_ALL, 3, 3><<<gridBlocks, PPB, 0, st>>>(pa);
+			if (opsMask == OPS_STROKE_AA && uniJoin == VGB_JOIN_ROUND && uniCap == VGB_CAP_ROUND) VGB_COUNT_K<OPS_STROKE_AA, 1, 1><<<countBlocks, PPB, 0, st>>>(pa);
+			else if (opsMask == OPS_STROKE_AA && uniJoin == VGB_JOIN_MITER && uniCap == VGB_CAP_BUTT) VGB_COUNT_K<OPS_STROKE_AA, 0, 0><<<countBlocks, PPB, 0, st>>>(pa);
+			else if (opsMask == OPS_STROKE_AA) VGB_COUNT_K<OPS_STROKE_AA, 3, 3><<<countBlocks, PPB, 0, st>>>(pa);
+			else if (opsMask == OPS_FILL_AA) VGB_COUNT_K<OPS_FILL_AA, 3, 3><<<countBlocks, PPB, 0, st>>>(pa);
+			else VGB_COUNT_K<OPS_ALL, 3, 3><<<countBlocks, PPB, 0, st>>>(pa);
 #undef VGB_COUNT_K
 			++launches;
 			if (scan<ScanOps<uint2>>(dBlockTotals.as<uint2>(), numBlocks, dBlockBase.as<ulonglong2>(), err)) return VGB_ERR_CUDA;
+#if VGB_GROUP32
+			k_mesh_off<<<(numJobs + 1 + 255) / 256, 256, 0, st>>>(dPieceStart.as<uint32_t>(), dPieceJob.as<uint32_t>(), numJobs, numPieces, numBlocks,
+			                                                       dBlockBase.as<ulonglong2>(), dMeshTotals.as<uint2>(), dMeshOff.as<ulonglong2>());
+			++launches;
+#else
 			if (scan<ScanOps<uint2>>(dMeshTotals.as<uint2>(), numJobs, dMeshOff.as<ulonglong2>(), err)) return VGB_ERR_CUDA;
+#endif
 			if (readback(totals, dMeshOff.as<ulonglong2>() + numJobs, 16, err)) return VGB_ERR_CUDA;
 		} else {
 			VGB_CUDA(cudaMemsetAsync(dMeshOff.p, 0, (size_t)(numJobs + 1) * 16, st));

@@ -216,10 +216,11 @@ enum { OPS_STROKE_AA = 1, OPS_FILL_AA = 2, OPS_OTHER = 4, OPS_ALL = 7 };
  * the epsilon below which vec2Dir returns zero.  Then the side is the sign of the raw cross
  * product as well.  Anything else (near-collinear, hairpin, degenerate) returns false and takes
  * the full classify(), so counts stay bit-exact.  needSide: the caller needs PF_LEFT (the warp's
- * last lane publishes the hand-over word).
+ * last lane publishes the hand-over word).  pm, p, pn: the piece's polyline point and its
+ * wrapped neighbours, loaded by the caller (so that it can keep several groups' loads in flight).
  */
 template<int JT, int CT>
-__device__ __forceinline__ bool quickCountAA(const JobCtx& J, uint32_t q, const float2* __restrict__ pts, bool needSide, Piece& P)
+__device__ __forceinline__ bool quickCountAA(const JobCtx& J, uint32_t q, float2 pm, float2 p, float2 pn, bool needSide, Piece& P)
 {
 	const uint32_t jt = JT < 3 ? (uint32_t)JT : J.join;
 	const uint32_t ct = CT < 3 ? (uint32_t)CT : J.cap;
@@ -253,8 +254,6 @@ __device__ __forceinline__ bool quickCountAA(const JobCtx& J, uint32_t q, const 
 		P.flags |= PF_CLOSING;
 	}
 	if (jt == VGB_JOIN_ROUND || needSide) {
-		const float2* v = pts + J.first;
-		const float2 pm = v[q > 0 ? q - 1 : N - 1], p = v[q], pn = v[q < N - 1 ? q + 1 : 0u];
 		const float ax = p.x - pm.x, ay = p.y - pm.y, bx = pn.x - p.x, by = pn.y - p.y;
 		const float la = ax * ax + ay * ay, lb = bx * bx + by * by;
 		const float cr = ax * by - ay * bx;
