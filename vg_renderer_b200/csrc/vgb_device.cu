@@ -1006,6 +1006,12 @@ public:
 	DevBuf dSubNum, dSubFirst, dSubClosed, dPts, dDD, dJobPieces, dPieceStart, dJobRec, dPieceJob;
 	DevBuf dBlockTotals, dBlockBase, dMeshTotals, dMeshOff, dScanTmp, dBlockTail;
 	DevBuf dSlotFirst, dCounters, dDenseFirst, dDensePts;
+	/* sizes of the uploaded batch, learnt by the first run (they are facts about the input, and the
+	 * kernels are deterministic): later runs of the SAME upload reuse them instead of draining the
+	 * stream three times to read them back, so the host can enqueue a whole step ahead */
+	bool sizesKnown = false;
+	uint32_t kNumPts = 0, kNumPieces = 0;
+	uint64_t kTotals[2] = {0, 0};
 	bool slotMode = false;   /* single-pass flatten into recorder-sized slots */
 	bool slotsUsed = false;  /* the last run's point buffer is slotted (not dense) */
 	uint32_t totalSlots = 0;
@@ -1110,6 +1116,7 @@ public:
 		if (rc) return VGB_ERR_CUDA;
 		uploaded = true;
 		ran = false;
+		sizesKnown = false;
 		return 0;
 	}
 
@@ -1197,7 +1204,11 @@ public:
 				k_flatten<false><<<fb, 128, 0, st>>>(fa);
 				++launches;
 				if (scan<ScanOps<uint32_t>>(dSubNum.as<uint32_t>(), numSub, dSubFirst.as<uint32_t>(), err)) return VGB_ERR_CUDA;
-				if (readback(&numPts, dSubFirst.as<uint32_t>() + numSub, 4, err)) return VGB_ERR_CUDA;
+				if (sizesKnown) {
+					numPts = kNumPts;
+				} else if (readback(&numPts, dSubFirst.as<uint32_t>() + numSub, 4, err)) {
+					return VGB_ERR_CUDA;
+				}
 				if (dPts.ensure((size_t)numPts * 8 + 16, err)) return VGB_ERR_CUDA;
 				fa.pts = dPts.as<float2>();
 				k_flatten<true><<<fb, 128, 0, st>>>(fa);
@@ -1220,9 +1231,16 @@ public:
 			                                                     dDraws.as<DrawRec>(), dJobPieces.as<uint32_t>());
 			launches += 2;
 			if (scan<ScanOps<uint32_t>>(dJobPieces.as<uint32_t>(), numJobs, dPieceStart.as<uint32_t>(), err)) return VGB_ERR_CUDA;
-			if (readback(&numPieces, dPieceStart.as<uint32_t>() + numJobs, 4, err)) return VGB_ERR_CUDA;
+			if (sizesKnown) {
+				numPieces = kNumPieces;
+			} else if (readback(&numPieces, dPieceStart.as<uint32_t>() + numJobs, 4, err)) {
+				return VGB_ERR_CUDA;
+			}
 		}
-		if (slotsUsed) {
+		if (slotsUsed && sizesKnown) {
+			numPts = kNumPts;
+			sz.num_points = numPts;
+		} else if (slotsUsed) {
 			uint32_t c[4];
 			if (readback(c, dCounters.p, 16, err)) return VGB_ERR_CUDA;
 			if (c[1]) {
@@ -1285,7 +1303,12 @@ public:
 #else
 			if (scan<ScanOps<uint2>>(dMeshTotals.as<uint2>(), numJobs, dMeshOff.as<ulonglong2>(), err)) return VGB_ERR_CUDA;
 #endif
-			if (readback(totals, dMeshOff.as<ulonglong2>() + numJobs, 16, err)) return VGB_ERR_CUDA;
+			if (sizesKnown) {
+				totals[0] = kTotals[0];
+				totals[1] = kTotals[1];
+			} else if (readback(totals, dMeshOff.as<ulonglong2>() + numJobs, 16, err)) {
+				return VGB_ERR_CUDA;
+			}
 		} else {
 			VGB_CUDA(cudaMemsetAsync(dMeshOff.p, 0, (size_t)(numJobs + 1) * 16, st));
 		}
@@ -1326,6 +1349,11 @@ public:
 		VGB_CUDA(cudaEventRecord(ev[3], st));
 		sz.kernel_launches = launches;
 		ran = true;
+		kNumPts = numPts;
+		kNumPieces = numPieces;
+		kTotals[0] = totals[0];
+		kTotals[1] = totals[1];
+		sizesKnown = true;
 		return 0;
 	}
 
