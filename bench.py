@@ -314,12 +314,13 @@ def main():
         idx, _p3 = pinned_empty((I + 16,), np.uint32 if args.merged else np.uint16)
         pin_in, _p4 = pinned_empty((n, 8), np.float32)
         pin_in[:] = p8
-        mvo = np.zeros(n + 1, np.uint64)
-        mio = np.zeros(n + 1, np.uint64)
+        mvo, _p5 = pinned_empty((n + 1,), np.uint64)
+        mio, _p6 = pinned_empty((n + 1,), np.uint64)
 
         def e2e_step():
+            # host buffer in (borrowed, DMA'd by upload), host buffers out
             b.reset(1.0)
-            b.add_cubic_strokes(pin_in, width=WIDTH, cap=CAP, join=JOIN)
+            b.set_cubic_strokes(pin_in, width=WIDTH, cap=CAP, join=JOIN)
             b.upload()
             b.run(index_u32=args.merged, vertex_base=vertex_base)
             b._chk(b.L.vgb_batch_download(b.h, pos.ctypes.data, col.ctypes.data, idx.ctypes.data, len(pos), len(idx),
@@ -332,7 +333,7 @@ def main():
             e2e_step()
         t1 = time.perf_counter()
         e2e_ms = allmax((t1 - t0) * 1e3) / args.e2e_steps
-        h2d = 8 * 4 * n + 2 * n + 16 * n + 2 * 4 * n + 3 * 4 * n + 16  # data + cmd + subRec + jobs + scale/tol(/xform none) + draw
+        h2d = 8 * 4 * n + 16  # the coordinates + one draw record (tables are generated on the device)
         d2h = 12 * V + idx_bytes * I + 16 * (n + 1)
         e2e = {"value": total_verts / (e2e_ms * 1e-3) / 1e6, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                "ms_per_step": e2e_ms, "d2h_gbs": d2h / (e2e_ms * 1e-3) / 1e9}

@@ -159,6 +159,14 @@ VGB_API int vgb_batch_add_cubic_strokes(vgb_batch* b, const float* p8, uint32_t 
 VGB_API int vgb_batch_add_rounded_rect_fills(vgb_batch* b, const float* xywhr, uint32_t n, float scale, float tess_tol,
                                              uint32_t color, int aa);
 
+/* zero-copy variant for the host-buffer path: REPLACES everything recorded by the n paths of
+ * vgb_batch_add_cubic_strokes, but p8 is only borrowed -- it is read (DMA, straight from the
+ * caller's memory: make it pinned) by the next vgb_batch_upload / _run / _execute, where the command,
+ * sub-path and job tables are generated on the device; keep it valid and unchanged until then.
+ * Non-finite coordinates are detected on the device: the run fails with VGB_ERR_NONFINITE. */
+VGB_API int vgb_batch_set_cubic_strokes(vgb_batch* b, const float* p8, uint32_t n, float scale, float tess_tol,
+                                        uint32_t op, uint32_t color, float width, uint32_t cap, uint32_t join);
+
 /* stroker-only entry (strokerXXX called on caller polylines, no Path object involved):
  * replaces the flatten stage's output by these polylines; draws then refer to "paths" that are
  * single sub-paths.  pts = x,y interleaved; sub-path s = pts[first[s] .. first[s]+num[s]).      */

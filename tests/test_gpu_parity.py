@@ -350,3 +350,30 @@ def test_per_object_plain_thin_fan(ref):
     rpos, rcol, ridx = ref.mesh(vgb.OP_CONVEX_FILL, v[:9], True, 0)
     np.testing.assert_array_equal(idx, ridx)
     np.testing.assert_array_equal(pos, v[:9])
+
+
+def test_zero_copy_bulk_equals_recorded(gpu_batch, ref):
+    """vgb_batch_set_cubic_strokes (tables generated on the device from the caller's buffer) gives
+    the same result as the recorded path; non-finite input is caught on the device"""
+    from vg_renderer_b200.api import pinned_empty
+    p8 = W.config3_cubics(5000, first=4242)
+    pin, _keep = pinned_empty((5000, 8), np.float32)
+    pin[:] = p8
+    for cap, join, width in ((1, 1, 4.0), (0, 0, 2.5), (2, 2, 9.0)):
+        gpu_batch.reset(1.0)
+        gpu_batch.set_cubic_strokes(pin, width=width, cap=cap, join=join)
+        gpu_batch.run()
+        check_same(gpu_batch.download(), ref.run_batch(BatchTables.cubic_strokes(p8, width=width, cap=cap, join=join)))
+        gpu_batch.run()  # second run of the same upload reuses the learnt sizes
+        check_same(gpu_batch.download(), ref.run_batch(BatchTables.cubic_strokes(p8, width=width, cap=cap, join=join)))
+    bad = p8.copy()
+    bad[77, 3] = np.nan
+    gpu_batch.reset(1.0)
+    gpu_batch.set_cubic_strokes(bad)
+    with pytest.raises(vgb.VgbError) as e:
+        gpu_batch.run()
+    assert e.value.code == -2
+    gpu_batch.reset(1.0)
+    gpu_batch.set_cubic_strokes(pin)
+    with pytest.raises(vgb.VgbError):
+        gpu_batch.begin_path()

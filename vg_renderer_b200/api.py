@@ -85,6 +85,7 @@ def load_library():
     L.vgb_batch_convex_fill.argtypes = [vp, u32, i]
     L.vgb_batch_add_cubic_strokes.argtypes = [vp, vp, u32, f, f, u32, u32, f, u32, u32]
     L.vgb_batch_add_rounded_rect_fills.argtypes = [vp, vp, u32, f, f, u32, i]
+    L.vgb_batch_set_cubic_strokes.argtypes = [vp, vp, u32, f, f, u32, u32, f, u32, u32]
     L.vgb_batch_set_polylines.argtypes = [vp, vp, u32, vp, vp, vp, u32, f, f]
     L.vgb_batch_draw_polyline.argtypes = [vp, u32, u32, u32, f, u32, u32]
     L.vgb_batch_draw_all.argtypes = [vp, u32, u32, f, u32, u32]
@@ -211,6 +212,12 @@ class Batch:
     def add_cubic_strokes(self, p8, scale=1.0, tol=0.25, op=OP_STROKE_AA, color=0xFF0000FF, width=4.0, cap=CAP_ROUND, join=JOIN_ROUND):
         p8 = np.ascontiguousarray(p8, np.float32).reshape(-1, 8)
         return self._chk(self.L.vgb_batch_add_cubic_strokes(self.h, _ptr(p8), len(p8), scale, tol, op, color, width, cap, join))
+
+    def set_cubic_strokes(self, p8, scale=1.0, tol=0.25, op=OP_STROKE_AA, color=0xFF0000FF, width=4.0, cap=CAP_ROUND, join=JOIN_ROUND):
+        """zero-copy bulk input: p8 (float32 [n,8], ideally pinned) is BORROWED until the next upload/run/execute"""
+        assert p8.dtype == np.float32 and p8.flags["C_CONTIGUOUS"]
+        self._bulk_ref = p8  # keep the caller's buffer alive
+        return self._chk(self.L.vgb_batch_set_cubic_strokes(self.h, _ptr(p8), p8.size // 8, scale, tol, op, color, width, cap, join))
 
     def add_rounded_rect_fills(self, xywhr, scale=1.0, tol=0.25, color=0xFF00FF00, aa=True):
         q = np.ascontiguousarray(xywhr, np.float32).reshape(-1, 5)

@@ -71,9 +71,15 @@ struct vgb_batch
 	std::vector<uint32_t> rawFirst, rawNum;
 	std::vector<uint8_t> rawClosed;
 	bool dirty = true;
+	/* borrowed bulk input (vgb_batch_set_cubic_strokes) */
+	const float* bulkP8 = nullptr;
+	uint32_t bulkN = 0;
+	float bulkScale = 1.0f, bulkTol = 0.25f;
 
 	void clear(float fr)
 	{
+		bulkP8 = nullptr;
+		bulkN = 0;
 		fringe = fr;
 		cmd.clear(); data.clear(); subs.clear();
 		pathScale.clear(); pathTol.clear(); pathXform.clear();
@@ -83,6 +89,15 @@ struct vgb_batch
 		rawMode = false;
 		rawPts.clear(); rawFirst.clear(); rawNum.clear(); rawClosed.clear();
 		dirty = true;
+	}
+
+	/* per-path transforms are materialised lazily: identity rows are only written once some path
+	 * actually has a transform (or at upload, if any does) */
+	void xformIdentityUpTo(size_t numPaths)
+	{
+		if (!anyXform) return;
+		static const float ident[6] = {1, 0, 0, 1, 0, 0};
+		while (pathXform.size() < 6 * numPaths) pathXform.insert(pathXform.end(), ident, ident + 6);
 	}
 
 	void closeSub()
@@ -107,6 +122,7 @@ struct vgb_batch
 	int push(uint8_t c, const float* d, uint32_t n, bool startsSub)
 	{
 		if (rawMode) return fail(VGB_ERR_STATE, "path commands after vgb_batch_set_polylines");
+		if (bulkP8) return fail(VGB_ERR_STATE, "path commands after vgb_batch_set_cubic_strokes (reset first)");
 		if (!inPath) return fail(VGB_ERR_INVALID, "path command outside begin_path");
 		if (drawn) return fail(VGB_ERR_INVALID, "path command after a draw: begin a new path");
 		if (!finite_all(d, n)) return fail(VGB_ERR_NONFINITE, "non-finite coordinate");
@@ -173,6 +189,7 @@ int vgb_batch_begin_path(vgb_batch* b, float scale, float tol, const float* xfor
 {
 	if (!b) return fail(VGB_ERR_INVALID, "null batch");
 	if (b->rawMode) return fail(VGB_ERR_STATE, "begin_path after vgb_batch_set_polylines");
+	if (b->bulkP8) return fail(VGB_ERR_STATE, "begin_path after vgb_batch_set_cubic_strokes (reset first)");
 	if (!(scale > 0.0f) || !(tol > 0.0f) || !finite_all(&scale, 1) || !finite_all(&tol, 1)) return fail(VGB_ERR_INVALID, "scale and tolerance must be positive and finite");
 	if (xform6 && !finite_all(xform6, 6)) return fail(VGB_ERR_NONFINITE, "non-finite transform");
 	b->closeSub();
@@ -180,10 +197,13 @@ int vgb_batch_begin_path(vgb_batch* b, float scale, float tol, const float* xfor
 	b->curFirstSub = (uint32_t)b->subs.size();
 	b->pathScale.push_back(scale);
 	b->pathTol.push_back(tol);
-	static const float ident[6] = {1, 0, 0, 1, 0, 0};
-	const float* m = xform6 ? xform6 : ident;
-	b->pathXform.insert(b->pathXform.end(), m, m + 6);
-	if (xform6) b->anyXform = true;
+	if (xform6) {
+		b->anyXform = true;
+		b->xformIdentityUpTo(b->pathScale.size() - 1); /* rows of the earlier, untransformed paths */
+		b->pathXform.insert(b->pathXform.end(), xform6, xform6 + 6);
+	} else {
+		b->xformIdentityUpTo(b->pathScale.size());
+	}
 	b->inPath = true;
 	b->subOpen = false;
 	b->drawn = false;
@@ -284,9 +304,12 @@ static int addDraw(vgb_batch* b, uint32_t op, uint32_t color, float width, uint3
 	r.pathId = pathId;
 	const uint32_t d = (uint32_t)b->draws.size();
 	b->draws.push_back(r);
-	for (uint32_t s = sub0; s < sub1; ++s) {
-		b->jobSub.push_back(s);
-		b->jobDraw.push_back(d);
+	const size_t j0 = b->jobSub.size(), nj = sub1 > sub0 ? sub1 - sub0 : 0;
+	b->jobSub.resize(j0 + nj);
+	b->jobDraw.resize(j0 + nj);
+	for (size_t k = 0; k < nj; ++k) {
+		b->jobSub[j0 + k] = sub0 + (uint32_t)k;
+		b->jobDraw[j0 + k] = d;
 	}
 	b->dirty = true;
 	return 0;
@@ -311,7 +334,7 @@ int vgb_batch_add_cubic_strokes(vgb_batch* b, const float* p8, uint32_t n, float
                                 uint32_t op, uint32_t color, float width, uint32_t cap, uint32_t join)
 {
 	if (!b || (!p8 && n)) return fail(VGB_ERR_INVALID, "null argument");
-	if (b->rawMode) return fail(VGB_ERR_STATE, "recording after vgb_batch_set_polylines");
+	if (b->rawMode || b->bulkP8) return fail(VGB_ERR_STATE, "recording after vgb_batch_set_polylines / set_cubic_strokes");
 	if (!(scale > 0.0f) || !(tol > 0.0f)) return fail(VGB_ERR_INVALID, "scale and tolerance must be positive");
 	if (!finite_all(p8, 8 * (size_t)n)) return fail(VGB_ERR_NONFINITE, "non-finite coordinate");
 	if (n == 0) return 0;
@@ -337,14 +360,26 @@ int vgb_batch_add_cubic_strokes(vgb_batch* b, const float* p8, uint32_t n, float
 	}
 	b->pathScale.insert(b->pathScale.end(), n, scale);
 	b->pathTol.insert(b->pathTol.end(), n, tol);
-	{
-		static const float ident[6] = {1, 0, 0, 1, 0, 0};
-		const size_t x0 = b->pathXform.size();
-		b->pathXform.resize(x0 + 6 * (size_t)n);
-		for (uint32_t i = 0; i < n; ++i) memcpy(&b->pathXform[x0 + 6 * (size_t)i], ident, sizeof(ident));
-	}
+	b->xformIdentityUpTo(b->pathScale.size());
 	/* scale/tol are uniform over these paths, so one draw record serves all of them */
 	return addDraw(b, op, color, width, cap, join, path0, sub0, sub0 + n);
+}
+
+int vgb_batch_set_cubic_strokes(vgb_batch* b, const float* p8, uint32_t n, float scale, float tol,
+                                uint32_t op, uint32_t color, float width, uint32_t cap, uint32_t join)
+{
+	if (!b || (!p8 && n)) return fail(VGB_ERR_INVALID, "null argument");
+	if (!(scale > 0.0f) || !(tol > 0.0f)) return fail(VGB_ERR_INVALID, "scale and tolerance must be positive");
+	if (op != VGB_OP_STROKE_AA && op != VGB_OP_STROKE && op != VGB_OP_STROKE_AA_THIN) return fail(VGB_ERR_INVALID, "not a stroke op");
+	const float fr = b->fringe;
+	b->clear(fr);
+	b->bulkP8 = p8;
+	b->bulkN = n;
+	b->bulkScale = scale;
+	b->bulkTol = tol;
+	b->pathScale.assign(1, scale); /* path 0 carries the (uniform) flatten parameters of every bulk path */
+	b->pathTol.assign(1, tol);
+	return addDraw(b, op, color, width, cap, join, 0, 0, 0); /* one draw record, jobs are implicit (job i = sub-path i) */
 }
 
 int vgb_batch_add_rounded_rect_fills(vgb_batch* b, const float* q, uint32_t n, float scale, float tol, uint32_t color, int aa)
@@ -364,7 +399,6 @@ int vgb_batch_add_rounded_rect_fills(vgb_batch* b, const float* q, uint32_t n, f
 		const float* r = q + 5 * (size_t)i;
 		b->pathScale.push_back(scale);
 		b->pathTol.push_back(tol);
-		b->pathXform.insert(b->pathXform.end(), ident, ident + 6);
 		if (r[4] < 0.1f && degenerateRect(r[2], r[3])) continue; /* empty path: no sub-path, no mesh */
 		SubRec s;
 		s.cmdBegin = (uint32_t)b->cmd.size();
@@ -376,6 +410,7 @@ int vgb_batch_add_rounded_rect_fills(vgb_batch* b, const float* q, uint32_t n, f
 		b->subs.push_back(s);
 		++made;
 	}
+	b->xformIdentityUpTo(b->pathScale.size());
 	return addDraw(b, aa ? VGB_OP_CONVEX_FILL_AA : VGB_OP_CONVEX_FILL, color, 0.0f, 0, 0, path0, sub0, sub0 + made);
 }
 
@@ -424,6 +459,10 @@ int vgb_batch_recorded_counts(vgb_batch* b, uint32_t* out6)
 {
 	if (!b || !out6) return fail(VGB_ERR_INVALID, "null argument");
 	b->closeSub();
+	if (b->bulkP8) {
+		out6[0] = b->bulkN; out6[1] = b->bulkN; out6[2] = 2 * b->bulkN; out6[3] = 8 * b->bulkN; out6[4] = 1; out6[5] = b->bulkN;
+		return 0;
+	}
 	out6[0] = (uint32_t)b->pathScale.size();
 	out6[1] = (uint32_t)(b->rawMode ? b->rawFirst.size() : b->subs.size());
 	out6[2] = (uint32_t)b->cmd.size();
@@ -466,7 +505,14 @@ int vgb_batch_upload(vgb_batch* b)
 	t.pathScale = b->pathScale.data();
 	t.pathTol = b->pathTol.data();
 	t.numPaths = (uint32_t)b->pathScale.size();
-	if (b->rawMode) {
+	if (b->bulkP8) {
+		t.bulkP8 = b->bulkP8;
+		t.bulkN = b->bulkN;
+		t.bulkScale = b->bulkScale;
+		t.bulkTol = b->bulkTol;
+		t.numSub = b->bulkN;
+		t.numJobs = b->bulkN;
+	} else if (b->rawMode) {
 		static const float none[2] = {0.0f, 0.0f};
 		t.rawPts = b->rawPts.empty() ? none : b->rawPts.data();
 		t.numRawPts = (uint32_t)(b->rawPts.size() / 2);
@@ -510,13 +556,16 @@ int vgb_batch_upload(vgb_batch* b)
 		t.numCmd = (uint32_t)b->cmd.size();
 		t.data = b->data.data();
 		t.numData = (uint32_t)b->data.size();
+		b->xformIdentityUpTo(b->pathScale.size());
 		t.pathXform = b->anyXform ? b->pathXform.data() : nullptr;
 	}
 	t.draws = b->draws.data();
 	t.numDraws = (uint32_t)b->draws.size();
-	t.jobSub = b->jobSub.data();
-	t.jobDraw = b->jobDraw.data();
-	t.numJobs = (uint32_t)b->jobSub.size();
+	if (!b->bulkP8) {
+		t.jobSub = b->jobSub.data();
+		t.jobDraw = b->jobDraw.data();
+		t.numJobs = (uint32_t)b->jobSub.size();
+	}
 	std::string err;
 	const int rc = b->pipe->upload(t, &err);
 	if (rc) return fail(rc, err.c_str());

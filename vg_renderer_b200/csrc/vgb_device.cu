@@ -301,6 +301,53 @@ __global__ void __launch_bounds__(128) k_flatten_slots(SlotArgs a)
 	}
 }
 
+/* bulk mode (vgb_batch_set_cubic_strokes): the coordinates arrive straight from the caller's
+ * buffer; every table the pipeline needs for "path i = moveTo + cubicTo, one stroke" is generated
+ * here instead of being built and shipped by the host.  A sub-path with a non-finite coordinate
+ * gets an empty command range (the reference would never return from pathCubicTo) and raises the
+ * error flag. */
+static constexpr uint32_t BULK_SLOT = 52; /* point slots per bulk cubic (moveTo 1 + cubic 48 + spare) */
+
+__global__ void k_bulk_cubic_tables(const float* __restrict__ p8, uint32_t n, float scale, float tol, uint8_t* __restrict__ cmd,
+                                    SubRec* __restrict__ subRec, float* __restrict__ pathScale, float* __restrict__ pathTol,
+                                    uint32_t* __restrict__ jobSub, uint32_t* __restrict__ jobDraw, uint32_t* __restrict__ slotFirst,
+                                    uint32_t* __restrict__ errFlag)
+{
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i > n) return;
+	slotFirst[i] = i * BULK_SLOT;
+	if (i == n) return;
+	const float4 a = reinterpret_cast<const float4*>(p8)[2 * i], b = reinterpret_cast<const float4*>(p8)[2 * i + 1];
+	const uint32_t bits = (__float_as_uint(a.x) & 0x7F800000u) == 0x7F800000u || (__float_as_uint(a.y) & 0x7F800000u) == 0x7F800000u ||
+	                      (__float_as_uint(a.z) & 0x7F800000u) == 0x7F800000u || (__float_as_uint(a.w) & 0x7F800000u) == 0x7F800000u ||
+	                      (__float_as_uint(b.x) & 0x7F800000u) == 0x7F800000u || (__float_as_uint(b.y) & 0x7F800000u) == 0x7F800000u ||
+	                      (__float_as_uint(b.z) & 0x7F800000u) == 0x7F800000u || (__float_as_uint(b.w) & 0x7F800000u) == 0x7F800000u;
+	if (bits) {
+		atomicOr(errFlag, 1u);
+	}
+	reinterpret_cast<uchar2*>(cmd)[i] = make_uchar2(VGB_CMD_MOVE_TO, VGB_CMD_CUBIC_TO);
+	SubRec r;
+	r.cmdBegin = 2 * i;
+	r.cmdEnd = bits ? 2 * i : 2 * i + 2;
+	r.dataBegin = 8 * i;
+	r.pathId = i;
+	subRec[i] = r;
+	pathScale[i] = scale;
+	pathTol[i] = tol;
+	jobSub[i] = i;
+	jobDraw[i] = 0;
+}
+
+/* mesh table as two plain u64 arrays (what vgb_batch_download hands out) */
+__global__ void k_split_mesh_off(const ulonglong2* __restrict__ meshOff, uint32_t n, uint64_t* __restrict__ v, uint64_t* __restrict__ i)
+{
+	const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+	if (j >= n) return;
+	const ulonglong2 o = meshOff[j];
+	v[j] = o.x;
+	i[j] = o.y;
+}
+
 /* dense copy of a slotted point buffer (only for reading paths back: download_paths) */
 __global__ void k_gather_points(const float2* __restrict__ pts, const uint32_t* __restrict__ subFirst, const uint32_t* __restrict__ subNum,
                                 const uint32_t* __restrict__ denseFirst, uint32_t numSub, float2* __restrict__ out)
@@ -1005,7 +1052,8 @@ public:
 	/* intermediates */
 	DevBuf dSubNum, dSubFirst, dSubClosed, dPts, dDD, dJobPieces, dPieceStart, dJobRec, dPieceJob;
 	DevBuf dBlockTotals, dBlockBase, dMeshTotals, dMeshOff, dScanTmp, dBlockTail;
-	DevBuf dSlotFirst, dCounters, dDenseFirst, dDensePts;
+	DevBuf dSlotFirst, dCounters, dDenseFirst, dDensePts, dBulkErr, dMeshSplit;
+	bool bulkMode = false;
 	/* sizes of the uploaded batch, learnt by the first run (they are facts about the input, and the
 	 * kernels are deterministic): later runs of the SAME upload reuse them instead of draining the
 	 * stream three times to read them back, so the host can enqueue a whole step ahead */
@@ -1033,7 +1081,7 @@ public:
 		cudaSetDevice(dev);
 		DevBuf* all[] = {&dSubRec, &dCmd, &dData, &dScale, &dTol, &dXform, &dDraws, &dJobSub, &dJobDraw, &dSubNum, &dSubFirst,
 		                 &dSubClosed, &dPts, &dDD, &dJobPieces, &dPieceStart, &dJobRec, &dPieceJob, &dBlockTotals, &dBlockBase,
-		                 &dMeshTotals, &dMeshOff, &dScanTmp, &dBlockTail, &dSlotFirst, &dCounters, &dDenseFirst, &dDensePts, &dPos, &dCol, &dIdx};
+		                 &dMeshTotals, &dMeshOff, &dScanTmp, &dBlockTail, &dSlotFirst, &dCounters, &dDenseFirst, &dDensePts, &dBulkErr, &dMeshSplit, &dPos, &dCol, &dIdx};
 		for (DevBuf* b : all) b->release();
 		for (auto& e : ev) if (e) cudaEventDestroy(e);
 		for (auto& e : userEv) if (e) cudaEventDestroy(e);
@@ -1082,9 +1130,30 @@ public:
 		numPaths = t.numPaths;
 		hasXform = t.pathXform != nullptr;
 		int rc = 0;
-		rc |= up(dScale, t.pathScale, t.numPaths, err);
-		rc |= up(dTol, t.pathTol, t.numPaths, err);
-		if (rawMode) {
+		bulkMode = t.bulkP8 != nullptr;
+		if (bulkMode) {
+			const uint32_t n = t.bulkN;
+			numPaths = n;
+			if (dScale.ensure((size_t)n * 4 + 16, err) || dTol.ensure((size_t)n * 4 + 16, err) || dCmd.ensure((size_t)n * 2 + 16, err) ||
+			    dSubRec.ensure((size_t)n * sizeof(SubRec) + 16, err) || dJobSub.ensure((size_t)n * 4 + 16, err) ||
+			    dJobDraw.ensure((size_t)n * 4 + 16, err) || dSlotFirst.ensure((size_t)(n + 1) * 4, err) || dBulkErr.ensure(16, err))
+				return VGB_ERR_CUDA;
+			rc |= up(dData, t.bulkP8, 8 * (size_t)n, err); /* DMA straight from the caller's buffer */
+			VGB_CUDA(cudaMemsetAsync(dBulkErr.p, 0, 4, st));
+			k_bulk_cubic_tables<<<(n + 1 + 255) / 256, 256, 0, st>>>(dData.as<float>(), n, t.bulkScale, t.bulkTol, dCmd.as<uint8_t>(), dSubRec.as<SubRec>(),
+			                                                         dScale.as<float>(), dTol.as<float>(), dJobSub.as<uint32_t>(), dJobDraw.as<uint32_t>(),
+			                                                         dSlotFirst.as<uint32_t>(), dBulkErr.as<uint32_t>());
+			VGB_CUDA(cudaGetLastError());
+			hasXform = false;
+			slotMode = n > 0 && (uint64_t)n * BULK_SLOT < 0xE0000000ull && getenv("VGB_TWO_PASS_FLATTEN") == nullptr;
+			totalSlots = n * BULK_SLOT;
+		} else {
+			rc |= up(dScale, t.pathScale, t.numPaths, err);
+			rc |= up(dTol, t.pathTol, t.numPaths, err);
+		}
+		if (bulkMode) {
+			/* nothing else to ship */
+		} else if (rawMode) {
 			rc |= up(dPts, t.rawPts, 2 * (size_t)t.numRawPts, err);
 			rc |= up(dSubNum, t.rawNum, t.numSub, err);
 			rc |= up(dSubFirst, t.rawFirst, t.numSub, err);
@@ -1111,8 +1180,10 @@ public:
 		}
 		if (opsMask == 0 || (opsMask & (opsMask - 1))) opsMask = OPS_ALL; /* mixed batches use the general kernel */
 		rc |= up(dDraws, t.draws, t.numDraws, err);
-		rc |= up(dJobSub, t.jobSub, t.numJobs, err);
-		rc |= up(dJobDraw, t.jobDraw, t.numJobs, err);
+		if (!bulkMode) {
+			rc |= up(dJobSub, t.jobSub, t.numJobs, err);
+			rc |= up(dJobDraw, t.jobDraw, t.numJobs, err);
+		}
 		if (rc) return VGB_ERR_CUDA;
 		uploaded = true;
 		ran = false;
@@ -1235,6 +1306,14 @@ public:
 				numPieces = kNumPieces;
 			} else if (readback(&numPieces, dPieceStart.as<uint32_t>() + numJobs, 4, err)) {
 				return VGB_ERR_CUDA;
+			}
+		}
+		if (bulkMode && !sizesKnown) {
+			uint32_t e = 0;
+			if (readback(&e, dBulkErr.p, 4, err)) return VGB_ERR_CUDA;
+			if (e) {
+				if (err) *err = "non-finite coordinate in the bulk input";
+				return VGB_ERR_NONFINITE;
 			}
 		}
 		if (slotsUsed && sizesKnown) {
@@ -1427,13 +1506,14 @@ public:
 		if (color && sz.num_vertices) VGB_CUDA(cudaMemcpyAsync(color, dCol.p, sz.num_vertices * 4, cudaMemcpyDeviceToHost, st));
 		if (index && sz.num_indices) VGB_CUDA(cudaMemcpyAsync(index, dIdx.p, sz.num_indices * idxBytes, cudaMemcpyDeviceToHost, st));
 		if (mvo || mio) {
-			std::vector<uint64_t> tmp(2 * ((size_t)numJobs + 1));
-			VGB_CUDA(cudaMemcpyAsync(tmp.data(), dMeshOff.p, tmp.size() * 8, cudaMemcpyDeviceToHost, st));
-			VGB_CUDA(cudaStreamSynchronize(st));
-			for (size_t j = 0; j <= numJobs; ++j) {
-				if (mvo) mvo[j] = tmp[2 * j];
-				if (mio) mio[j] = tmp[2 * j + 1];
-			}
+			const uint32_t n = numJobs + 1;
+			if (dMeshSplit.ensure((size_t)n * 16, err)) return VGB_ERR_CUDA;
+			uint64_t* dv = dMeshSplit.as<uint64_t>();
+			uint64_t* di = dv + n;
+			k_split_mesh_off<<<(n + 255) / 256, 256, 0, st>>>(dMeshOff.as<ulonglong2>(), n, dv, di);
+			VGB_CUDA(cudaGetLastError());
+			if (mvo) VGB_CUDA(cudaMemcpyAsync(mvo, dv, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
+			if (mio) VGB_CUDA(cudaMemcpyAsync(mio, di, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
 		}
 		VGB_CUDA(cudaStreamSynchronize(st));
 		return 0;

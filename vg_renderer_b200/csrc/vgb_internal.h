@@ -66,6 +66,10 @@ struct HostTables
 	const uint32_t* rawFirst = nullptr;
 	const uint32_t* rawNum = nullptr;
 	const uint8_t* rawClosed = nullptr;
+	/* bulk mode (vgb_batch_set_cubic_strokes): n single-cubic paths, tables generated on the device */
+	const float* bulkP8 = nullptr;
+	uint32_t bulkN = 0;
+	float bulkScale = 1.0f, bulkTol = 0.25f;
 	/* draws and jobs */
 	const DrawRec* draws = nullptr;
 	uint32_t numDraws = 0;
