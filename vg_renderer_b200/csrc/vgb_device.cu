@@ -857,10 +857,16 @@ __global__ void k_mesh_off(const uint32_t* __restrict__ pieceStart, const uint32
 
 /* each warp counts GC consecutive groups; the loads of all of them are issued before any is used
  * (the kernel is a chain of dependent loads: piece -> job record -> points) */
-static constexpr uint32_t GC = 4;
+#ifndef VGB_GC
+#define VGB_GC 2
+#endif
+#ifndef VGB_COUNT_MIN_BLOCKS
+#define VGB_COUNT_MIN_BLOCKS 12
+#endif
+static constexpr uint32_t GC = VGB_GC;
 
 template<uint32_t OPS, int JT, int CT>
-__global__ void __launch_bounds__(128) k_group_count(PieceArgs a)
+__global__ void __launch_bounds__(128, VGB_COUNT_MIN_BLOCKS) k_group_count(PieceArgs a)
 {
 	const uint32_t lane = threadIdx.x & 31;
 	const uint32_t w0 = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * GC;
