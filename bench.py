@@ -13,7 +13,7 @@
   e2e      same metric through the C ABI with HOST buffers: record (memcpy of the pinned input
            into the batch tables) + H2D + run + D2H of pos/colour/index/mesh table into pinned
            host arrays, every step, wall clock between barriers, max over ranks
-  roofline k_piece_emit: algorithmic bytes (32*C + 12*V + 2*I) / its CUDA-event
+  roofline k_group_emit: algorithmic bytes (32*C + 12*V + 2*I) / its CUDA-event
            duration, against MEASURED_PEAKS.json's hbm_gbs
   cpu_baseline / --impl reference: the reference's own path.cpp + stroker.cpp (oracle/_ref,
            compiled from /root/reference against the bx shim) on the host cores
@@ -301,7 +301,7 @@ def main():
                 traffic = tj.get("dram_bytes_per_launch")
         except Exception:  # noqa: BLE001
             pass
-    roofline = {"bound": "hbm", "kernel": "k_piece_emit", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+    roofline = {"bound": "hbm", "kernel": "k_group_emit", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": emit_avg,
                 "pipeline_frac": (alg_bytes / (ms_per_step * 1e-3) / 1e9) / peak,
                 "stage_ms": {"flatten": tm["flatten"], "count_scan": tm["stroke_count"], "emit": tm["emit"], "total": tm["total"]}}

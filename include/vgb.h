@@ -159,6 +159,16 @@ VGB_API int vgb_batch_add_cubic_strokes(vgb_batch* b, const float* p8, uint32_t 
 VGB_API int vgb_batch_add_rounded_rect_fills(vgb_batch* b, const float* xywhr, uint32_t n, float scale, float tess_tol,
                                              uint32_t color, int aa);
 
+/* ingest whole tables (what a command-list front-end would hand over): path p =
+ * commands cmd[path_cmd_off[p] .. path_cmd_off[p+1]) with floats from data[path_data_off[p] ..],
+ * flatten parameters path_scale/tol[p], optional transform path_xform[6p..] (NULL = identity), and the
+ * draws draw_*[draw_begin[p] .. draw_begin[p+1]) issued on it in order.  Same result and validation as
+ * the per-call recording (vgb_batch_begin_path / *_to / stroke / convex_fill). */
+VGB_API int vgb_batch_add_paths(vgb_batch* b, uint32_t num_paths, const uint32_t* path_cmd_off, const uint32_t* path_data_off,
+                                const uint8_t* cmd, const float* data, const float* path_scale, const float* path_tol,
+                                const float* path_xform, const uint32_t* draw_begin, const uint32_t* draw_op,
+                                const uint32_t* draw_color, const float* draw_width, const uint8_t* draw_cap, const uint8_t* draw_join);
+
 /* zero-copy variant for the host-buffer path: REPLACES everything recorded by the n paths of
  * vgb_batch_add_cubic_strokes, but p8 is only borrowed -- it is read (DMA, straight from the
  * caller's memory: make it pinned) by the next vgb_batch_upload / _run / _execute, where the command,

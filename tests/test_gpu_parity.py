@@ -377,3 +377,27 @@ def test_zero_copy_bulk_equals_recorded(gpu_batch, ref):
     gpu_batch.set_cubic_strokes(pin)
     with pytest.raises(vgb.VgbError):
         gpu_batch.begin_path()
+
+
+def test_tiger_like_scene_and_instances(gpu_batch, ref):
+    """BASELINE configs[1]/[4] on the synthetic stand-in for tiger.svg (workloads.tiger_like): every
+    path convex-AA-filled, most AA-stroked; then instanced with random affine transforms, per-instance
+    flatten scale, clamped widths and thin strokes -- the general (mixed-op) kernels at some scale"""
+    t = W.tiger_like()
+    gpu_batch.reset(1.0)
+    gpu_batch.add_tables(t)
+    gpu_batch.run()
+    out = gpu_batch.download()
+    exp = ref.run_batch(t)
+    assert exp["num_meshes"] == 775 and exp["num_subpaths"] == 488
+    check_same(out, exp)
+    ti = W.instance_tables(t, 12)
+    gpu_batch.reset(1.0)
+    gpu_batch.add_tables(ti)
+    gpu_batch.run()
+    check_same(gpu_batch.download(), ref.run_batch(ti))
+    gpu_batch.run(index_u32=True)  # merged index space over the whole instanced scene
+    o32 = gpu_batch.download()
+    e = ref.run_batch(ti)
+    merged = e["index"].astype(np.uint64) + np.repeat(e["mesh_vtx_off"][:-1], np.diff(e["mesh_idx_off"]).astype(np.int64))
+    np.testing.assert_array_equal(o32["index"].astype(np.uint64), merged)

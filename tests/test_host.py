@@ -106,3 +106,37 @@ def test_arc_subpath_rule_and_polyline():
     r = b.recorded()
     assert r["num_subpaths"] == 2 and r["num_cmds"] == 4
     assert r["num_data"] == 6 + 6 + 2 + (1 + 4)
+
+
+def test_table_ingest_equals_per_call_recording():
+    from vg_renderer_b200 import workloads as W
+    t = mixed_recorder().tables()
+    a = vgb.Batch(-1)
+    a.add_tables(t)
+    b = mixed_recorder().replay(vgb.Batch(-1))
+    ra, rb = a.recorded(), b.recorded()
+    for k in ("num_paths", "num_subpaths", "num_cmds", "num_data", "num_draws", "num_jobs"):
+        assert ra[k] == rb[k], k
+    for k in ("cmd_begin", "cmd_end", "data_begin", "path_id", "job_subpath", "job_draw"):
+        np.testing.assert_array_equal(ra[k], rb[k])
+    ti = W.instance_tables(W.tiger_like(40), 5)
+    c = vgb.Batch(-1)
+    c.add_tables(ti)
+    rc = c.recorded()
+    assert rc["num_paths"] == 200 and rc["num_draws"] == len(ti.draw_op)
+    assert set(np.unique(ti.draw_op).tolist()) <= {0, 1, 3}
+    assert np.all(ti.draw_width[ti.draw_op == 3] == 1.0)  # thin strokes carry the fringe as width
+
+
+def test_bulk_zero_copy_recorded_counts():
+    p8 = np.zeros((7, 8), np.float32)
+    b = vgb.Batch(-1)
+    b.set_cubic_strokes(p8)
+    r = b.recorded()
+    assert (r["num_paths"], r["num_subpaths"], r["num_jobs"], r["num_draws"]) == (7, 7, 7, 1)
+    with pytest.raises(vgb.VgbError):
+        b.begin_path()
+    with pytest.raises(vgb.VgbError):
+        b.add_cubic_strokes(p8)
+    b.reset(1.0)
+    b.begin_path().move_to(0, 0)

@@ -85,6 +85,7 @@ def load_library():
     L.vgb_batch_convex_fill.argtypes = [vp, u32, i]
     L.vgb_batch_add_cubic_strokes.argtypes = [vp, vp, u32, f, f, u32, u32, f, u32, u32]
     L.vgb_batch_add_rounded_rect_fills.argtypes = [vp, vp, u32, f, f, u32, i]
+    L.vgb_batch_add_paths.argtypes = [vp, u32] + [vp] * 13
     L.vgb_batch_set_cubic_strokes.argtypes = [vp, vp, u32, f, f, u32, u32, f, u32, u32]
     L.vgb_batch_set_polylines.argtypes = [vp, vp, u32, vp, vp, vp, u32, f, f]
     L.vgb_batch_draw_polyline.argtypes = [vp, u32, u32, u32, f, u32, u32]
@@ -212,6 +213,12 @@ class Batch:
     def add_cubic_strokes(self, p8, scale=1.0, tol=0.25, op=OP_STROKE_AA, color=0xFF0000FF, width=4.0, cap=CAP_ROUND, join=JOIN_ROUND):
         p8 = np.ascontiguousarray(p8, np.float32).reshape(-1, 8)
         return self._chk(self.L.vgb_batch_add_cubic_strokes(self.h, _ptr(p8), len(p8), scale, tol, op, color, width, cap, join))
+
+    def add_tables(self, t):
+        """ingest a tables.BatchTables (numpy) in one call: vgb_batch_add_paths"""
+        return self._chk(self.L.vgb_batch_add_paths(self.h, t.num_paths, _ptr(t.path_cmd_off), _ptr(t.path_data_off), _ptr(t.cmd), _ptr(t.data),
+                                                     _ptr(t.path_scale), _ptr(t.path_tol), _ptr(t.path_xform), _ptr(t.draw_begin), _ptr(t.draw_op),
+                                                     _ptr(t.draw_color), _ptr(t.draw_width), _ptr(t.draw_cap), _ptr(t.draw_join)))
 
     def set_cubic_strokes(self, p8, scale=1.0, tol=0.25, op=OP_STROKE_AA, color=0xFF0000FF, width=4.0, cap=CAP_ROUND, join=JOIN_ROUND):
         """zero-copy bulk input: p8 (float32 [n,8], ideally pinned) is BORROWED until the next upload/run/execute"""

@@ -365,6 +365,46 @@ int vgb_batch_add_cubic_strokes(vgb_batch* b, const float* p8, uint32_t n, float
 	return addDraw(b, op, color, width, cap, join, path0, sub0, sub0 + n);
 }
 
+int vgb_batch_add_paths(vgb_batch* b, uint32_t numPaths, const uint32_t* cmdOff, const uint32_t* dataOff, const uint8_t* cmd, const float* data,
+                        const float* scale, const float* tol, const float* xform, const uint32_t* drawBegin, const uint32_t* drawOp,
+                        const uint32_t* drawColor, const float* drawWidth, const uint8_t* drawCap, const uint8_t* drawJoin)
+{
+	if (!b || (numPaths && (!cmdOff || !dataOff || !scale || !tol || !drawBegin))) return fail(VGB_ERR_INVALID, "null argument");
+	for (uint32_t p = 0; p < numPaths; ++p) {
+		int rc = vgb_batch_begin_path(b, scale[p], tol[p], xform ? xform + 6 * (size_t)p : nullptr);
+		const float* d = data + dataOff[p];
+		for (uint32_t c = cmdOff[p]; c < cmdOff[p + 1] && !rc; ++c) {
+			switch (cmd[c]) {
+			case VGB_CMD_MOVE_TO: rc = vgb_batch_move_to(b, d[0], d[1]); d += 2; break;
+			case VGB_CMD_LINE_TO: rc = vgb_batch_line_to(b, d[0], d[1]); d += 2; break;
+			case VGB_CMD_CUBIC_TO: rc = vgb_batch_cubic_to(b, d[0], d[1], d[2], d[3], d[4], d[5]); d += 6; break;
+			case VGB_CMD_QUAD_TO: rc = vgb_batch_quadratic_to(b, d[0], d[1], d[2], d[3]); d += 4; break;
+			case VGB_CMD_ARC_TO: rc = vgb_batch_arc_to(b, d[0], d[1], d[2], d[3], d[4]); d += 5; break;
+			case VGB_CMD_RECT: rc = vgb_batch_rect(b, d[0], d[1], d[2], d[3]); d += 4; break;
+			case VGB_CMD_ROUNDED_RECT: rc = vgb_batch_rounded_rect(b, d[0], d[1], d[2], d[3], d[4]); d += 5; break;
+			case VGB_CMD_ROUNDED_RECT_VARYING: rc = vgb_batch_rounded_rect_varying(b, d[0], d[1], d[2], d[3], d[4], d[5], d[6], d[7]); d += 8; break;
+			case VGB_CMD_CIRCLE: rc = vgb_batch_circle(b, d[0], d[1], d[2]); d += 3; break;
+			case VGB_CMD_ELLIPSE: rc = vgb_batch_ellipse(b, d[0], d[1], d[2], d[3]); d += 4; break;
+			case VGB_CMD_ARC: rc = vgb_batch_arc(b, d[0], d[1], d[2], d[3], d[4], d[5] != 0.0f ? VGB_WINDING_CW : VGB_WINDING_CCW); d += 6; break;
+			case VGB_CMD_POLYLINE: {
+				uint32_t np;
+				memcpy(&np, d, 4);
+				rc = vgb_batch_polyline(b, d + 1, np);
+				d += 1 + 2 * (size_t)np;
+			} break;
+			case VGB_CMD_CLOSE: rc = vgb_batch_close(b); break;
+			default: rc = fail(VGB_ERR_INVALID, "unknown command");
+			}
+		}
+		for (uint32_t k = drawBegin[p]; k < drawBegin[p + 1] && !rc; ++k) {
+			if (drawOp[k] == VGB_OP_CONVEX_FILL_AA || drawOp[k] == VGB_OP_CONVEX_FILL) rc = vgb_batch_convex_fill(b, drawColor[k], drawOp[k] == VGB_OP_CONVEX_FILL_AA);
+			else rc = vgb_batch_stroke(b, drawOp[k], drawColor[k], drawWidth[k], drawCap[k], drawJoin[k]);
+		}
+		if (rc) return rc;
+	}
+	return 0;
+}
+
 int vgb_batch_set_cubic_strokes(vgb_batch* b, const float* p8, uint32_t n, float scale, float tol,
                                 uint32_t op, uint32_t color, float width, uint32_t cap, uint32_t join)
 {
