@@ -1000,12 +1000,14 @@ __global__ void __launch_bounds__(128, VGB_EMIT_MIN_BLOCKS) k_group_emit(PieceAr
 		S.col = a.col + bb.x + vl;
 		S.idx = reinterpret_cast<IDX*>(a.idx) + bb.y + il;
 	}
-	const bool isCap = P.kind == PK_CAP_START || P.kind == PK_CAP_END;
-	if (valid && !isCap) {
-		emitPiece<OPS, JT, CT>(a, J, P, F, prev, S);
-	}
-	if (valid && isCap) {
-		emitPiece<OPS, JT, CT>(a, J, P, F, prev, S); /* the few cap lanes of the warp, after the joins */
+	if (valid) {
+		if ((OPS & OPS_STROKE_AA) && (!(OPS & ~OPS_STROKE_AA) || J.op == VGB_OP_STROKE_AA)) {
+			/* joins and round caps share one code path (see emitStrokeAA) */
+			const bool firstLeft = (P.flags & PF_CLOSING) ? firstJoinLeft(J, a.pts) : false;
+			emitStrokeAA<JT, CT>(J, P, F, prev, firstLeft, S);
+		} else {
+			emitPiece<OPS, JT, CT>(a, J, P, F, prev, S);
+		}
 	}
 	if (fits) {
 		fenceProxyAsync();

@@ -307,6 +307,7 @@ __device__ __forceinline__ Piece classify(const JobCtx& J, uint32_t q, const flo
 				P.n = J.nHC;
 				P.vcount = 2 * J.nHC;
 				P.icount = isStart ? 9 * J.nHC - 12 : 9 * J.nHC + 6;
+				P.a01 = vgb_atan2(P.d01.x, -P.d01.y); /* startAngle = atan2(l.y, l.x), l = perpCCW(d) (1476, 1919) */
 			} else {
 				P.vcount = 4;
 				P.icount = isStart ? 6u : 24u;
@@ -613,6 +614,96 @@ __device__ __forceinline__ void emitJoinAA(const JobCtx& J, const Piece& P, uint
 	}
 	if (P.flags & PF_CLOSING) {
 		/* stroker.cpp:1970-1984: previous = this piece, first = piece 0 (its F is 0) */
+		S.connect(k, out4FromTail(0, jt, packTail(P), F + P.vcount), joinIn4(firstLeft, 0));
+	}
+}
+
+/*
+ * Joins AND round caps of an AA stroke through one code path (used by the warp-autonomous kernel,
+ * where the few cap lanes of a warp would otherwise run a whole separate function while the join
+ * lanes wait).  A round cap is emitted as "a join without inner pair whose every arc point is a
+ * middle point": both kinds share the sin/cos loop and the paired stores; only the short index
+ * patterns differ.  Butt/square caps (4 vertices) and miter joins keep their own small bodies.
+ * Values are exactly those of emitJoinAA / emitCapAA (same expressions, same order).
+ */
+template<int JT = 3, int CT = 3, class SINK>
+__device__ __forceinline__ void emitStrokeAA(const JobCtx& J, const Piece& P, uint32_t F, uint4 prev, bool firstLeft, const SINK& S)
+{
+	const uint32_t jt = JT < 3 ? (uint32_t)JT : J.join;
+	const uint32_t ct = CT < 3 ? (uint32_t)CT : J.cap;
+	const bool isCap = P.kind != PK_JOIN;
+	const bool isEnd = P.kind == PK_CAP_END;
+	if ((isCap && ct != VGB_CAP_ROUND) || (!isCap && jt == VGB_JOIN_MITER)) {
+		if (isCap) {
+			CapRec R;
+			R.p = P.p; R.d = P.d01; R.hsw = J.hsw; R.hsw_aa = J.hsw_aa; R.fringe = J.fringe; R.color = J.color; R.c0 = J.c0;
+			R.n = P.n; R.F = F; R.prev = prev; R.vl = 0; R.il = 0; R.base = S.base; R.info = (ct << 16) | ((isEnd ? 1u : 0u) << 24);
+			emitCapAA<CT>(R, S);
+		} else {
+			emitJoinAA<JT>(J, P, F, prev, firstLeft, S);
+		}
+		return;
+	}
+	const bool left = (P.flags & PF_LEFT) != 0;
+	const float hsw = J.hsw, hsw_aa = J.hsw_aa;
+	const float2 p1 = P.p;
+	const uint32_t n = P.n; /* join: arc segments; cap: nHC */
+	if (!isCap) {
+		const float2 vs = left ? P.v : f2(-P.v.x, -P.v.y);
+		const float2 d01 = P.d01, d12 = P.d12;
+		const float2 s01 = left ? f2(d01.y, -d01.x) : f2(-d01.y, d01.x);
+		const float2 s12 = left ? f2(d12.y, -d12.x) : f2(-d12.y, d12.x);
+		S.VP(0, p1.x + vs.x * hsw_aa, p1.y + vs.y * hsw_aa, J.c0, p1.x + vs.x * hsw, p1.y + vs.y * hsw, J.color);
+		float ax = p1.x + s01.x * hsw, ay = p1.y + s01.y * hsw;
+		float bx = p1.x + s12.x * hsw, by = p1.y + s12.y * hsw;
+		if (jt == VGB_JOIN_BEVEL) {
+			const float t = fabsf(s01.x * s12.x + s01.y * s12.y) * J.fringe;
+			ax = ax - d01.x * t;
+			ay = ay - d01.y * t;
+			bx = bx + d12.x * t;
+			by = by + d12.y * t;
+		}
+		S.VP(2, ax, ay, J.color, p1.x + s01.x * hsw_aa, p1.y + s01.y * hsw_aa, J.c0);
+		S.VP(2 + 2 * n, bx, by, J.color, p1.x + s12.x * hsw_aa, p1.y + s12.y * hsw_aa, J.c0);
+	}
+	/* arc points by angle: joins i = 1..n-1 at vertex 2+2i, caps i = 0..nHC-1 at vertex 2i */
+	const uint32_t vb = isCap ? 0u : 2u;
+	const float capDen = (float)(n - 1);
+	for (uint32_t i = isCap ? 0u : 1u; i < n; ++i) {
+		const float t = isCap ? (float)i * VGB_PI / capDen : (float)i * P.arcDa;
+		const float a = P.a01 + (isEnd ? -t : t);
+		float sa, ca;
+		vgb_sincos(a, &sa, &ca);
+		S.VP(vb + 2 * i, p1.x + ca * hsw, p1.y + sa * hsw, J.color, p1.x + ca * hsw_aa, p1.y + sa * hsw_aa, J.c0);
+	}
+	uint32_t k = 0;
+	if (P.flags & PF_HAS_PREV) {
+		const uint32_t e = F + 2 * (n - 1);
+		S.connect(0, prev, isCap ? make_uint4(F + 1, F, e, e + 1) : joinIn4(left, F));
+		k = 18;
+	}
+	if (isCap) {
+		/* fan + fringe quads (1491-1510 / 1947-1968): an end cap swaps the 2nd and 3rd index of each triangle */
+		const uint32_t o2 = isEnd ? 4u : 2u, o3 = isEnd ? 2u : 4u;
+		for (uint32_t i = 0; i + 2 < n; ++i, k += 3) {
+			S.tri(k, F, F + 2 * i + o2, F + 2 * i + o3);
+		}
+		const uint32_t q2 = isEnd ? 3u : 1u, q3 = isEnd ? 1u : 3u, r2 = isEnd ? 2u : 3u, r3 = isEnd ? 3u : 2u;
+		for (uint32_t i = 0; i + 1 < n; ++i, k += 6) {
+			const uint32_t b = F + 2 * i;
+			S.tri(k, b, b + q2, b + q3);
+			S.tri(k + 3, b, b + r2, b + r3);
+		}
+		return;
+	}
+	uint32_t A = F + 2;
+	const uint32_t u2 = left ? 0u : 2u, u3 = left ? 2u : 0u, w2 = left ? 1u : 3u, w3 = left ? 3u : 1u, x2 = left ? 3u : 2u, x3 = left ? 2u : 3u;
+	for (uint32_t i = 0; i < n; ++i, k += 9, A += 2) {
+		S.tri(k, F + 1, A + u2, A + u3);
+		S.tri(k + 3, A, A + w2, A + w3);
+		S.tri(k + 6, A, A + x2, A + x3);
+	}
+	if (P.flags & PF_CLOSING) {
 		S.connect(k, out4FromTail(0, jt, packTail(P), F + P.vcount), joinIn4(firstLeft, 0));
 	}
 }
