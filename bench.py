@@ -107,14 +107,23 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------
 # CPU reference arm (oracle/_ref): one process per host core, disjoint curve ranges
 # ------------------------------------------------------------------------------------------
+_BARRIER = None
+
+
+def _cpu_init(barrier):
+    global _BARRIER
+    _BARRIER = barrier
+
+
 def _cpu_worker(args):
-    kind, first, count, barrier_path = args
+    kind, first, count = args
     from oracle.pyref import RefLib
     from vg_renderer_b200 import workloads as W
     from vg_renderer_b200.tables import BatchTables
     lib = RefLib(kind)
     t = BatchTables.cubic_strokes(W.config3_cubics(count, first=first), width=WIDTH, cap=CAP, join=JOIN)
     lib.run_batch(t, store=False, path_range=(0, min(count, 2000)))  # warm caches / allocator
+    _BARRIER.wait()  # every process starts the timed part together
     t0 = time.perf_counter()
     out = lib.run_batch(t, store=False)
     t1 = time.perf_counter()
@@ -122,11 +131,13 @@ def _cpu_worker(args):
 
 
 def cpu_reference_run(per_proc, procs, kind):
-    """-> (total_vertices, wall_seconds): all processes run concurrently on disjoint ranges."""
+    """-> (total_vertices, wall_seconds): one process per core on disjoint ranges of the stream, all
+    released by a barrier; wall = first start to last finish (CLOCK_MONOTONIC is system-wide)."""
     import multiprocessing as mp
     ctx = mp.get_context("fork")
-    with ctx.Pool(procs) as pool:
-        res = pool.map(_cpu_worker, [(kind, i * per_proc, per_proc, None) for i in range(procs)])
+    barrier = ctx.Barrier(procs)
+    with ctx.Pool(procs, initializer=_cpu_init, initargs=(barrier,)) as pool:
+        res = pool.map(_cpu_worker, [(kind, i * per_proc, per_proc) for i in range(procs)], chunksize=1)
     verts = sum(r[0] for r in res)
     wall = max(r[2] for r in res) - min(r[1] for r in res)
     return verts, wall

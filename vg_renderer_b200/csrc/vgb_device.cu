@@ -813,12 +813,12 @@ __global__ void __launch_bounds__(PPB, VGB_EMIT_MIN_BLOCKS) k_piece_emit(PieceAr
 #ifndef VGB_CVW
 #define VGB_CVW 288
 #endif
-#ifndef VGB_CIW_BYTES
-#define VGB_CIW_BYTES 2560
+#ifndef VGB_CIW
+#define VGB_CIW 1280
 #endif
 static constexpr uint32_t GRP = VGB_GROUP32 ? 32u : PPB; /* pieces per offset group */
 static constexpr uint32_t CVW = VGB_CVW;                 /* staged vertices per warp */
-static constexpr uint32_t CIW_BYTES = VGB_CIW_BYTES;     /* staged index bytes per warp */
+static constexpr uint32_t CIW_COUNT = VGB_CIW;           /* staged indices per warp (uint16 or uint32) */
 
 __device__ __forceinline__ uint2 warpInclusive(uint2 v, uint32_t lane)
 {
@@ -932,10 +932,12 @@ __global__ void __launch_bounds__(128, VGB_COUNT_MIN_BLOCKS) k_group_count(Piece
 	}
 }
 
-template<class IDX, uint32_t OPS, int JT, int CT>
+/* BIGI: index image sized for ~40 indices per piece (uint32 output of fat pieces); otherwise half of
+ * that for uint32, so that thin meshes keep 9 blocks per SM.  uint16 always uses the full count. */
+template<class IDX, uint32_t OPS, int JT, int CT, bool BIGI>
 __global__ void __launch_bounds__(128, VGB_EMIT_MIN_BLOCKS) k_group_emit(PieceArgs a)
 {
-	constexpr uint32_t CIW = CIW_BYTES / sizeof(IDX);
+	constexpr uint32_t CIW = (sizeof(IDX) == 2 || BIGI) ? CIW_COUNT : CIW_COUNT / 2;
 	constexpr uint32_t KI = 16 / sizeof(IDX);
 	constexpr uint32_t POS_BYTES = (CVW + 2) * 8, COL_BYTES = (CVW + 4) * 4, IDX_BYTES = (CIW + KI) * sizeof(IDX);
 	constexpr uint32_t WBYTES = POS_BYTES + COL_BYTES + IDX_BYTES;
@@ -1411,17 +1413,23 @@ public:
 			pa.col = dCol.as<uint32_t>();
 			pa.idx = dIdx.p;
 #if VGB_GROUP32
-#define VGB_EMIT_K k_group_emit
+			/* uint32 indices: pick the index-image size from the batch's average indices per group */
+			const bool bigI = idxBytes == 4 && numBlocks > 0 && totals[1] / numBlocks > (uint64_t)(CIW_COUNT / 2) * 3 / 4;
+#define VGB_EMIT_K(T, O, J, C)                                                   \
+	do {                                                                         \
+		if (bigI) k_group_emit<T, O, J, C, true><<<gridBlocks, PPB, 0, st>>>(pa); \
+		else k_group_emit<T, O, J, C, false><<<gridBlocks, PPB, 0, st>>>(pa);     \
+	} while (0)
 #else
-#define VGB_EMIT_K k_piece_emit
+#define VGB_EMIT_K(T, O, J, C) k_piece_emit<T, O, J, C><<<gridBlocks, PPB, 0, st>>>(pa)
 #endif
 #define VGB_LAUNCH_EMIT(T)                                                                                  \
 	do {                                                                                                    \
-		if (opsMask == OPS_STROKE_AA && uniJoin == VGB_JOIN_ROUND && uniCap == VGB_CAP_ROUND) VGB_EMIT_K<T, OPS_STROKE_AA, 1, 1><<<gridBlocks, PPB, 0, st>>>(pa); \
-		else if (opsMask == OPS_STROKE_AA && uniJoin == VGB_JOIN_MITER && uniCap == VGB_CAP_BUTT) VGB_EMIT_K<T, OPS_STROKE_AA, 0, 0><<<gridBlocks, PPB, 0, st>>>(pa); \
-		else if (opsMask == OPS_STROKE_AA) VGB_EMIT_K<T, OPS_STROKE_AA, 3, 3><<<gridBlocks, PPB, 0, st>>>(pa); \
-		else if (opsMask == OPS_FILL_AA) VGB_EMIT_K<T, OPS_FILL_AA, 3, 3><<<gridBlocks, PPB, 0, st>>>(pa); \
-		else VGB_EMIT_K<T, OPS_ALL, 3, 3><<<gridBlocks, PPB, 0, st>>>(pa);                                 \
+		if (opsMask == OPS_STROKE_AA && uniJoin == VGB_JOIN_ROUND && uniCap == VGB_CAP_ROUND) VGB_EMIT_K(T, OPS_STROKE_AA, 1, 1); \
+		else if (opsMask == OPS_STROKE_AA && uniJoin == VGB_JOIN_MITER && uniCap == VGB_CAP_BUTT) VGB_EMIT_K(T, OPS_STROKE_AA, 0, 0); \
+		else if (opsMask == OPS_STROKE_AA) VGB_EMIT_K(T, OPS_STROKE_AA, 3, 3); \
+		else if (opsMask == OPS_FILL_AA) VGB_EMIT_K(T, OPS_FILL_AA, 3, 3); \
+		else VGB_EMIT_K(T, OPS_ALL, 3, 3);                                 \
 	} while (0)
 			if (idxBytes == 2) {
 				VGB_LAUNCH_EMIT(uint16_t);
