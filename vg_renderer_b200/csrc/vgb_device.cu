@@ -1024,6 +1024,65 @@ __global__ void __launch_bounds__(128, VGB_EMIT_MIN_BLOCKS) k_group_emit(PieceAr
 }
 
 /* =========================================================================================
+ * pure convex-AA-fill batches (BASELINE configs[3]): sizes are closed-form (V = 2N, I = 9N - 6,
+ * stroker.cpp:726-730), so there is no count pass at all, and every output of a polygon vertex has
+ * a closed-form address in its mesh: the vertex pair at 2i, its fan triangle at 3i (i < N-2), its
+ * fringe quad at 3(N-2) + 6i.  One thread per polygon vertex writes them straight to HBM --
+ * consecutive lanes write consecutive addresses in each of the four streams.
+ * ======================================================================================= */
+__global__ void k_fill_job_sizes(const uint32_t* __restrict__ jobSub, uint32_t numJobs, const uint32_t* __restrict__ subNum,
+                                 uint32_t* __restrict__ jobPieces, uint2* __restrict__ meshTotals)
+{
+	const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+	if (j >= numJobs) return;
+	const uint32_t N = subNum[jobSub[j]];
+	const bool ok = N >= 3; /* vg.cpp:3101 */
+	jobPieces[j] = ok ? N : 0u;
+	meshTotals[j] = ok ? make_uint2(2 * N, 9 * N - 6) : make_uint2(0u, 0u);
+}
+
+template<class IDX>
+__global__ void __launch_bounds__(256) k_fill_emit(PieceArgs a)
+{
+	const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+	if (g >= a.numPieces) return;
+	const uint32_t j = a.pieceJob[g];
+	uint32_t ps;
+	const JobCtx J = loadJob(a, j, &ps);
+	const uint32_t i = g - ps, N = J.N;
+	const ulonglong2 mo = a.meshOff[j];
+	const float2* v = a.pts + J.first;
+	const float2 p = v[i];
+	const float2 d01 = vdir(v[i == 0 ? N - 1 : i - 1], p);
+	const float2 d12 = vdir(p, v[i == N - 1 ? 0 : i + 1]);
+	/* orientation from the first triangle, stroker.cpp:721-723 */
+	const float2 p0 = v[0], p1 = v[1], p2 = v[2];
+	const float ax = p1.x - p0.x, ay = p1.y - p0.y, bx = p2.x - p0.x, by = p2.y - p0.y;
+	const float aa = J.fringe * 0.5f * vgb_sign(ax * by - bx * ay);
+	const float2 e = extrusion(d01, d12);
+	const float ex = e.x * aa, ey = e.y * aa;
+	reinterpret_cast<float4*>(a.pos + mo.x)[i] = make_float4(p.x + ex, p.y + ey, p.x - ex, p.y - ey);
+	reinterpret_cast<uint2*>(a.col + mo.x)[i] = make_uint2(J.color, J.c0);
+	const uint32_t base = sizeof(IDX) == 2 ? 0u : (uint32_t)(mo.x + a.vertexBase);
+	IDX* idx = reinterpret_cast<IDX*>(a.idx) + mo.y;
+	const uint32_t f = 2 * i;
+	if (i + 2 < N) {
+		IDX* t = idx + 3 * i;
+		t[0] = (IDX)(base);
+		t[1] = (IDX)(base + f + 2);
+		t[2] = (IDX)(base + f + 4);
+	}
+	IDX* q = idx + 3 * (N - 2) + 6 * i;
+	const uint32_t nA = (i + 1 < N) ? f + 3 : 1u, nB = (i + 1 < N) ? f + 2 : 0u; /* next vertex's (outer, inner), wrapping to (1, 0) */
+	q[0] = (IDX)(base + f);
+	q[1] = (IDX)(base + f + 1);
+	q[2] = (IDX)(base + nA);
+	q[3] = (IDX)(base + f);
+	q[4] = (IDX)(base + nA);
+	q[5] = (IDX)(base + nB);
+}
+
+/* =========================================================================================
  * host side
  * ======================================================================================= */
 struct DevBuf
@@ -1301,6 +1360,7 @@ public:
 		VGB_CUDA(cudaEventRecord(ev[1], st));
 
 		/* ---- draws, jobs, pieces ---- */
+		const bool fillOnly = opsMask == OPS_FILL_AA && VGB_GROUP32 && getenv("VGB_GENERIC_FILL") == nullptr;
 		uint32_t numPieces = 0;
 		if (numJobs) {
 			if (dDD.ensure((size_t)numDraws * sizeof(DrawDerived), err) || dJobPieces.ensure((size_t)numJobs * 4, err) ||
@@ -1308,8 +1368,14 @@ public:
 				return VGB_ERR_CUDA;
 			k_draw_prep<<<(numDraws + 127) / 128, 128, 0, st>>>(dDraws.as<DrawRec>(), numDraws, dScale.as<float>(), dTol.as<float>(), ht.fringe,
 			                                                     dDD.as<DrawDerived>());
-			k_job_pieces<<<(numJobs + 255) / 256, 256, 0, st>>>(dJobSub.as<uint32_t>(), dJobDraw.as<uint32_t>(), numJobs, dSubNum.as<uint32_t>(),
-			                                                     dDraws.as<DrawRec>(), dJobPieces.as<uint32_t>());
+			if (fillOnly) {
+				if (dMeshTotals.ensure((size_t)numJobs * 8, err)) return VGB_ERR_CUDA;
+				k_fill_job_sizes<<<(numJobs + 255) / 256, 256, 0, st>>>(dJobSub.as<uint32_t>(), numJobs, dSubNum.as<uint32_t>(),
+				                                                         dJobPieces.as<uint32_t>(), dMeshTotals.as<uint2>());
+			} else {
+				k_job_pieces<<<(numJobs + 255) / 256, 256, 0, st>>>(dJobSub.as<uint32_t>(), dJobDraw.as<uint32_t>(), numJobs, dSubNum.as<uint32_t>(),
+				                                                     dDraws.as<DrawRec>(), dJobPieces.as<uint32_t>());
+			}
 			launches += 2;
 			if (scan<ScanOps<uint32_t>>(dJobPieces.as<uint32_t>(), numJobs, dPieceStart.as<uint32_t>(), err)) return VGB_ERR_CUDA;
 			if (sizesKnown) {
@@ -1370,6 +1436,10 @@ public:
 			pa.blockBase = dBlockBase.as<ulonglong2>();
 			pa.meshOff = dMeshOff.as<ulonglong2>();
 			pa.vertexBase = vertexBase;
+			if (fillOnly) {
+				/* closed-form sizes: the mesh table is a plain scan of (2N, 9N-6); no count kernel */
+				if (scan<ScanOps<uint2>>(dMeshTotals.as<uint2>(), numJobs, dMeshOff.as<ulonglong2>(), err)) return VGB_ERR_CUDA;
+			} else {
 #if VGB_GROUP32
 #define VGB_COUNT_K k_group_count
 			const uint32_t countBlocks = (numBlocks + 4 * GC - 1) / (4 * GC); /* 4 warps per block, GC groups per warp */
@@ -1392,6 +1462,7 @@ public:
 #else
 			if (scan<ScanOps<uint2>>(dMeshTotals.as<uint2>(), numJobs, dMeshOff.as<ulonglong2>(), err)) return VGB_ERR_CUDA;
 #endif
+			} /* !fillOnly */
 			if (sizesKnown) {
 				totals[0] = kTotals[0];
 				totals[1] = kTotals[1];
@@ -1431,7 +1502,10 @@ public:
 		else if (opsMask == OPS_FILL_AA) VGB_EMIT_K(T, OPS_FILL_AA, 3, 3); \
 		else VGB_EMIT_K(T, OPS_ALL, 3, 3);                                 \
 	} while (0)
-			if (idxBytes == 2) {
+			if (fillOnly) {
+				if (idxBytes == 2) k_fill_emit<uint16_t><<<(numPieces + 255) / 256, 256, 0, st>>>(pa);
+				else k_fill_emit<uint32_t><<<(numPieces + 255) / 256, 256, 0, st>>>(pa);
+			} else if (idxBytes == 2) {
 				VGB_LAUNCH_EMIT(uint16_t);
 			} else {
 				VGB_LAUNCH_EMIT(uint32_t);
