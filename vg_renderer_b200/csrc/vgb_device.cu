@@ -4,17 +4,20 @@
  * Kernels (all HBM-streaming fp32/integer work: no tensor cores -- there is no dense
  * contraction anywhere on this path):
  *
- *   k_flatten<false>   thread per sub-path: walk commands, count polyline points
- *   scan (u32)         sub-path point counts -> first-vertex offsets
- *   k_flatten<true>    same walk, store (transformed) points at the scanned offsets
- *   k_draw_prep        per-draw constants (hsw, da, nHC ...) with the shared fp32 math
- *   k_job_pieces       pieces per job (mesh)            -> scan -> pieceStart
- *   k_block_first_job  first job overlapping each 128-piece block
- *   k_piece_count      thread per piece: classify() -> per-block (V,I) totals + per-mesh totals
- *   scan (u32x2->u64x2) block totals -> block bases; mesh totals -> mesh table
- *   k_piece_emit       the hot kernel: thread per piece emits its vertices/colours/indices into
- *                      a shared-memory image of the block's (contiguous) output range, then the
- *                      whole block streams that image to HBM with 128-bit coalesced stores.
+ *   k_flatten_slots    thread per sub-path, ONE pass: walk commands, store (transformed) points into
+ *                      the sub-path's recorder-sized slot (overflow arena + two-pass fallback
+ *                      k_flatten<false/true> + scan)
+ *   k_bulk_cubic_tables  bulk mode: all tables generated on the device from the caller's coordinates
+ *   k_draw_prep        per-draw constants (hsw, da, nHC, nfix ...) with the shared fp32 math
+ *   k_job_pieces       pieces per job (mesh) -> scan -> pieceStart;  k_job_prep: 48-byte job records
+ *                      + per-piece job ids
+ *   k_group_count      lane per piece: sizes -> per-warp-group (V,I) totals, hand-over words,
+ *                      within-group mesh starts (geometry-free shortcut when sizes are provable)
+ *   scan (u32x2->u64x2), k_mesh_off   group bases, mesh table
+ *   k_group_emit       the hot kernel: a warp owns 32 pieces = one contiguous output range; lanes emit
+ *                      vertices / colours / indices into a warp-private shared-memory image that
+ *                      leaves through the TMA engine (cp.async.bulk), no block barrier anywhere
+ *   k_fill_job_sizes, k_fill_emit   pure convex-AA-fill batches: closed-form sizes and addresses
  *
  * Build: nvcc -gencode arch=compute_100a,code=sm_100a -fmad=false (see Makefile).  -fmad=false
  * plus vgb_math.h's __f*_rn intrinsics make every float result identical to the non-FMA CPU
@@ -40,21 +43,10 @@ namespace vgb
 		}                                                                                     \
 	} while (0)
 
-#ifndef VGB_PPB
-#define VGB_PPB 128
-#endif
-#ifndef VGB_CV
-#define VGB_CV 1536
-#endif
-#ifndef VGB_CI_BYTES
-#define VGB_CI_BYTES 13312
-#endif
 #ifndef VGB_EMIT_MIN_BLOCKS
 #define VGB_EMIT_MIN_BLOCKS 9
 #endif
-static constexpr uint32_t PPB = VGB_PPB;           /* pieces per block == threads per block   */
-static constexpr uint32_t CV = VGB_CV;             /* staged vertices per round               */
-static constexpr uint32_t CI_BYTES = VGB_CI_BYTES; /* staged index bytes per round            */
+static constexpr uint32_t PPB = 128; /* threads per block of the piece kernels (4 warps = 4 groups) */
 
 /* =========================================================================================
  * scans
@@ -80,17 +72,6 @@ template<> struct ScanOps<uint2>
 	{
 		return make_ulonglong2(__shfl_up_sync(0xffffffffu, a.x, d), __shfl_up_sync(0xffffffffu, a.y, d));
 	}
-};
-
-/* in-block variant: sums of one block fit 32 bits */
-struct ScanOpsU2
-{
-	typedef uint2 In;
-	typedef uint2 Acc;
-	__device__ static Acc zero() { return make_uint2(0u, 0u); }
-	__device__ static Acc cvt(In a) { return a; }
-	__device__ static Acc add(Acc a, Acc b) { return make_uint2(a.x + b.x, a.y + b.y); }
-	__device__ static Acc shflUp(Acc a, int d) { return make_uint2(__shfl_up_sync(0xffffffffu, a.x, d), __shfl_up_sync(0xffffffffu, a.y, d)); }
 };
 
 static constexpr uint32_t SCAN_THREADS = 256;
@@ -500,51 +481,6 @@ __device__ __forceinline__ JobCtx loadJob(const PieceArgs& a, uint32_t j, uint32
 	return J;
 }
 
-/* shared prologue of count and emit: which job / local piece does this thread own */
-struct Owner
-{
-	uint32_t j, q;
-	bool valid;
-};
-
-template<uint32_t OPS, int JT, int CT>
-__global__ void __launch_bounds__(PPB) k_piece_count(PieceArgs a)
-{
-	const uint32_t g = blockIdx.x * PPB + threadIdx.x;
-	Owner o;
-	o.valid = g < a.numPieces;
-	o.j = o.valid ? a.pieceJob[g] : 0;
-	o.q = 0;
-	uint32_t vc = 0, ic = 0;
-	if (o.valid) {
-		uint32_t ps;
-		const JobCtx J = loadJob(a, o.j, &ps);
-		o.q = g - ps;
-		const Piece P = classify<OPS, JT, CT>(J, o.q, a.pts);
-		vc = P.vcount;
-		ic = P.icount;
-		if (threadIdx.x == PPB - 1) {
-			a.blockTail[blockIdx.x] = packTail(P);
-		}
-	}
-	/* per-mesh totals: lanes of one warp owning the same job reduce first, one atomic per run */
-	{
-		const uint32_t key = o.valid ? o.j : 0xFFFFFFFFu;
-		const uint32_t m = __match_any_sync(0xffffffffu, key);
-		const uint32_t sv = __reduce_add_sync(m, vc);
-		const uint32_t si = __reduce_add_sync(m, ic);
-		if (o.valid && (threadIdx.x & 31) == (uint32_t)(__ffs(m) - 1)) {
-			atomicAdd(&a.meshTotals[o.j].x, sv);
-			atomicAdd(&a.meshTotals[o.j].y, si);
-		}
-	}
-	uint2 total;
-	blockInclusive<ScanOpsU2, false>(make_uint2(vc, ic), &total);
-	if (threadIdx.x == 0) {
-		a.blockTotals[blockIdx.x] = total;
-	}
-}
-
 /* ---- shared -> global copy-out through the TMA engine (1-D bulk copy, no tensor map) ----------
  * The block's output image sits in shared memory laid out so that element e is at
  * sbuf[e - alignedBase]: 16-byte chunks of the image line up with 16-byte chunks of HBM.  The
@@ -562,7 +498,6 @@ __device__ __forceinline__ void bulkStore(void* gdst, const void* ssrc, uint32_t
 }
 __device__ __forceinline__ void bulkCommit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulkWaitRead() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
-__device__ __forceinline__ void bulkWaitAll() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
 /* one WARP streams one array: lane 0 issues (and later waits for) the bulk copy of the 16-byte
  * aligned body, lanes 1..16 store the ragged head/tail (fewer than 16 bytes each) */
@@ -593,28 +528,6 @@ __device__ __forceinline__ void copyOutWarp(T* __restrict__ gbase, uint64_t gs, 
 	}
 }
 
-__device__ __forceinline__ CapRec makeCapRec(const JobCtx& J, const Piece& P, uint32_t F, uint4 prev, uint32_t vl, uint32_t il, uint32_t base, uint32_t owner)
-{
-	CapRec R;
-	R.p = P.p;
-	R.d = P.d01;
-	R.hsw = J.hsw;
-	R.hsw_aa = J.hsw_aa;
-	R.fringe = J.fringe;
-	R.color = J.color;
-	R.c0 = J.c0;
-	R.n = P.n;
-	R.F = F;
-	R.prev = prev;
-	R.vl = vl;
-	R.il = il;
-	R.base = base;
-	R.info = owner | (J.cap << 16) | ((P.kind == PK_CAP_END ? 1u : 0u) << 24);
-	return R;
-}
-
-static constexpr uint32_t CAPMAX = 32; /* caps per block handed to warp 0; the rest are emitted in place */
-
 template<uint32_t OPS, int JT, int CT, class SINK>
 __device__ __forceinline__ void emitPiece(const PieceArgs& a, const JobCtx& J, const Piece& P, uint32_t F, uint4 prev, const SINK& S)
 {
@@ -635,11 +548,7 @@ __device__ __forceinline__ void emitPiece(const PieceArgs& a, const JobCtx& J, c
 		S.V(0, P.p.x, P.p.y, J.color);
 		return;
 	}
-	if ((OPS & OPS_STROKE_AA) && P.kind == PK_JOIN) {
-		const bool firstLeft = (P.flags & PF_CLOSING) ? firstJoinLeft(J, a.pts) : false;
-		emitJoinAA<JT>(J, P, F, prev, firstLeft, S);
-	} else if ((OPS & OPS_STROKE_AA) && (P.kind == PK_CAP_START || P.kind == PK_CAP_END)) {
-		emitCapAA<CT>(makeCapRec(J, P, F, prev, 0, 0, S.base, 0), S);
+	if (false) {
 	} else if ((OPS & OPS_FILL_AA) && P.kind == PK_FILL_VTX) {
 		emitFillVtx(J, P, a.pts, S);
 	} else if ((OPS & OPS_FILL_AA) && P.kind == PK_FILL_FAN) {
@@ -647,176 +556,21 @@ __device__ __forceinline__ void emitPiece(const PieceArgs& a, const JobCtx& J, c
 	}
 }
 
-template<class IDX, uint32_t OPS, int JT, int CT>
-__global__ void __launch_bounds__(PPB, VGB_EMIT_MIN_BLOCKS) k_piece_emit(PieceArgs a)
-{
-	constexpr uint32_t CI = CI_BYTES / sizeof(IDX);
-	constexpr uint32_t KI = 16 / sizeof(IDX);
-	__shared__ uint32_t sVl[PPB + 1];
-	__shared__ uint32_t sIl[PPB + 1];
-	__shared__ uint32_t sTail[PPB];
-	__shared__ CapRec sCap[CAPMAX];
-	__shared__ uint32_t sCapCount;
-	__shared__ __align__(16) float2 sPos[CV + 2];
-	__shared__ __align__(16) uint32_t sCol[CV + 4];
-	__shared__ __align__(16) IDX sIdx[CI + KI];
-
-	const uint32_t t = threadIdx.x;
-	const uint32_t g = blockIdx.x * PPB + t;
-	if (t == 0) {
-		sCapCount = 0;
-	}
-	Owner o;
-	o.valid = g < a.numPieces;
-	o.j = o.valid ? a.pieceJob[g] : 0;
-	o.q = 0;
-	JobCtx J;
-	Piece P;
-	P.kind = PK_NONE;
-	P.vcount = P.icount = 0;
-	if (o.valid) {
-		uint32_t ps;
-		J = loadJob(a, o.j, &ps);
-		o.q = g - ps;
-		P = classify<OPS, JT, CT>(J, o.q, a.pts);
-		sTail[t] = packTail(P);
-	}
-	/* hand-over of the previous block's last piece (written by the count kernel) */
-	const uint32_t tail0 = (t == 0 && blockIdx.x > 0) ? a.blockTail[blockIdx.x - 1] : 0u;
-	/* local offsets (the scan's two barriers also publish sTail) */
-	uint2 total;
-	const uint2 inc = blockInclusive<ScanOpsU2, false>(make_uint2(P.vcount, P.icount), &total);
-	const uint32_t vl = inc.x - P.vcount;
-	const uint32_t il = inc.y - P.icount;
-	sVl[t] = vl;
-	sIl[t] = il;
-	if (t == 0) {
-		sVl[PPB] = total.x;
-		sIl[PPB] = total.y;
-	}
-	const ulonglong2 bb = a.blockBase[blockIdx.x];
-	/* mesh-local id of this piece's first vertex; what the previous piece handed over */
-	uint32_t F = 0;
-	ulonglong2 mo = make_ulonglong2(0, 0);
-	uint4 prev = make_uint4(0, 0, 0, 0);
-	if (o.valid) {
-		mo = a.meshOff[o.j];
-		F = (uint32_t)(bb.x + vl - mo.x);
-		if (P.flags & PF_HAS_PREV) {
-			/* piece q-1 of the same job is owned by thread t-1 (or by the previous block's last thread) */
-			const uint32_t tw = t > 0 ? sTail[t - 1] : tail0;
-			prev = ((OPS & OPS_OTHER) && J.op != VGB_OP_STROKE_AA) ? ribbonOutFromTail(J, tw, F)
-			                                                        : out4FromTail(CT < 3 ? (uint32_t)CT : J.cap, JT < 3 ? (uint32_t)JT : J.join, tw, F);
-		}
-	}
-	const uint32_t idxBase = sizeof(IDX) == 2 ? 0u : (uint32_t)(mo.x + a.vertexBase);
-	/* caps (a few per block) are detached from their owners and emitted by the low lanes of warp 0:
-	 * every other warp then runs join code only, instead of join + start-cap + end-cap code */
-	bool deferred = false;
-	if (o.valid && (P.kind == PK_CAP_START || P.kind == PK_CAP_END) && (!(OPS & OPS_OTHER) || J.op == VGB_OP_STROKE_AA)) {
-		const uint32_t slot = atomicAdd(&sCapCount, 1u);
-		if (slot < CAPMAX) {
-			sCap[slot] = makeCapRec(J, P, F, prev, vl, il, idxBase, t);
-			deferred = true;
-		}
-	}
-
-	/* rounds: as many consecutive pieces as fit the staging buffers (one round in the common case) */
-	static_assert(PPB >= 128, "copy-out uses warps 1..3");
-	const uint32_t nThreads = min(PPB, a.numPieces - blockIdx.x * PPB);
-	const uint32_t warp = t >> 5, lane = t & 31;
-	const bool single = total.x <= CV && total.y <= CI; /* block-uniform */
-	uint32_t ta = 0;
-	while (ta < nThreads) {
-		const uint32_t v0 = sVl[ta], i0 = sIl[ta];
-		uint32_t tb;
-		if (single) {
-			__syncthreads(); /* cap records written above -> readable by warp 0 */
-			tb = nThreads;
-		} else {
-			const bool fits = t >= ta && t < nThreads && (sVl[t + 1] - v0) <= CV && (sIl[t + 1] - i0) <= CI;
-			tb = ta + __syncthreads_count(fits);
-		}
-		const uint64_t gv = bb.x + v0; /* global element offsets of the round */
-		const uint64_t gi = bb.y + i0;
-		if (tb == ta) {
-			/* a single piece larger than the staging buffers: its owner writes it straight to HBM */
-			if (t == ta) {
-				Sink<IDX, !(OPS & OPS_OTHER)> S;
-				S.pos = a.pos + gv;
-				S.col = a.col + gv;
-				S.idx = reinterpret_cast<IDX*>(a.idx) + gi;
-				S.base = idxBase;
-				emitPiece<OPS, JT, CT>(a, J, P, F, prev, S);
-			}
-			ta += 1;
-			__syncthreads();
-			continue;
-		}
-		const uint32_t shV2 = (uint32_t)(gv & 1), shV4 = (uint32_t)(gv & 3), shI = (uint32_t)(gi & (KI - 1));
-		if (t >= ta && t < tb && !deferred) {
-			Sink<IDX, !(OPS & OPS_OTHER)> S;
-			S.pos = sPos + shV2 + (vl - v0);
-			S.col = sCol + shV4 + (vl - v0);
-			S.idx = sIdx + shI + (il - i0);
-			S.base = idxBase;
-			emitPiece<OPS, JT, CT>(a, J, P, F, prev, S);
-		}
-		if (t < min(sCapCount, CAPMAX)) {
-			const CapRec R = sCap[t];
-			const uint32_t owner = R.info & 0xFFFF;
-			if (owner >= ta && owner < tb) {
-				Sink<IDX, !(OPS & OPS_OTHER)> S;
-				S.pos = sPos + shV2 + (R.vl - v0);
-				S.col = sCol + shV4 + (R.vl - v0);
-				S.idx = sIdx + shI + (R.il - i0);
-				S.base = R.base;
-				emitCapAA<CT>(R, S);
-			}
-		}
-		fenceProxyAsync(); /* generic-proxy writes above -> visible to the async (TMA) proxy */
-		__syncthreads();
-		const uint32_t nv = sVl[tb] - v0, ni = sIl[tb] - i0;
-		if (warp == 1) {
-			copyOutWarp<float2>(a.pos, gv, nv, sPos, lane);
-		} else if (warp == 2) {
-			copyOutWarp<uint32_t>(a.col, gv, nv, sCol, lane);
-		} else if (warp == 3) {
-			copyOutWarp<IDX>(reinterpret_cast<IDX*>(a.idx), gi, ni, sIdx, lane);
-		}
-		ta = tb;
-		if (ta < nThreads) {
-			/* another round reuses the staging buffers: wait until the TMA has read them */
-			if (warp >= 1 && lane == 0) {
-				bulkWaitRead();
-			}
-			__syncthreads();
-		}
-	}
-	if (warp >= 1 && lane == 0) {
-		/* the CTA may retire once the TMA has READ the staging buffers; the global writes complete
-		 * asynchronously and are ordered before kernel completion */
-		bulkWaitRead();
-	}
-}
-
 /* =========================================================================================
- * warp-autonomous variants (VGB_GROUP32): the unit that owns a contiguous output range is a WARP
- * (32 pieces) instead of a 128-thread block.  Offsets come from a shuffle scan, the hand-over
- * from the previous lane (or the previous warp's tail word), the staging image is private to
- * the warp and leaves through the warp's own bulk copies -- there is not a single block barrier,
- * so a warp waiting on memory never holds its three siblings.
+ * count / emit: the unit that owns a contiguous output range is a WARP (a "group" of 32 pieces).
+ * Offsets come from a shuffle scan, the hand-over from the previous lane (or the previous warp's
+ * tail word), the staging image is private to the warp and leaves through the warp's own bulk
+ * copies -- there is not a single block barrier, so a warp waiting on memory never holds its
+ * three siblings.  (Round-1 history: a block-granular version with a block scan and caps detached
+ * to warp 0 reached 1.65 ms on the headline workload; this one 1.16 ms -- profiles/README.md.)
  * ======================================================================================= */
-#ifndef VGB_GROUP32
-#define VGB_GROUP32 1
-#endif
 #ifndef VGB_CVW
 #define VGB_CVW 288
 #endif
 #ifndef VGB_CIW
 #define VGB_CIW 1280
 #endif
-static constexpr uint32_t GRP = VGB_GROUP32 ? 32u : PPB; /* pieces per offset group */
+static constexpr uint32_t GRP = 32;                      /* pieces per offset group (one warp) */
 static constexpr uint32_t CVW = VGB_CVW;                 /* staged vertices per warp */
 static constexpr uint32_t CIW_COUNT = VGB_CIW;           /* staged indices per warp (uint16 or uint32) */
 
@@ -1360,7 +1114,7 @@ public:
 		VGB_CUDA(cudaEventRecord(ev[1], st));
 
 		/* ---- draws, jobs, pieces ---- */
-		const bool fillOnly = opsMask == OPS_FILL_AA && VGB_GROUP32 && getenv("VGB_GENERIC_FILL") == nullptr;
+		const bool fillOnly = opsMask == OPS_FILL_AA && getenv("VGB_GENERIC_FILL") == nullptr;
 		uint32_t numPieces = 0;
 		if (numJobs) {
 			if (dDD.ensure((size_t)numDraws * sizeof(DrawDerived), err) || dJobPieces.ensure((size_t)numJobs * 4, err) ||
@@ -1422,9 +1176,6 @@ public:
 			                                                   dSubNum.as<uint32_t>(), dSubClosed.as<uint8_t>(), dDD.as<DrawDerived>(),
 			                                                   dPieceStart.as<uint32_t>(), dJobRec.as<JobRec>(), dPieceJob.as<uint32_t>());
 			++launches;
-#if !VGB_GROUP32
-			VGB_CUDA(cudaMemsetAsync(dMeshTotals.p, 0, (size_t)numJobs * 8, st));
-#endif
 			pa.numPieces = numPieces;
 			pa.numJobs = numJobs;
 			pa.pieceJob = dPieceJob.as<uint32_t>();
@@ -1440,13 +1191,8 @@ public:
 				/* closed-form sizes: the mesh table is a plain scan of (2N, 9N-6); no count kernel */
 				if (scan<ScanOps<uint2>>(dMeshTotals.as<uint2>(), numJobs, dMeshOff.as<ulonglong2>(), err)) return VGB_ERR_CUDA;
 			} else {
-#if VGB_GROUP32
 #define VGB_COUNT_K k_group_count
 			const uint32_t countBlocks = (numBlocks + 4 * GC - 1) / (4 * GC); /* 4 warps per block, GC groups per warp */
-#else
-#define VGB_COUNT_K k_piece_count
-			const uint32_t countBlocks = gridBlocks;
-#endif
 			if (opsMask == OPS_STROKE_AA && uniJoin == VGB_JOIN_ROUND && uniCap == VGB_CAP_ROUND) VGB_COUNT_K<OPS_STROKE_AA, 1, 1><<<countBlocks, PPB, 0, st>>>(pa);
 			else if (opsMask == OPS_STROKE_AA && uniJoin == VGB_JOIN_MITER && uniCap == VGB_CAP_BUTT) VGB_COUNT_K<OPS_STROKE_AA, 0, 0><<<countBlocks, PPB, 0, st>>>(pa);
 			else if (opsMask == OPS_STROKE_AA) VGB_COUNT_K<OPS_STROKE_AA, 3, 3><<<countBlocks, PPB, 0, st>>>(pa);
@@ -1455,13 +1201,9 @@ public:
 #undef VGB_COUNT_K
 			++launches;
 			if (scan<ScanOps<uint2>>(dBlockTotals.as<uint2>(), numBlocks, dBlockBase.as<ulonglong2>(), err)) return VGB_ERR_CUDA;
-#if VGB_GROUP32
 			k_mesh_off<<<(numJobs + 1 + 255) / 256, 256, 0, st>>>(dPieceStart.as<uint32_t>(), dPieceJob.as<uint32_t>(), numJobs, numPieces, numBlocks,
 			                                                       dBlockBase.as<ulonglong2>(), dMeshTotals.as<uint2>(), dMeshOff.as<ulonglong2>());
 			++launches;
-#else
-			if (scan<ScanOps<uint2>>(dMeshTotals.as<uint2>(), numJobs, dMeshOff.as<ulonglong2>(), err)) return VGB_ERR_CUDA;
-#endif
 			} /* !fillOnly */
 			if (sizesKnown) {
 				totals[0] = kTotals[0];
@@ -1483,7 +1225,6 @@ public:
 			pa.pos = dPos.as<float2>();
 			pa.col = dCol.as<uint32_t>();
 			pa.idx = dIdx.p;
-#if VGB_GROUP32
 			/* uint32 indices: pick the index-image size from the batch's average indices per group */
 			const bool bigI = idxBytes == 4 && numBlocks > 0 && totals[1] / numBlocks > (uint64_t)(CIW_COUNT / 2) * 3 / 4;
 #define VGB_EMIT_K(T, O, J, C)                                                   \
@@ -1491,9 +1232,6 @@ public:
 		if (bigI) k_group_emit<T, O, J, C, true><<<gridBlocks, PPB, 0, st>>>(pa); \
 		else k_group_emit<T, O, J, C, false><<<gridBlocks, PPB, 0, st>>>(pa);     \
 	} while (0)
-#else
-#define VGB_EMIT_K(T, O, J, C) k_piece_emit<T, O, J, C><<<gridBlocks, PPB, 0, st>>>(pa)
-#endif
 #define VGB_LAUNCH_EMIT(T)                                                                                  \
 	do {                                                                                                    \
 		if (opsMask == OPS_STROKE_AA && uniJoin == VGB_JOIN_ROUND && uniCap == VGB_CAP_ROUND) VGB_EMIT_K(T, OPS_STROKE_AA, 1, 1); \

@@ -357,26 +357,9 @@ __device__ __forceinline__ Piece classify(const JobCtx& J, uint32_t q, const flo
 	return P;
 }
 
-/* (LeftAA, Left, Right, RightAA) a piece hands to the next one; F = its first vertex id */
-__device__ __forceinline__ uint4 pieceOut4(const JobCtx& J, const Piece& P, uint32_t F)
-{
-	if (P.kind == PK_CAP_START) {
-		if (J.cap == VGB_CAP_ROUND) {
-			const uint32_t e = 2 * (P.n - 1);
-			return make_uint4(F + 1, F, F + e, F + e + 1);
-		}
-		return make_uint4(F, F + 1, F + 2, F + 3);
-	}
-	/* join */
-	const uint32_t n2 = (J.join == VGB_JOIN_MITER) ? 0u : 2 * P.n;
-	if (P.flags & PF_LEFT) {
-		return make_uint4(F, F + 1, F + 2 + n2, F + 3 + n2);
-	}
-	return make_uint4(F + 3 + n2, F + 2 + n2, F + 1, F);
-}
-
 /* A piece's hand-over to its successor packed in one word: kind | left << 3 | n << 4 | vcount << 16.
- * The successor rebuilds pieceOut4 from it and its own F (F_prev = F - vcount_prev). */
+ * The successor rebuilds the four ids (LeftAA, Left, Right, RightAA) from it and its own F
+ * (F_prev = F - vcount_prev). */
 __device__ __forceinline__ uint32_t packTail(const Piece& P)
 {
 	return P.kind | ((P.flags & PF_LEFT) ? 8u : 0u) | ((P.n & 0xFFFu) << 4) | (P.vcount << 16);
