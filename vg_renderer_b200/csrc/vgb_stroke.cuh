@@ -631,33 +631,49 @@ __device__ __forceinline__ void emitStrokeAA(const JobCtx& J, const Piece& P, ui
 	const float hsw = J.hsw, hsw_aa = J.hsw_aa;
 	const float2 p1 = P.p;
 	const uint32_t n = P.n; /* join: arc segments; cap: nHC */
+	const float2 d01 = P.d01, d12 = P.d12;
+	const float2 s01 = left ? f2(d01.y, -d01.x) : f2(-d01.y, d01.x);
+	const float2 s12 = left ? f2(d12.y, -d12.x) : f2(-d12.y, d12.x);
 	if (!isCap) {
 		const float2 vs = left ? P.v : f2(-P.v.x, -P.v.y);
-		const float2 d01 = P.d01, d12 = P.d12;
-		const float2 s01 = left ? f2(d01.y, -d01.x) : f2(-d01.y, d01.x);
-		const float2 s12 = left ? f2(d12.y, -d12.x) : f2(-d12.y, d12.x);
 		S.VP(0, p1.x + vs.x * hsw_aa, p1.y + vs.y * hsw_aa, J.c0, p1.x + vs.x * hsw, p1.y + vs.y * hsw, J.color);
-		float ax = p1.x + s01.x * hsw, ay = p1.y + s01.y * hsw;
-		float bx = p1.x + s12.x * hsw, by = p1.y + s12.y * hsw;
-		if (jt == VGB_JOIN_BEVEL) {
-			const float t = fabsf(s01.x * s12.x + s01.y * s12.y) * J.fringe;
-			ax = ax - d01.x * t;
-			ay = ay - d01.y * t;
-			bx = bx + d12.x * t;
-			by = by + d12.y * t;
-		}
-		S.VP(2, ax, ay, J.color, p1.x + s01.x * hsw_aa, p1.y + s01.y * hsw_aa, J.c0);
-		S.VP(2 + 2 * n, bx, by, J.color, p1.x + s12.x * hsw_aa, p1.y + s12.y * hsw_aa, J.c0);
 	}
-	/* arc points by angle: joins i = 1..n-1 at vertex 2+2i, caps i = 0..nHC-1 at vertex 2i */
+	/* One loop over the arc points of both kinds, so that the cap lanes' iterations are shared:
+	 *   join: k = 0..n at vertex 2+2k; the end points k = 0 and k = n take their direction from the
+	 *         segment normals (s01, s12), the middle ones from the angle a01 + k*arcDa;
+	 *   cap:  k = 0..nHC-1 at vertex 2k, all from the angle startAngle +- k*pi/(nHC-1).
+	 * sin/cos is evaluated for every lane and iteration and simply not used where a normal applies. */
 	const uint32_t vb = isCap ? 0u : 2u;
+	const uint32_t cnt = isCap ? n : n + 1;
 	const float capDen = (float)(n - 1);
-	for (uint32_t i = isCap ? 0u : 1u; i < n; ++i) {
+	const float bev = (!isCap && jt == VGB_JOIN_BEVEL) ? fabsf(s01.x * s12.x + s01.y * s12.y) * J.fringe : 0.0f;
+	for (uint32_t i = 0; i < cnt; ++i) {
 		const float t = isCap ? (float)i * VGB_PI / capDen : (float)i * P.arcDa;
 		const float a = P.a01 + (isEnd ? -t : t);
-		float sa, ca;
-		vgb_sincos(a, &sa, &ca);
-		S.VP(vb + 2 * i, p1.x + ca * hsw, p1.y + sa * hsw, J.color, p1.x + ca * hsw_aa, p1.y + sa * hsw_aa, J.c0);
+		float dy, dx;
+		vgb_sincos(a, &dy, &dx);
+		const bool first = !isCap && i == 0, last = !isCap && i == n;
+		if (first) {
+			dx = s01.x;
+			dy = s01.y;
+		}
+		if (last) {
+			dx = s12.x;
+			dy = s12.y;
+		}
+		float ix = p1.x + dx * hsw, iy = p1.y + dy * hsw;
+		if (jt == VGB_JOIN_BEVEL) {
+			/* stroker.cpp:1614-1617, 1643-1646 (bev is 0 for caps: x - d*0 would still be exact, but skip it) */
+			if (first) {
+				ix = ix - d01.x * bev;
+				iy = iy - d01.y * bev;
+			}
+			if (last) {
+				ix = ix + d12.x * bev;
+				iy = iy + d12.y * bev;
+			}
+		}
+		S.VP(vb + 2 * i, ix, iy, J.color, p1.x + dx * hsw_aa, p1.y + dy * hsw_aa, J.c0);
 	}
 	uint32_t k = 0;
 	if (P.flags & PF_HAS_PREV) {
