@@ -84,6 +84,41 @@ enum {
 	VGB_RUN_INDEX_U32 = 1  /* merged uint32 indices: local + mesh first vertex + vertex_base  */
 };
 
+/* Final layout: what vg.cpp's merge step createDrawCommand_VertexColor
+ * (vg.cpp:5207-5244) builds out of the meshes one by one, produced by the batch in one go:
+ *   - pos / color streams as they are (a vertex buffer of the context is a contiguous slice),
+ *   - a uv stream holding the white-pixel uv for every vertex (vg.cpp:5220-5227, 4907-4919),
+ *   - uint16 indices rebased by the number of vertices already in the mesh's draw command
+ *     (vgutil::batchTransformDrawIndices, vg_util.cpp:447-520, called at vg.cpp:5240),
+ *   - the draw-command table: a new vertex buffer and a new draw command start whenever the
+ *     next mesh would take the current buffer past max_vb_vertices (allocVertices,
+ *     vg.cpp:5321-5342; allocDrawCommand, vg.cpp:5359-5405).
+ * Set with vgb_batch_set_final_layout before vgb_batch_run(VGB_RUN_INDEX_U16). */
+typedef struct vgb_final_cfg {
+	uint32_t max_vb_vertices; /* ContextConfig::m_MaxVBVertices, 2..65536                               */
+	uint32_t vb_id;           /* id of the context's current vertex buffer (m_NumVertexBuffers - 1)       */
+	uint32_t vb_count;        /* vertices already in it (VertexBuffer::m_Count)                           */
+	uint32_t cmd_vertices;    /* vertices already in the open draw command this batch continues
+	                             (DrawCommand::m_NumVertices; 0 = the batch opens a new command)          */
+	uint32_t ib_count;        /* indices already in the active index buffer (IndexBuffer::m_Count)        */
+	int16_t uv[2];            /* getWhitePixelUV(), VG_CONFIG_UV_INT16 layout                             */
+} vgb_final_cfg;
+
+/* the DrawCommand fields this path decides (vg.cpp:125-129) + where the command's data sits
+ * in the batch's streams */
+typedef struct vgb_draw_cmd {
+	uint32_t vb_id;        /* m_VertexBufferID                                              */
+	uint32_t first_vertex; /* m_FirstVertexID: where the batch's vertices start in that buffer */
+	uint32_t first_index;  /* m_FirstIndexID  (ib_count + indices of the earlier commands)   */
+	uint32_t num_vertices; /* vertices the batch adds to the command                        */
+	uint32_t num_indices;
+	uint32_t first_mesh;   /* meshes [first_mesh, first_mesh + num_meshes) of the batch       */
+	uint32_t num_meshes;
+	uint32_t reserved;
+	uint64_t stream_vertex; /* offset of the command's first vertex in the pos/uv/color streams */
+	uint64_t stream_index;  /* offset of its first index in the index stream                  */
+} vgb_draw_cmd;
+
 typedef struct vgb_batch vgb_batch;
 
 /* vg::Mesh (include/vg/vg.h:353-360), C layout */
@@ -202,6 +237,16 @@ VGB_API int vgb_batch_upload(vgb_batch* b);
 VGB_API int vgb_batch_run(vgb_batch* b, uint32_t flags, uint64_t vertex_base);
 VGB_API int vgb_batch_sync(vgb_batch* b);
 VGB_API int vgb_batch_get_sizes(vgb_batch* b, vgb_sizes* out);
+
+/* final layout: cfg is copied; NULL switches back to per-mesh local indices.  Applies to the next
+ * runs with VGB_RUN_INDEX_U16 (VGB_ERR_INVALID with uint32 indices or a bad max_vb_vertices). */
+VGB_API int vgb_batch_set_final_layout(vgb_batch* b, const vgb_final_cfg* cfg);
+/* after a final-layout run: the uv stream (2 int16 per vertex; nullable), the draw commands
+ * (nullable) and their number.  VGB_ERR_CAPACITY if a buffer is too small or if one mesh alone has
+ * max_vb_vertices vertices or more (the reference asserts on that, vg.cpp:5323).  uv_device
+ * (nullable) receives the device pointer of the uv stream. */
+VGB_API int vgb_batch_download_final(vgb_batch* b, int16_t* uv, uint64_t vtx_capacity, vgb_draw_cmd* cmds, uint32_t cmd_capacity,
+                                     uint32_t* num_cmds, void** uv_device);
 
 /* device-resident results (valid until the next run/reset/destroy) */
 VGB_API int vgb_batch_device_ptrs(vgb_batch* b, void** pos, void** color, void** index,

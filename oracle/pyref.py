@@ -117,6 +117,28 @@ class _Lib:
         return out
 
 
+    def final_layout(self, mesh_vtx_off, mesh_idx_off, index_local, cfg):
+        """vg.cpp's merge step over stored meshes.  cfg: vg_renderer_b200.api.FinalCfg.
+        -> (index[I] u16 rebased, uv[V,2] i16, cmds structured array) or raises on an oversize mesh."""
+        from vg_renderer_b200.api import DRAW_CMD_DTYPE
+        f = getattr(self.lib, self.prefix + "_final_layout")
+        f.restype = C.c_int
+        mvo = np.ascontiguousarray(mesh_vtx_off, np.uint64)
+        mio = np.ascontiguousarray(mesh_idx_off, np.uint64)
+        il = np.ascontiguousarray(index_local, np.uint16)
+        nm = len(mvo) - 1
+        nv, ni = int(mvo[-1] - mvo[0]), int(mio[-1] - mio[0])
+        idx = np.zeros(max(ni, 1), np.uint16)
+        uv = np.zeros((max(nv, 1), 2), np.int16)
+        cmds = np.zeros(nm + 1, DRAW_CMD_DTYPE)
+        n = C.c_uint32()
+        rc = f(_p(mvo, C.c_uint64), _p(mio, C.c_uint64), C.c_uint32(nm), _p(il, C.c_uint16), C.byref(cfg),
+               _p(idx, C.c_uint16), _p(uv, C.c_int16), cmds.ctypes.data_as(C.c_void_p), C.c_uint32(nm + 1), C.byref(n))
+        if rc != 0:
+            raise RuntimeError(f"final_layout rc={rc}")
+        return idx[:ni], uv[:nv], cmds[: n.value]
+
+
 class RefLib(_Lib):
     """The compiled reference (oracle/_ref). kind: scalar (golden) | sse | libm."""
     prefix = "vgref"

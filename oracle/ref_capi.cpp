@@ -209,4 +209,59 @@ int vgref_run_batch(uint32_t pathBegin, uint32_t pathEnd,
 	return 0;
 }
 
+/* ---- final layout ---------------------------------------------------------
+ * src/vg.cpp itself cannot be compiled here (bgfx, bx handle allocators), so the BOOK-KEEPING of
+ * its merge step is restated below with the reference statement cited on each line; the two data
+ * transforms of that step are the reference's own compiled functions: vgutil::memset32 for the uv
+ * splat (vg.cpp:5223) and vgutil::batchTransformDrawIndices for the index rebase (vg.cpp:5240).
+ * Input: the meshes of a batch in submission order (local uint16 indices), as vgref_run_batch
+ * stores them.  Empty meshes are skipped like vg.cpp:3101 / 3450 skip them.  One record per draw
+ * command the batch touches; a record describes the batch's share of that command. */
+int vgref_final_layout(const uint64_t* meshVtxOff, const uint64_t* meshIdxOff, uint32_t numMeshes, const uint16_t* idxLocal,
+                       const vgb_final_cfg* cfg, uint16_t* idxOut, int16_t* uvOut, vgb_draw_cmd* cmds, uint32_t cmdCap, uint32_t* numCmds)
+{
+	uint32_t vbID = cfg->vb_id, vbCount = cfg->vb_count, ibCount = cfg->ib_count; /* Context state on entry */
+	bool forceNew = cfg->cmd_vertices == 0;      /* m_ForceNewDrawCommand: no open command to continue  */
+	uint32_t cmdNumVertices = cfg->cmd_vertices; /* m_NumVertices of the command being appended to     */
+	vgb_draw_cmd* cur = nullptr;
+	uint32_t n = 0;
+	for (uint32_t m = 0; m < numMeshes; ++m) {
+		const uint64_t vo = meshVtxOff[m] - meshVtxOff[0], io = meshIdxOff[m] - meshIdxOff[0];
+		const uint32_t nv = (uint32_t)(meshVtxOff[m + 1] - meshVtxOff[m]), ni = (uint32_t)(meshIdxOff[m + 1] - meshIdxOff[m]);
+		if (nv == 0) continue;
+		if (nv >= cfg->max_vb_vertices) return -5;  /* VG_CHECK, vg.cpp:5323 */
+		if (vbCount + nv > cfg->max_vb_vertices) {  /* allocVertices: the buffer cannot hold it, vg.cpp:5327-5335 */
+			++vbID;
+			vbCount = 0;
+			forceNew = true;
+		}
+		const uint32_t firstVertexID = vbCount;     /* vg.cpp:5339-5340 */
+		vbCount += nv;
+		const uint32_t firstIndexID = ibCount;      /* allocIndices, vg.cpp:5353-5355 */
+		ibCount += ni;
+		if (forceNew || !cur) {                     /* allocDrawCommand, vg.cpp:5368-5402 (type and handle never change here) */
+			if (n == cmdCap) return -5;
+			cur = &cmds[n++];
+			memset(cur, 0, sizeof(*cur));
+			cur->vb_id = vbID;
+			cur->first_vertex = firstVertexID;
+			cur->first_index = firstIndexID;
+			cur->first_mesh = m;
+			cur->stream_vertex = vo;
+			cur->stream_index = io;
+			if (forceNew) cmdNumVertices = 0;       /* vg.cpp:5391 */
+			forceNew = false;                       /* vg.cpp:5402 */
+		}
+		/* createDrawCommand_VertexColor, vg.cpp:5214-5243 (pos and colour are plain copies) */
+		vgutil::memset32(uvOut + 2 * vo, nv, cfg->uv);
+		vgutil::batchTransformDrawIndices(idxLocal + io, ni, idxOut + io, (uint16_t)cmdNumVertices);
+		cmdNumVertices += nv;
+		cur->num_vertices += nv;
+		cur->num_indices += ni;
+		cur->num_meshes = m + 1 - cur->first_mesh;
+	}
+	*numCmds = n;
+	return 0;
+}
+
 } /* extern "C" */

@@ -1056,3 +1056,60 @@ void vgo_math_eval(uint32_t op, const float* x, const float* y, float* out, uint
 		}
 	}
 }
+
+/* ---- final layout (vg.cpp:5207-5244, 5321-5405) -------------------------------
+ * Restatement of the merge step for colour meshes: first-fit packing of the meshes into vertex
+ * buffers of max_vb_vertices, one draw command per buffer the batch touches, uint16 indices
+ * rebased by the vertices that precede the mesh in its command, white-pixel uv for every vertex. */
+int vgo_final_layout(const uint64_t* meshVtxOff, const uint64_t* meshIdxOff, uint32_t numMeshes, const uint16_t* idxLocal,
+                     const vgb_final_cfg* cfg, uint16_t* idxOut, int16_t* uvOut, vgb_draw_cmd* cmds, uint32_t cmdCap, uint32_t* numCmds)
+{
+	uint32_t vb = cfg->vb_id, inVb = cfg->vb_count, inIb = cfg->ib_count, inCmd = cfg->cmd_vertices;
+	int open = 0; /* a record for the current command exists */
+	uint32_t n = 0;
+	for (uint32_t m = 0; m < numMeshes; ++m) {
+		const uint64_t vo = meshVtxOff[m] - meshVtxOff[0], io = meshIdxOff[m] - meshIdxOff[0];
+		const uint32_t nv = (uint32_t)(meshVtxOff[m + 1] - meshVtxOff[m]), ni = (uint32_t)(meshIdxOff[m + 1] - meshIdxOff[m]);
+		if (nv == 0) {
+			continue; /* never submitted: vg.cpp:3101, 3450 */
+		}
+		if (nv >= cfg->max_vb_vertices) {
+			return -5; /* vg.cpp:5323 */
+		}
+		if (inVb + nv > cfg->max_vb_vertices) { /* vg.cpp:5327 */
+			vb += 1;
+			inVb = 0;
+			inCmd = 0;
+			open = 0;
+		}
+		if (!open) {
+			if (n == cmdCap) {
+				return -5;
+			}
+			vgb_draw_cmd* c = &cmds[n++];
+			memset(c, 0, sizeof(*c));
+			c->vb_id = vb;
+			c->first_vertex = inVb;
+			c->first_index = inIb;
+			c->first_mesh = m;
+			c->stream_vertex = vo;
+			c->stream_index = io;
+			open = 1;
+		}
+		for (uint32_t i = 0; i < nv; ++i) { /* vg.cpp:5220-5227 */
+			uvOut[2 * (vo + i)] = cfg->uv[0];
+			uvOut[2 * (vo + i) + 1] = cfg->uv[1];
+		}
+		for (uint32_t i = 0; i < ni; ++i) { /* vg.cpp:5240, vg_util.cpp:447-520 */
+			idxOut[io + i] = (uint16_t)(idxLocal[io + i] + (uint16_t)inCmd);
+		}
+		inVb += nv;
+		inIb += ni;
+		inCmd += nv;
+		cmds[n - 1].num_vertices += nv;
+		cmds[n - 1].num_indices += ni;
+		cmds[n - 1].num_meshes = m + 1 - cmds[n - 1].first_mesh;
+	}
+	*numCmds = n;
+	return 0;
+}

@@ -32,6 +32,9 @@ int vgo_run_batch(uint32_t pathBegin, uint32_t pathEnd,
                   int store, float* pos, uint32_t* col, uint16_t* idx, uint64_t vCap, uint64_t iCap,
                   uint64_t* meshVtxOff, uint64_t* meshIdxOff, uint32_t meshCap, uint64_t* totals);
 
+int vgo_final_layout(const uint64_t* meshVtxOff, const uint64_t* meshIdxOff, uint32_t numMeshes, const uint16_t* idxLocal,
+                     const vgb_final_cfg* cfg, uint16_t* idxOut, int16_t* uvOut, vgb_draw_cmd* cmds, uint32_t cmdCap, uint32_t* numCmds);
+
 #ifdef __cplusplus
 }
 #endif

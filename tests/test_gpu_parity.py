@@ -401,3 +401,75 @@ def test_tiger_like_scene_and_instances(gpu_batch, ref):
     e = ref.run_batch(ti)
     merged = e["index"].astype(np.uint64) + np.repeat(e["mesh_vtx_off"][:-1], np.diff(e["mesh_idx_off"]).astype(np.int64))
     np.testing.assert_array_equal(o32["index"].astype(np.uint64), merged)
+
+
+# ---- final layout: vg.cpp's merge step, fused ------------------------------------
+FINAL_FIELDS = ("vb_id", "first_vertex", "first_index", "num_vertices", "num_indices", "stream_vertex", "stream_index")
+
+
+def check_final(gpu_batch, ref, tables, cfg):
+    exp = ref.run_batch(tables)
+    e_idx, e_uv, e_cmds = ref.final_layout(exp["mesh_vtx_off"], exp["mesh_idx_off"], exp["index"], cfg)
+    gpu_batch.set_final_layout(cfg)
+    try:
+        gpu_batch.run()
+        out = gpu_batch.download()
+        uv, cmds = gpu_batch.download_final()
+    finally:
+        gpu_batch.set_final_layout(None)
+    np.testing.assert_array_equal(out["pos"], exp["pos"])
+    np.testing.assert_array_equal(out["color"], exp["color"])
+    np.testing.assert_array_equal(out["mesh_vtx_off"], exp["mesh_vtx_off"])
+    np.testing.assert_array_equal(out["index"], e_idx)
+    np.testing.assert_array_equal(uv, e_uv)
+    assert len(cmds) == len(e_cmds)
+    for f in FINAL_FIELDS:
+        np.testing.assert_array_equal(cmds[f], e_cmds[f], err_msg=f)
+    # the mesh ranges partition the batch in order (empty meshes may sit on either side of a border)
+    assert np.all(cmds["first_mesh"][1:] >= cmds["first_mesh"][:-1])
+    return cmds
+
+
+@pytest.mark.parametrize("max_vb,vb_count,cmd_vertices", [(65536, 0, 0), (65536, 60000, 1234), (65536, 65500, 65500), (4096, 100, 0),
+                                                           (2000, 0, 0), (2000, 1999, 1999), (1 << 12, 1 << 12, 17)])
+def test_final_layout_cubic_strokes(gpu_batch, ref, max_vb, vb_count, cmd_vertices):
+    p8 = W.config3_cubics(3000, first=77)
+    gpu_batch.reset(1.0)
+    gpu_batch.add_cubic_strokes(p8, width=4.0, cap=1, join=1)
+    cfg = vgb.make_final_cfg(max_vb, vb_id=5, vb_count=vb_count, cmd_vertices=cmd_vertices, ib_count=999, uv=(127, -3))
+    cmds = check_final(gpu_batch, ref, BatchTables.cubic_strokes(p8, width=4.0, cap=1, join=1), cfg)
+    assert len(cmds) >= 3000 * 150 // max_vb
+
+
+def test_final_layout_mixed_scene_with_empty_meshes(gpu_batch, ref):
+    t = W.instance_tables(W.tiger_like(), 6)
+    for max_vb, vbc in ((65536, 0), (9000, 8999), (2500, 40)):
+        gpu_batch.reset(1.0)
+        gpu_batch.add_tables(t)
+        check_final(gpu_batch, ref, t, vgb.make_final_cfg(max_vb, vb_id=0, vb_count=vbc, cmd_vertices=min(vbc, 7), ib_count=0, uv=(1, 2)))
+
+
+def test_final_layout_fill_only_batch(gpu_batch, ref):
+    rr = W.config4_rrects(5000, r=32)
+    gpu_batch.reset(1.0)
+    gpu_batch.add_rounded_rect_fills(rr, aa=True)
+    check_final(gpu_batch, ref, BatchTables.rounded_rect_fills(rr, aa=True), vgb.make_final_cfg(65536, 2, 11, 11, 5, (300, 300)))
+
+
+def test_final_layout_rejects_oversize_mesh_and_u32(gpu_batch):
+    p8 = W.config3_cubics(50, first=3)
+    gpu_batch.reset(1.0)
+    gpu_batch.add_cubic_strokes(p8, width=4.0, cap=1, join=1)
+    gpu_batch.set_final_layout(vgb.make_final_cfg(64))  # every mesh has more than 64 vertices
+    try:
+        gpu_batch.run()
+        with pytest.raises(vgb.VgbError):
+            gpu_batch.download_final()
+        with pytest.raises(vgb.VgbError):
+            gpu_batch.run(index_u32=True)
+        with pytest.raises(vgb.VgbError):
+            gpu_batch.set_final_layout(vgb.make_final_cfg(70000))
+    finally:
+        gpu_batch.set_final_layout(None)
+    gpu_batch.run()  # back to per-mesh local indices
+    assert int(gpu_batch.download()["index"].max()) < 400

@@ -185,3 +185,59 @@ def test_libm_shim_sensitivity():
         # 1e-4 abs, or 2 ulp where the coordinate's own float spacing exceeds that (|x| >= 1024)
         tol = np.maximum(1e-4, 2 * np.spacing(np.abs(a["pos"])))
         assert np.all(np.abs(a["pos"] - b["pos"]) <= tol)
+
+
+# ---- final layout ------------------------------------------------------------------
+def _final_cfgs():
+    from vg_renderer_b200.api import make_final_cfg
+    return [make_final_cfg(65536), make_final_cfg(65536, 4, 65000, 100, 12, (7, 8)), make_final_cfg(4096, 0, 4096, 4096, 0, (-1, 1)),
+            make_final_cfg(1500, 2, 1499, 0, 3, (127, 127)), make_final_cfg(1000, 9, 0, 0, 1 << 20, (0, 0))]
+
+
+def test_golden_final_layout(orc):
+    from vg_renderer_b200.api import make_final_cfg
+    g = np.load(os.path.join(GOLD, "final_layout.npz"))
+    o = orc.run_batch(BatchTables.cubic_strokes(W.config3_cubics(400, first=5), width=4.0, cap=1, join=1))
+    for name in "abc":
+        c = [int(v) for v in g[name + "_cfg"]]
+        idx, uv, cmds = orc.final_layout(o["mesh_vtx_off"], o["mesh_idx_off"], o["index"], make_final_cfg(*c[:5], uv=(c[5], c[6])))
+        np.testing.assert_array_equal(idx, g[name + "_index"])
+        assert cmds.tobytes() == g[name + "_cmds"].tobytes()
+        assert np.all(uv == np.asarray(c[5:7], np.int16))
+
+
+def test_final_layout_properties(orc):
+    """what the merge contract guarantees, whatever the sizes: every command's indices address its own
+    vertices only, commands tile the streams, no buffer holds more than max_vb_vertices"""
+    o = orc.run_batch(mixed_recorder().tables())
+    for cfg in _final_cfgs():
+        if int(np.diff(o["mesh_vtx_off"]).max()) >= cfg.max_vb_vertices:
+            with pytest.raises(RuntimeError):
+                orc.final_layout(o["mesh_vtx_off"], o["mesh_idx_off"], o["index"], cfg)
+            continue
+        idx, uv, cmds = orc.final_layout(o["mesh_vtx_off"], o["mesh_idx_off"], o["index"], cfg)
+        assert int(cmds["num_vertices"].sum()) == o["num_vertices"] and int(cmds["num_indices"].sum()) == o["num_indices"]
+        for k, c in enumerate(cmds):
+            lo = cfg.cmd_vertices if (k == 0 and c["first_vertex"] == cfg.vb_count and cfg.cmd_vertices) else 0
+            part = idx[int(c["stream_index"]): int(c["stream_index"]) + int(c["num_indices"])]
+            assert part.min() >= lo and part.max() < lo + c["num_vertices"]
+            assert c["first_vertex"] + c["num_vertices"] <= cfg.max_vb_vertices
+        assert np.all(np.diff(cmds["vb_id"].astype(np.int64)) == 1)
+
+
+@needs_ref
+def test_final_layout_restatement_vs_reference_functions(orc):
+    ref = RefLib("scalar")
+    for t in (BatchTables.cubic_strokes(W.config3_cubics(1200, first=9), width=4.0, cap=1, join=1), mixed_recorder().tables()):
+        o = ref.run_batch(t)
+        for cfg in _final_cfgs():
+            try:
+                a = ref.final_layout(o["mesh_vtx_off"], o["mesh_idx_off"], o["index"], cfg)
+            except RuntimeError:
+                with pytest.raises(RuntimeError):
+                    orc.final_layout(o["mesh_vtx_off"], o["mesh_idx_off"], o["index"], cfg)
+                continue
+            b = orc.final_layout(o["mesh_vtx_off"], o["mesh_idx_off"], o["index"], cfg)
+            np.testing.assert_array_equal(a[0], b[0])
+            np.testing.assert_array_equal(a[1], b[1])
+            assert a[2].tobytes() == b[2].tobytes()

@@ -85,3 +85,18 @@ np.savez_compressed(os.path.join(OUT, "stream20k.npz"), variant=np.uint32(ref.va
                     totals=np.array([o["num_vertices"], o["num_indices"], o["num_points"], o["checksum"]], np.uint64))
 for f in sorted(os.listdir(OUT)):
     print(f, os.path.getsize(os.path.join(OUT, f)))
+
+# 5. final layout: the merge step over a stored batch, from the reference-side
+#    wrapper (vgutil::batchTransformDrawIndices / memset32 are the reference's own functions)
+from vg_renderer_b200.api import make_final_cfg  # noqa: E402
+
+d = {"variant": np.uint32(ref.variant())}
+t = BatchTables.cubic_strokes(W.config3_cubics(400, first=5), width=4.0, cap=1, join=1)
+o = ref.run_batch(t)
+FINAL_CASES = {"a": (65536, 3, 0, 0, 0, (127, 127)), "b": (4096, 1, 4000, 4000, 77, (5, -9)), "c": (1500, 0, 1499, 3, 1, (1, 1))}
+for name, args in FINAL_CASES.items():
+    idx, uv, cmds = ref.final_layout(o["mesh_vtx_off"], o["mesh_idx_off"], o["index"], make_final_cfg(*args))
+    d[f"{name}_cfg"] = np.asarray(args[:5] + args[5], np.int64)
+    d[f"{name}_index"] = idx
+    d[f"{name}_cmds"] = cmds
+np.savez_compressed(os.path.join(OUT, "final_layout.npz"), **d)

@@ -39,6 +39,32 @@ class Sizes(C.Structure):
                 ("reserved", C.c_uint32)]
 
 
+class FinalCfg(C.Structure):
+    """vgb_final_cfg: the context state the merge step starts from (include/vgb.h)."""
+    _fields_ = [("max_vb_vertices", C.c_uint32), ("vb_id", C.c_uint32), ("vb_count", C.c_uint32),
+                ("cmd_vertices", C.c_uint32), ("ib_count", C.c_uint32), ("uv", C.c_int16 * 2)]
+
+
+class DrawCmd(C.Structure):
+    """vgb_draw_cmd"""
+    _fields_ = [("vb_id", C.c_uint32), ("first_vertex", C.c_uint32), ("first_index", C.c_uint32),
+                ("num_vertices", C.c_uint32), ("num_indices", C.c_uint32), ("first_mesh", C.c_uint32),
+                ("num_meshes", C.c_uint32), ("reserved", C.c_uint32), ("stream_vertex", C.c_uint64),
+                ("stream_index", C.c_uint64)]
+
+
+DRAW_CMD_DTYPE = np.dtype([("vb_id", "<u4"), ("first_vertex", "<u4"), ("first_index", "<u4"), ("num_vertices", "<u4"),
+                           ("num_indices", "<u4"), ("first_mesh", "<u4"), ("num_meshes", "<u4"), ("reserved", "<u4"),
+                           ("stream_vertex", "<u8"), ("stream_index", "<u8")])
+
+
+def make_final_cfg(max_vb_vertices=65536, vb_id=0, vb_count=0, cmd_vertices=0, ib_count=0, uv=(16, 16)):
+    c = FinalCfg()
+    c.max_vb_vertices, c.vb_id, c.vb_count, c.cmd_vertices, c.ib_count = max_vb_vertices, vb_id, vb_count, cmd_vertices, ib_count
+    c.uv[0], c.uv[1] = uv
+    return c
+
+
 class SubPath(C.Structure):
     _fields_ = [("first_vertex", C.c_uint32), ("num_vertices", C.c_uint32), ("is_closed", C.c_uint8)]
 
@@ -100,6 +126,8 @@ def load_library():
     L.vgb_batch_device_ptrs.argtypes = [vp] + [C.POINTER(vp)] * 7
     L.vgb_batch_download.argtypes = [vp, vp, vp, vp, u64, u64, vp, vp]
     L.vgb_batch_download_paths.argtypes = [vp, vp, u64, vp, u32]
+    L.vgb_batch_set_final_layout.argtypes = [vp, C.POINTER(FinalCfg)]
+    L.vgb_batch_download_final.argtypes = [vp, vp, u64, vp, u32, C.POINTER(u32), C.POINTER(vp)]
     L.vgb_batch_execute.argtypes = [vp, u32, vp, vp, vp, u64, u64, vp, vp, C.POINTER(Sizes)]
     L.vgb_batch_last_run_ms.argtypes = [vp] + [C.POINTER(f)] * 4
     L.vgb_batch_mark.argtypes = [vp, u32]
@@ -298,6 +326,21 @@ class Batch:
         self._chk(self.L.vgb_batch_download(self.h, _ptr(pos), _ptr(col), _ptr(idx), nv, ni, _ptr(mvo), _ptr(mio)))
         return dict(pos=pos, color=col, index=idx, mesh_vtx_off=mvo, mesh_idx_off=mio,
                     num_vertices=nv, num_indices=ni, num_meshes=nm, num_points=int(s.num_points))
+
+    def set_final_layout(self, cfg):
+        """cfg: FinalCfg (make_final_cfg) or None.  The next uint16 runs produce vg.cpp's merged layout."""
+        self._chk(self.L.vgb_batch_set_final_layout(self.h, C.byref(cfg) if cfg is not None else None))
+
+    def download_final(self, want_uv=True):
+        """-> (uv[V,2] int16 | None, cmds: structured array of DRAW_CMD_DTYPE)"""
+        s = self.sizes()
+        nv = int(s.num_vertices)
+        n = C.c_uint32()
+        self._chk(self.L.vgb_batch_download_final(self.h, None, 0, None, 0, C.byref(n), None))
+        cmds = np.zeros(n.value, DRAW_CMD_DTYPE)
+        uv = np.empty((nv, 2), np.int16) if want_uv else None
+        self._chk(self.L.vgb_batch_download_final(self.h, _ptr(uv), nv, _ptr(cmds), n.value, C.byref(n), None))
+        return uv, cmds
 
     def download_paths(self):
         """-> (pts[T,2] f32, [(first, num, closed), ...])"""

@@ -673,6 +673,26 @@ int vgb_batch_download_paths(vgb_batch* b, float* pts, uint64_t ptsCap, vgb_subp
 	return 0;
 }
 
+int vgb_batch_set_final_layout(vgb_batch* b, const vgb_final_cfg* cfg)
+{
+	NEED_PIPE(b);
+	if (!b) return fail(VGB_ERR_INVALID, "null batch");
+	std::string err;
+	const int rc = b->pipe->setFinal(cfg, &err);
+	if (rc) return fail(rc, err.c_str());
+	return 0;
+}
+
+int vgb_batch_download_final(vgb_batch* b, int16_t* uv, uint64_t vcap, vgb_draw_cmd* cmds, uint32_t cmdCap, uint32_t* numCmds, void** uvDev)
+{
+	NEED_PIPE(b);
+	if (!b) return fail(VGB_ERR_INVALID, "null batch");
+	std::string err;
+	const int rc = b->pipe->downloadFinal(uv, vcap, cmds, cmdCap, numCmds, uvDev, &err);
+	if (rc) return fail(rc, err.c_str());
+	return 0;
+}
+
 int vgb_batch_execute(vgb_batch* b, uint32_t flags, float* pos, uint32_t* color, void* index, uint64_t vcap, uint64_t icap,
                       uint64_t* mvo, uint64_t* mio, vgb_sizes* sizesOut)
 {

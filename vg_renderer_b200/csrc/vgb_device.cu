@@ -31,6 +31,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <vector>
 
 namespace vgb
 {
@@ -452,6 +453,7 @@ struct PieceArgs
 	const ulonglong2* blockBase; /* numBlocks + 1 */
 	const ulonglong2* meshOff;   /* numJobs + 1   */
 	uint64_t vertexBase;
+	const uint32_t* meshBase; /* final layout: per-mesh index base (nullptr otherwise) */
 	/* emit outputs */
 	float2* pos;
 	uint32_t* col;
@@ -609,6 +611,120 @@ __global__ void k_mesh_off(const uint32_t* __restrict__ pieceStart, const uint32
 	meshOff[j] = o;
 }
 
+/* ---- final layout: vertex-buffer segmentation + draw-command table ---------------
+ * The reference packs meshes into vertex buffers first-fit in submission order (allocVertices,
+ * vg.cpp:5321-5342): mesh m joins the current buffer iff count + nv(m) <= max, else a new buffer and
+ * a new draw command start with it.  That greedy rule is a chain  s -> next(s)  over mesh ids, with
+ *   next(s) = the largest e > s such that  P[e] - P[s] <= max      (P = exclusive vertex offsets),
+ * a pure function of s.  So: (1) next(s) for every mesh by binary search in P, in parallel;
+ * (2) K rounds of pointer doubling J <- J o J, each of which also doubles the list of known
+ * segment starts (starts[j + 2^k] = J_k[starts[j]]);  (3) one record per segment;  (4) per-mesh
+ * index base = P[m] - P[start of its segment] (+ the vertices already in the continued command). */
+struct FinalHdr
+{
+	uint32_t vbId0;    /* vertex buffer of segment 0                                   */
+	uint32_t first0;   /* first vertex of segment 0 in its buffer                      */
+	uint32_t cmdV0;    /* vertices already in the draw command segment 0 continues     */
+	uint32_t oversize; /* a mesh with >= max vertices was seen                         */
+	uint32_t numCmds;
+	uint32_t pad[3];
+};
+
+__global__ void k_seg_next(const ulonglong2* __restrict__ meshOff, uint32_t M, uint32_t maxV, uint32_t vbId, uint32_t vbCount, uint32_t cmdV,
+                           uint32_t* __restrict__ next, uint32_t* __restrict__ starts, FinalHdr* __restrict__ hdr)
+{
+	const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+	if (s > M) return;
+	if (s == M) {
+		next[M] = M;
+		return;
+	}
+	const uint64_t P0 = meshOff[s].x;
+	if (meshOff[s + 1].x - P0 >= (uint64_t)maxV) atomicOr(&hdr->oversize, 1u); /* VG_CHECK at vg.cpp:5323 */
+	uint64_t T = P0 + maxV;
+	bool fresh = true; /* segment starts at vertex 0 of a new buffer */
+	if (s == 0 && vbCount > 0) {
+		/* the first mesh continues the context's current buffer if it fits */
+		if (vbCount + (meshOff[1].x - P0) <= (uint64_t)maxV) {
+			T = P0 + maxV - vbCount;
+			fresh = false;
+		}
+	}
+	/* largest e in (s, M] with P[e] <= T */
+	uint32_t lo = s + 1, hi = M;
+	while (lo < hi) {
+		const uint32_t mid = lo + (hi - lo + 1) / 2;
+		if (meshOff[mid].x <= T) lo = mid;
+		else hi = mid - 1;
+	}
+	next[s] = lo;
+	if (s == 0) {
+		starts[0] = 0;
+		hdr->vbId0 = fresh && vbCount > 0 ? vbId + 1 : vbId;
+		hdr->first0 = fresh ? 0u : vbCount;
+		hdr->cmdV0 = fresh ? 0u : cmdV;
+	}
+}
+
+/* one doubling round: Jout = Jin o Jin, and starts[j + half] = Jin[starts[j]] for j < half */
+__global__ void k_seg_double(const uint32_t* __restrict__ Jin, uint32_t* __restrict__ Jout, uint32_t M, uint32_t* __restrict__ starts, uint32_t half,
+                             uint32_t writeJ)
+{
+	const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+	if (s < half) starts[s + half] = Jin[starts[s]];
+	if (writeJ && s <= M) Jout[s] = Jin[Jin[s]];
+}
+
+__global__ void k_seg_cmds(const uint32_t* __restrict__ starts, uint32_t numStarts, const ulonglong2* __restrict__ meshOff, uint32_t M, uint32_t ibCount,
+                           FinalHdr* __restrict__ hdr, vgb_draw_cmd* __restrict__ cmds)
+{
+	const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+	if (j >= numStarts) return;
+	const uint32_t s = starts[j];
+	if (s >= M) return;
+	const uint32_t e = j + 1 < numStarts ? starts[j + 1] : M;
+	const ulonglong2 a = meshOff[s], b = meshOff[e], o = meshOff[0];
+	vgb_draw_cmd c;
+	c.vb_id = hdr->vbId0 + j;
+	c.first_vertex = j == 0 ? hdr->first0 : 0u;
+	c.first_index = ibCount + (uint32_t)(a.y - o.y);
+	c.num_vertices = (uint32_t)(b.x - a.x);
+	c.num_indices = (uint32_t)(b.y - a.y);
+	c.first_mesh = s;
+	c.num_meshes = e - s;
+	c.reserved = 0;
+	c.stream_vertex = a.x - o.x;
+	c.stream_index = a.y - o.y;
+	cmds[j] = c;
+	if (e >= M) hdr->numCmds = j + 1;
+}
+
+/* index base of every mesh: vertices that precede it in its draw command (vg.cpp:5240) */
+__global__ void k_seg_mesh_base(const uint32_t* __restrict__ starts, uint32_t numStarts, const ulonglong2* __restrict__ meshOff, uint32_t M,
+                                const FinalHdr* __restrict__ hdr, uint32_t* __restrict__ meshBase)
+{
+	const uint32_t m = blockIdx.x * blockDim.x + threadIdx.x;
+	if (m >= M) return;
+	uint32_t lo = 0, hi = numStarts - 1; /* last j with starts[j] <= m */
+	while (lo < hi) {
+		const uint32_t mid = lo + (hi - lo + 1) / 2;
+		if (starts[mid] <= m) lo = mid;
+		else hi = mid - 1;
+	}
+	meshBase[m] = (uint32_t)(meshOff[m].x - meshOff[starts[lo]].x) + (lo == 0 ? hdr->cmdV0 : 0u);
+}
+
+/* the uv stream: every vertex of a colour mesh samples the white pixel (vg.cpp:5220-5227) */
+__global__ void k_fill_u32(uint32_t* __restrict__ dst, uint64_t n, uint32_t v)
+{
+	const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+	uint4* d4 = reinterpret_cast<uint4*>(dst);
+	const uint64_t n4 = n / 4;
+	const uint4 v4 = make_uint4(v, v, v, v);
+	for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) d4[i] = v4;
+	for (uint64_t i = n4 * 4 + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) dst[i] = v;
+}
+
 /* each warp counts GC consecutive groups; the loads of all of them are issued before any is used
  * (the kernel is a chain of dependent loads: piece -> job record -> points) */
 #ifndef VGB_GC
@@ -738,7 +854,10 @@ __global__ void __launch_bounds__(128, VGB_EMIT_MIN_BLOCKS) k_group_emit(PieceAr
 			                                                        : out4FromTail(CT < 3 ? (uint32_t)CT : J.cap, JT < 3 ? (uint32_t)JT : J.join, tw, F);
 		}
 	}
-	const uint32_t idxBase = sizeof(IDX) == 2 ? 0u : (uint32_t)(mo.x + a.vertexBase);
+	/* uint16: BIGI doubles as "final layout" (per-mesh base from the draw-command segmentation);
+	 * the plain per-mesh-local variant keeps base = 0 at compile time */
+	uint32_t idxBase = sizeof(IDX) == 2 ? 0u : (uint32_t)(mo.x + a.vertexBase);
+	if (sizeof(IDX) == 2 && BIGI && valid) idxBase = a.meshBase[j];
 	const bool fits = totV <= CVW && totI <= CIW; /* warp-uniform */
 	uint8_t* stage = sStage + wib * WBYTES;
 	float2* sPos = reinterpret_cast<float2*>(stage);
@@ -817,7 +936,7 @@ __global__ void __launch_bounds__(256) k_fill_emit(PieceArgs a)
 	const float ex = e.x * aa, ey = e.y * aa;
 	reinterpret_cast<float4*>(a.pos + mo.x)[i] = make_float4(p.x + ex, p.y + ey, p.x - ex, p.y - ey);
 	reinterpret_cast<uint2*>(a.col + mo.x)[i] = make_uint2(J.color, J.c0);
-	const uint32_t base = sizeof(IDX) == 2 ? 0u : (uint32_t)(mo.x + a.vertexBase);
+	const uint32_t base = sizeof(IDX) == 2 ? (a.meshBase != nullptr ? a.meshBase[j] : 0u) : (uint32_t)(mo.x + a.vertexBase);
 	IDX* idx = reinterpret_cast<IDX*>(a.idx) + mo.y;
 	const uint32_t f = 2 * i;
 	if (i + 2 < N) {
@@ -888,6 +1007,11 @@ public:
 	uint32_t totalSlots = 0;
 	/* outputs */
 	DevBuf dPos, dCol, dIdx;
+	/* final layout (A9) */
+	bool finalOn = false, finalRan = false;
+	vgb_final_cfg fcfg{};
+	uint32_t finalCmdCap = 0;
+	DevBuf dSegNext[2], dSegStarts, dSegHdr, dSegCmds, dMeshBase, dUV;
 	void* hPinned = nullptr; /* small pinned readback area */
 	HostTables ht;
 	bool hasXform = false, rawMode = false, uploaded = false, ran = false;
@@ -1216,6 +1340,44 @@ public:
 		}
 		sz.num_vertices = totals[0];
 		sz.num_indices = totals[1];
+		finalRan = false;
+		if (finalOn && numPieces) {
+			if (idxBytes != 2) {
+				if (err) *err = "the final layout has uint16 indices: run with VGB_RUN_INDEX_U16";
+				return VGB_ERR_INVALID;
+			}
+			/* two consecutive segments always hold more than max vertices together, so there are at most
+			 * 2V/max + 2 of them: K doubling rounds with 2^K above that bound */
+			const uint64_t segBound = 2 * totals[0] / fcfg.max_vb_vertices + 3;
+			uint32_t K = 0;
+			while (((uint64_t)1 << K) < segBound) ++K;
+			const uint32_t numStarts = 1u << K;
+			finalCmdCap = numStarts;
+			if (dSegNext[0].ensure((size_t)(numJobs + 1) * 4, err) || dSegNext[1].ensure((size_t)(numJobs + 1) * 4, err) ||
+			    dSegStarts.ensure((size_t)numStarts * 4, err) || dSegHdr.ensure(sizeof(FinalHdr), err) ||
+			    dSegCmds.ensure((size_t)numStarts * sizeof(vgb_draw_cmd), err) || dMeshBase.ensure((size_t)numJobs * 4, err))
+				return VGB_ERR_CUDA;
+			VGB_CUDA(cudaMemsetAsync(dSegHdr.p, 0, sizeof(FinalHdr), st));
+			const uint32_t jb = (numJobs + 1 + 255) / 256;
+			k_seg_next<<<jb, 256, 0, st>>>(dMeshOff.as<ulonglong2>(), numJobs, fcfg.max_vb_vertices, fcfg.vb_id, fcfg.vb_count, fcfg.cmd_vertices,
+			                               dSegNext[0].as<uint32_t>(), dSegStarts.as<uint32_t>(), dSegHdr.as<FinalHdr>());
+			++launches;
+			for (uint32_t k = 0; k < K; ++k) {
+				const uint32_t half = 1u << k, last = k + 1 == K;
+				const uint32_t nb = last ? (half + 255) / 256 : jb > (half + 255) / 256 ? jb : (half + 255) / 256;
+				k_seg_double<<<nb, 256, 0, st>>>(dSegNext[k & 1].as<uint32_t>(), dSegNext[(k + 1) & 1].as<uint32_t>(), numJobs, dSegStarts.as<uint32_t>(), half,
+				                                 last ? 0u : 1u);
+				++launches;
+			}
+			k_seg_cmds<<<(numStarts + 255) / 256, 256, 0, st>>>(dSegStarts.as<uint32_t>(), numStarts, dMeshOff.as<ulonglong2>(), numJobs, fcfg.ib_count,
+			                                                     dSegHdr.as<FinalHdr>(), dSegCmds.as<vgb_draw_cmd>());
+			k_seg_mesh_base<<<(numJobs + 255) / 256, 256, 0, st>>>(dSegStarts.as<uint32_t>(), numStarts, dMeshOff.as<ulonglong2>(), numJobs,
+			                                                        dSegHdr.as<FinalHdr>(), dMeshBase.as<uint32_t>());
+			launches += 2;
+			VGB_CUDA(cudaGetLastError());
+			pa.meshBase = dMeshBase.as<uint32_t>();
+			finalRan = true;
+		}
 		VGB_CUDA(cudaEventRecord(ev[2], st));
 
 		/* ---- emit ---- */
@@ -1226,7 +1388,7 @@ public:
 			pa.col = dCol.as<uint32_t>();
 			pa.idx = dIdx.p;
 			/* uint32 indices: pick the index-image size from the batch's average indices per group */
-			const bool bigI = idxBytes == 4 && numBlocks > 0 && totals[1] / numBlocks > (uint64_t)(CIW_COUNT / 2) * 3 / 4;
+			const bool bigI = idxBytes == 4 ? (numBlocks > 0 && totals[1] / numBlocks > (uint64_t)(CIW_COUNT / 2) * 3 / 4) : finalRan;
 #define VGB_EMIT_K(T, O, J, C)                                                   \
 	do {                                                                         \
 		if (bigI) k_group_emit<T, O, J, C, true><<<gridBlocks, PPB, 0, st>>>(pa); \
@@ -1252,6 +1414,13 @@ public:
 #undef VGB_EMIT_K
 			++launches;
 			VGB_CUDA(cudaGetLastError());
+			if (finalRan) {
+				if (dUV.ensure(totals[0] * 4 + 32, err)) return VGB_ERR_CUDA;
+				const uint32_t uvw = (uint32_t)(uint16_t)fcfg.uv[0] | ((uint32_t)(uint16_t)fcfg.uv[1] << 16);
+				k_fill_u32<<<148 * 8, 256, 0, st>>>(dUV.as<uint32_t>(), totals[0], uvw);
+				++launches;
+				VGB_CUDA(cudaGetLastError());
+			}
 		}
 		VGB_CUDA(cudaEventRecord(ev[3], st));
 		sz.kernel_launches = launches;
@@ -1297,6 +1466,65 @@ public:
 		VGB_CUDA(cudaSetDevice(dev));
 		VGB_CUDA(cudaEventSynchronize(userEv[b]));
 		VGB_CUDA(cudaEventElapsedTime(ms, userEv[a], userEv[b]));
+		return 0;
+	}
+
+	int setFinal(const vgb_final_cfg* cfg, std::string* err) override
+	{
+		if (!cfg) {
+			finalOn = false;
+			return 0;
+		}
+		if (cfg->max_vb_vertices < 2 || cfg->max_vb_vertices > 65536 || cfg->vb_count > cfg->max_vb_vertices || cfg->cmd_vertices > cfg->vb_count) {
+			if (err) *err = "final layout: need 2 <= max_vb_vertices <= 65536 and cmd_vertices <= vb_count <= max_vb_vertices";
+			return VGB_ERR_INVALID;
+		}
+		fcfg = *cfg;
+		finalOn = true;
+		return 0;
+	}
+
+	int downloadFinal(int16_t* uv, uint64_t vcap, vgb_draw_cmd* cmds, uint32_t cmdCap, uint32_t* numCmds, void** uvDev, std::string* err) override
+	{
+		if (!ran || (!finalRan && sz.num_vertices)) {
+			if (err) *err = "download_final needs a run with the final layout set";
+			return VGB_ERR_STATE;
+		}
+		VGB_CUDA(cudaSetDevice(dev));
+		if (uvDev) *uvDev = dUV.p;
+		if (numCmds) *numCmds = 0;
+		if (!sz.num_vertices) return 0;
+		FinalHdr h;
+		if (readback(&h, dSegHdr.p, sizeof(h), err)) return VGB_ERR_CUDA;
+		if (h.oversize) {
+			if (err) *err = "a single mesh has max_vb_vertices vertices or more (vg.cpp:5323)";
+			return VGB_ERR_CAPACITY;
+		}
+		/* a leading command that received only empty meshes carries nothing: drop it (ids stay as they are) */
+		std::vector<vgb_draw_cmd> tmp(h.numCmds);
+		if (h.numCmds) VGB_CUDA(cudaMemcpyAsync(tmp.data(), dSegCmds.p, (size_t)h.numCmds * sizeof(vgb_draw_cmd), cudaMemcpyDeviceToHost, st));
+		VGB_CUDA(cudaStreamSynchronize(st));
+		uint32_t n = 0;
+		for (uint32_t i = 0; i < h.numCmds; ++i) {
+			if (tmp[i].num_vertices == 0) continue;
+			if (cmds) {
+				if (n >= cmdCap) {
+					if (err) *err = "draw-command capacity too small";
+					return VGB_ERR_CAPACITY;
+				}
+				cmds[n] = tmp[i];
+			}
+			++n;
+		}
+		if (numCmds) *numCmds = n;
+		if (uv) {
+			if (vcap < sz.num_vertices) {
+				if (err) *err = "vertex capacity too small";
+				return VGB_ERR_CAPACITY;
+			}
+			VGB_CUDA(cudaMemcpyAsync(uv, dUV.p, (size_t)sz.num_vertices * 4, cudaMemcpyDeviceToHost, st));
+		}
+		VGB_CUDA(cudaStreamSynchronize(st));
 		return 0;
 	}
 

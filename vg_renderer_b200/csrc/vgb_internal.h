@@ -98,6 +98,8 @@ public:
 	virtual int download(float* pos, uint32_t* color, void* index, uint64_t vcap, uint64_t icap,
 	                     uint64_t* mvo, uint64_t* mio, std::string* err) = 0;
 	virtual int downloadPaths(float* pts, uint64_t ptsCap, vgb_subpath* subs, uint32_t subCap, std::string* err) = 0;
+	virtual int setFinal(const vgb_final_cfg* cfg, std::string* err) = 0;
+	virtual int downloadFinal(int16_t* uv, uint64_t vcap, vgb_draw_cmd* cmds, uint32_t cmdCap, uint32_t* numCmds, void** uvDev, std::string* err) = 0;
 	virtual RunTimes times() = 0;
 	virtual void* stream() = 0;
 	virtual int mark(uint32_t slot, std::string* err) = 0;
