@@ -248,6 +248,21 @@ VGB_API int vgb_batch_set_final_layout(vgb_batch* b, const vgb_final_cfg* cfg);
 VGB_API int vgb_batch_download_final(vgb_batch* b, int16_t* uv, uint64_t vtx_capacity, vgb_draw_cmd* cmds, uint32_t cmd_capacity,
                                      uint32_t* num_cmds, void** uv_device);
 
+/* Instance replay -- the device-side analogue of vg.cpp's shape cache
+ * (addCachedCommand vg.cpp:5802-5841, submitCachedMesh vg.cpp:6137-6160): the meshes of the last run
+ * stay resident and are written out n more times, copy k with
+ *     pos = T_k( Tinv( pos_cached ) )      both by vgutil::batchTransformPositions (scalar build,
+ *                                          vg_util.h:24-28), the intermediate rounded to float as the
+ *                                          cache stores it; inv_xform = NULL skips Tinv
+ *     colour copied, uint16 indices copied (per-mesh local) / uint32 merged indices + k * V,
+ * V = vertices of the cached run.  The index type is the last run's; not available after a
+ * final-layout run.  Mesh (k, m) starts at k*V + mesh_vtx_off[m] / k*I + mesh_idx_off[m]. */
+VGB_API int vgb_batch_replay(vgb_batch* b, const float* xforms /* n x 6 */, uint32_t n, const float* inv_xform /* 6 or NULL */);
+/* sizes of the replay (num_vertices = n*V, num_indices = n*I, num_meshes = n*M), device pointers, host copy */
+VGB_API int vgb_batch_replay_sizes(vgb_batch* b, vgb_sizes* out);
+VGB_API int vgb_batch_replay_device_ptrs(vgb_batch* b, void** pos, void** color, void** index);
+VGB_API int vgb_batch_download_replay(vgb_batch* b, float* pos, uint32_t* color, void* index, uint64_t vtx_capacity, uint64_t idx_capacity);
+
 /* device-resident results (valid until the next run/reset/destroy) */
 VGB_API int vgb_batch_device_ptrs(vgb_batch* b, void** pos, void** color, void** index,
                                   void** mesh_vtx_off_u64, void** mesh_idx_off_u64,

@@ -139,6 +139,17 @@ class _Lib:
         return idx[:ni], uv[:nv], cmds[: n.value]
 
 
+    def transform_positions(self, pos, mtx):
+        """vgutil::batchTransformPositions: pos[n,2] x 2x3 matrix (a, b, c, d, e, f) -> [n,2]"""
+        f = getattr(self.lib, self.prefix + "_transform_positions")
+        f.restype = None
+        pos = np.ascontiguousarray(pos, np.float32).reshape(-1, 2)
+        m = np.ascontiguousarray(mtx, np.float32).reshape(6)
+        out = np.empty_like(pos)
+        f(_p(pos, C.c_float), C.c_uint32(len(pos)), _p(m, C.c_float), _p(out, C.c_float))
+        return out
+
+
 class RefLib(_Lib):
     """The compiled reference (oracle/_ref). kind: scalar (golden) | sse | libm."""
     prefix = "vgref"

@@ -264,4 +264,11 @@ int vgref_final_layout(const uint64_t* meshVtxOff, const uint64_t* meshIdxOff, u
 	return 0;
 }
 
+/* vgutil::batchTransformPositions (vg_util.cpp:136-227; this build: the scalar branch), the
+ * function submitCachedMesh (vg.cpp:6137-6160) and transformPath (vg.cpp:4957-4975) call */
+void vgref_transform_positions(const float* pos, uint32_t n, const float* mtx, float* out)
+{
+	vgutil::batchTransformPositions(pos, n, out, mtx);
+}
+
 } /* extern "C" */

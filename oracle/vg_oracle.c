@@ -1113,3 +1113,13 @@ int vgo_final_layout(const uint64_t* meshVtxOff, const uint64_t* meshIdxOff, uin
 	*numCmds = n;
 	return 0;
 }
+
+/* vgutil::transformPos2D per vertex (vg_util.h:24-28, scalar association; -ffp-contract=off) */
+void vgo_transform_positions(const float* pos, uint32_t n, const float* mtx, float* out)
+{
+	for (uint32_t i = 0; i < n; ++i) {
+		const float x = pos[2 * i], y = pos[2 * i + 1];
+		out[2 * i] = mtx[0] * x + mtx[2] * y + mtx[4];
+		out[2 * i + 1] = mtx[1] * x + mtx[3] * y + mtx[5];
+	}
+}

@@ -473,3 +473,67 @@ def test_final_layout_rejects_oversize_mesh_and_u32(gpu_batch):
         gpu_batch.set_final_layout(None)
     gpu_batch.run()  # back to per-mesh local indices
     assert int(gpu_batch.download()["index"].max()) < 400
+
+
+# ---- instance replay: the shape cache's replay on the device -----------------------
+def _rand_xforms(n, seed=5):
+    rng = np.random.default_rng(seed)
+    a = rng.uniform(0, 2 * np.pi, n)
+    s = rng.uniform(0.5, 2.0, n)
+    m = np.stack([np.cos(a) * s, np.sin(a) * s, -np.sin(a) * s, np.cos(a) * s, rng.uniform(0, 4096, n), rng.uniform(0, 4096, n)], axis=1)
+    return m.astype(np.float32)
+
+
+@pytest.mark.parametrize("index_u32", [False, True])
+def test_replay_matches_reference_transform(gpu_batch, ref, index_u32):
+    t = W.tiger_like()
+    exp = ref.run_batch(t)
+    xf = _rand_xforms(7)
+    inv = np.asarray([0.5, 0.25, -0.125, 2.0, 3.0, -7.0], np.float32)
+    gpu_batch.reset(1.0)
+    gpu_batch.add_tables(t)
+    gpu_batch.run(index_u32=index_u32, vertex_base=123 if index_u32 else 0)
+    src = gpu_batch.download()
+    V, I = exp["num_vertices"], exp["num_indices"]
+    for use_inv in (False, True):
+        gpu_batch.replay(xf, inv if use_inv else None)
+        out = gpu_batch.download_replay()
+        assert out["num_vertices"] == 7 * V and out["num_indices"] == 7 * I and out["num_meshes"] == 7 * exp["num_meshes"]
+        cached = ref.transform_positions(exp["pos"], inv) if use_inv else exp["pos"]
+        for k in range(7):
+            np.testing.assert_array_equal(out["pos"][k * V:(k + 1) * V], ref.transform_positions(cached, xf[k]))
+            np.testing.assert_array_equal(out["color"][k * V:(k + 1) * V], exp["color"])
+            want = src["index"].astype(np.uint64) + (np.uint64(k * V) if index_u32 else np.uint64(0))
+            np.testing.assert_array_equal(out["index"][k * I:(k + 1) * I].astype(np.uint64), want)
+    # the source run is untouched
+    check_same(gpu_batch.download(), exp) if not index_u32 else None
+
+
+def test_replay_odd_sizes_and_errors(gpu_batch, ref):
+    """odd vertex / index counts (plain stroke of a 3-point polyline: V = 6+..., I multiple of 3) so that copies start unaligned"""
+    r = Recorder(fringe=1.0)
+    r.begin_path().move_to(0, 0).line_to(10, 3).line_to(4, 9).stroke(2, 0xFF112233, 3.0, 1, 1).stroke(3, 0xFF445566, 1.0, 0, 0)
+    exp = ref.run_batch(r.tables())
+    V, I = exp["num_vertices"], exp["num_indices"]
+    assert V % 2 == 1 or I % 8 != 0
+    r.replay(gpu_batch)
+    gpu_batch.run()
+    xf = _rand_xforms(37, seed=9)
+    gpu_batch.replay(xf)
+    out = gpu_batch.download_replay()
+    for k in range(37):
+        np.testing.assert_array_equal(out["pos"][k * V:(k + 1) * V], ref.transform_positions(exp["pos"], xf[k]))
+        np.testing.assert_array_equal(out["index"][k * I:(k + 1) * I], exp["index"])
+    gpu_batch.replay(np.zeros((0, 6), np.float32))
+    assert gpu_batch.replay_sizes().num_vertices == 0
+    bad = xf.copy()
+    bad[3, 2] = np.inf
+    with pytest.raises(vgb.VgbError):
+        gpu_batch.replay(bad)
+    gpu_batch.set_final_layout(vgb.make_final_cfg(65536))
+    try:
+        gpu_batch.run()
+        with pytest.raises(vgb.VgbError):
+            gpu_batch.replay(xf)
+    finally:
+        gpu_batch.set_final_layout(None)

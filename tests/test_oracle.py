@@ -241,3 +241,15 @@ def test_final_layout_restatement_vs_reference_functions(orc):
             np.testing.assert_array_equal(a[0], b[0])
             np.testing.assert_array_equal(a[1], b[1])
             assert a[2].tobytes() == b[2].tobytes()
+
+
+@needs_ref
+def test_transform_positions_restatement_vs_reference(orc):
+    ref = RefLib("scalar")
+    rng = np.random.default_rng(3)
+    pos = rng.uniform(-4096, 4096, (10001, 2)).astype(np.float32)
+    for k in range(8):
+        m = rng.uniform(-3, 3, 6).astype(np.float32)
+        np.testing.assert_array_equal(ref.transform_positions(pos, m), orc.transform_positions(pos, m))
+    ident = np.asarray([1, 0, 0, 1, 0, 0], np.float32)
+    np.testing.assert_array_equal(orc.transform_positions(pos, ident), pos)

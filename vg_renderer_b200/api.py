@@ -128,6 +128,10 @@ def load_library():
     L.vgb_batch_download_paths.argtypes = [vp, vp, u64, vp, u32]
     L.vgb_batch_set_final_layout.argtypes = [vp, C.POINTER(FinalCfg)]
     L.vgb_batch_download_final.argtypes = [vp, vp, u64, vp, u32, C.POINTER(u32), C.POINTER(vp)]
+    L.vgb_batch_replay.argtypes = [vp, vp, u32, vp]
+    L.vgb_batch_replay_sizes.argtypes = [vp, C.POINTER(Sizes)]
+    L.vgb_batch_replay_device_ptrs.argtypes = [vp] + [C.POINTER(vp)] * 3
+    L.vgb_batch_download_replay.argtypes = [vp, vp, vp, vp, u64, u64]
     L.vgb_batch_execute.argtypes = [vp, u32, vp, vp, vp, u64, u64, vp, vp, C.POINTER(Sizes)]
     L.vgb_batch_last_run_ms.argtypes = [vp] + [C.POINTER(f)] * 4
     L.vgb_batch_mark.argtypes = [vp, u32]
@@ -341,6 +345,26 @@ class Batch:
         uv = np.empty((nv, 2), np.int16) if want_uv else None
         self._chk(self.L.vgb_batch_download_final(self.h, _ptr(uv), nv, _ptr(cmds), n.value, C.byref(n), None))
         return uv, cmds
+
+    def replay(self, xforms, inv_xform=None):
+        """write the meshes of the last run once per row of xforms[n,6] (instance replay)"""
+        x = np.ascontiguousarray(xforms, np.float32).reshape(-1, 6)
+        inv = np.ascontiguousarray(inv_xform, np.float32).reshape(6) if inv_xform is not None else None
+        return self._chk(self.L.vgb_batch_replay(self.h, _ptr(x), len(x), _ptr(inv)))
+
+    def replay_sizes(self):
+        s = Sizes()
+        self._chk(self.L.vgb_batch_replay_sizes(self.h, C.byref(s)))
+        return s
+
+    def download_replay(self):
+        s = self.replay_sizes()
+        nv, ni = int(s.num_vertices), int(s.num_indices)
+        pos = np.empty((nv, 2), np.float32)
+        col = np.empty(nv, np.uint32)
+        idx = np.empty(ni, np.uint32 if self.index_u32 else np.uint16)
+        self._chk(self.L.vgb_batch_download_replay(self.h, _ptr(pos), _ptr(col), _ptr(idx), nv, ni))
+        return dict(pos=pos, color=col, index=idx, num_vertices=nv, num_indices=ni, num_meshes=int(s.num_meshes))
 
     def download_paths(self):
         """-> (pts[T,2] f32, [(first, num, closed), ...])"""

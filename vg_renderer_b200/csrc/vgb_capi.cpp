@@ -673,6 +673,51 @@ int vgb_batch_download_paths(vgb_batch* b, float* pts, uint64_t ptsCap, vgb_subp
 	return 0;
 }
 
+int vgb_batch_replay(vgb_batch* b, const float* xforms, uint32_t n, const float* inv)
+{
+	NEED_PIPE(b);
+	if (!b) return fail(VGB_ERR_INVALID, "null batch");
+	if (n && !xforms) return fail(VGB_ERR_INVALID, "null transforms");
+	for (size_t i = 0; i < (size_t)n * 6; ++i) {
+		if (!std::isfinite(xforms[i])) return fail(VGB_ERR_NONFINITE, "non-finite instance transform");
+	}
+	for (int i = 0; inv && i < 6; ++i) {
+		if (!std::isfinite(inv[i])) return fail(VGB_ERR_NONFINITE, "non-finite inverse transform");
+	}
+	std::string err;
+	const int rc = b->pipe->replay(xforms, n, inv, &err);
+	if (rc) return fail(rc, err.c_str());
+	return 0;
+}
+
+int vgb_batch_replay_sizes(vgb_batch* b, vgb_sizes* out)
+{
+	NEED_PIPE(b);
+	if (!b || !out) return fail(VGB_ERR_INVALID, "null argument");
+	std::string err;
+	const int rc = b->pipe->replaySizes(out, &err);
+	if (rc) return fail(rc, err.c_str());
+	return 0;
+}
+
+int vgb_batch_replay_device_ptrs(vgb_batch* b, void** pos, void** color, void** index)
+{
+	NEED_PIPE(b);
+	if (!b) return fail(VGB_ERR_INVALID, "null batch");
+	b->pipe->replayPtrs(pos, color, index);
+	return 0;
+}
+
+int vgb_batch_download_replay(vgb_batch* b, float* pos, uint32_t* color, void* index, uint64_t vcap, uint64_t icap)
+{
+	NEED_PIPE(b);
+	if (!b) return fail(VGB_ERR_INVALID, "null batch");
+	std::string err;
+	const int rc = b->pipe->downloadReplay(pos, color, index, vcap, icap, &err);
+	if (rc) return fail(rc, err.c_str());
+	return 0;
+}
+
 int vgb_batch_set_final_layout(vgb_batch* b, const vgb_final_cfg* cfg)
 {
 	NEED_PIPE(b);

@@ -725,6 +725,76 @@ __global__ void k_fill_u32(uint32_t* __restrict__ dst, uint64_t n, uint32_t v)
 	for (uint64_t i = n4 * 4 + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) dst[i] = v;
 }
 
+/* ---- instance replay (submitCachedMesh, vg.cpp:6137-6160) -------------------------
+ * Pure streaming: a thread owns one cached vertex and writes it for a chunk of instances (the source is
+ * read once per chunk, the six matrix entries are warp-uniform loads); stores of a warp are consecutive
+ * in every instance.  transformPos2D keeps the reference's scalar association (vg_util.h:24-28). */
+static constexpr uint32_t REPLAY_CHUNK = 8; /* instances per block row */
+
+__global__ void k_replay_vertices(const float2* __restrict__ pos, const uint32_t* __restrict__ col, uint64_t V, const float* __restrict__ xf, uint32_t n,
+                                  const float* __restrict__ inv, float2* __restrict__ outPos, uint32_t* __restrict__ outCol)
+{
+	const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= V) return;
+	float2 p = pos[i];
+	const uint32_t c = col[i];
+	if (inv != nullptr) {
+		/* what the cache holds: the mesh in the command list's local space, rounded to float */
+		const float x = inv[0] * p.x + inv[2] * p.y + inv[4];
+		const float y = inv[1] * p.x + inv[3] * p.y + inv[5];
+		p = make_float2(x, y);
+	}
+	for (uint32_t k0 = blockIdx.y * REPLAY_CHUNK; k0 < n; k0 += gridDim.y * REPLAY_CHUNK) {
+		const uint32_t k1 = min(n, k0 + REPLAY_CHUNK);
+		for (uint32_t k = k0; k < k1; ++k) {
+			const float* m = xf + 6 * (size_t)k;
+			const float x = __ldg(m + 0) * p.x + __ldg(m + 2) * p.y + __ldg(m + 4);
+			const float y = __ldg(m + 1) * p.x + __ldg(m + 3) * p.y + __ldg(m + 5);
+			__stcs(outPos + (uint64_t)k * V + i, make_float2(x, y));
+			__stcs(outCol + (uint64_t)k * V + i, c);
+		}
+	}
+}
+
+/* the replayed index stream seen as one flat array: a thread produces 8 consecutive elements (one or
+ * two 128-bit stores), walking the cached stream cyclically; merged uint32 indices move by V per copy */
+template<class IDX>
+__global__ void k_replay_indices(const IDX* __restrict__ src, uint64_t I, uint64_t V, uint32_t n, IDX* __restrict__ out)
+{
+	const uint64_t total = I * n;
+	const uint64_t g0 = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) * 8;
+	if (g0 >= total) return;
+	uint64_t k = g0 / I, i = g0 - k * I;
+	IDX v[8];
+#pragma unroll
+	for (int e = 0; e < 8; ++e) {
+		v[e] = (IDX)(src[i] + (sizeof(IDX) == 4 ? (IDX)(k * V) : (IDX)0));
+		if (++i == I) {
+			i = 0;
+			++k;
+		}
+		if (g0 + e + 1 >= total) { /* clamp the walk inside the last copy */
+			i = 0;
+			k = 0;
+		}
+	}
+	if (g0 + 8 <= total) {
+		if (sizeof(IDX) == 2) {
+			uint4 w;
+			w.x = (uint32_t)v[0] | ((uint32_t)v[1] << 16);
+			w.y = (uint32_t)v[2] | ((uint32_t)v[3] << 16);
+			w.z = (uint32_t)v[4] | ((uint32_t)v[5] << 16);
+			w.w = (uint32_t)v[6] | ((uint32_t)v[7] << 16);
+			__stcs(reinterpret_cast<uint4*>(out + g0), w);
+		} else {
+			__stcs(reinterpret_cast<uint4*>(out + g0), make_uint4(v[0], v[1], v[2], v[3]));
+			__stcs(reinterpret_cast<uint4*>(out + g0) + 1, make_uint4(v[4], v[5], v[6], v[7]));
+		}
+	} else {
+		for (int e = 0; e < 8 && g0 + e < total; ++e) out[g0 + e] = v[e];
+	}
+}
+
 /* each warp counts GC consecutive groups; the loads of all of them are issued before any is used
  * (the kernel is a chain of dependent loads: piece -> job record -> points) */
 #ifndef VGB_GC
@@ -1012,6 +1082,10 @@ public:
 	vgb_final_cfg fcfg{};
 	uint32_t finalCmdCap = 0;
 	DevBuf dSegNext[2], dSegStarts, dSegHdr, dSegCmds, dMeshBase, dUV;
+	/* instance replay */
+	DevBuf dRXf, dRPos, dRCol, dRIdx;
+	uint32_t replayN = 0;
+	bool replayRan = false;
 	void* hPinned = nullptr; /* small pinned readback area */
 	HostTables ht;
 	bool hasXform = false, rawMode = false, uploaded = false, ran = false;
@@ -1028,7 +1102,8 @@ public:
 		cudaSetDevice(dev);
 		DevBuf* all[] = {&dSubRec, &dCmd, &dData, &dScale, &dTol, &dXform, &dDraws, &dJobSub, &dJobDraw, &dSubNum, &dSubFirst,
 		                 &dSubClosed, &dPts, &dDD, &dJobPieces, &dPieceStart, &dJobRec, &dPieceJob, &dBlockTotals, &dBlockBase,
-		                 &dMeshTotals, &dMeshOff, &dScanTmp, &dBlockTail, &dSlotFirst, &dCounters, &dDenseFirst, &dDensePts, &dBulkErr, &dMeshSplit, &dPos, &dCol, &dIdx};
+		                 &dMeshTotals, &dMeshOff, &dScanTmp, &dBlockTail, &dSlotFirst, &dCounters, &dDenseFirst, &dDensePts, &dBulkErr, &dMeshSplit, &dPos, &dCol, &dIdx,
+		                 &dSegNext[0], &dSegNext[1], &dSegStarts, &dSegHdr, &dSegCmds, &dMeshBase, &dUV, &dRXf, &dRPos, &dRCol, &dRIdx};
 		for (DevBuf* b : all) b->release();
 		for (auto& e : ev) if (e) cudaEventDestroy(e);
 		for (auto& e : userEv) if (e) cudaEventDestroy(e);
@@ -1524,6 +1599,82 @@ public:
 			}
 			VGB_CUDA(cudaMemcpyAsync(uv, dUV.p, (size_t)sz.num_vertices * 4, cudaMemcpyDeviceToHost, st));
 		}
+		VGB_CUDA(cudaStreamSynchronize(st));
+		return 0;
+	}
+
+	int replay(const float* xforms, uint32_t n, const float* inv, std::string* err) override
+	{
+		if (!ran) {
+			if (err) *err = "replay before run";
+			return VGB_ERR_STATE;
+		}
+		if (finalRan) {
+			if (err) *err = "replay of a final-layout run is not supported: run with plain uint16 or uint32 indices";
+			return VGB_ERR_STATE;
+		}
+		VGB_CUDA(cudaSetDevice(dev));
+		const uint64_t V = sz.num_vertices, I = sz.num_indices;
+		replayN = n;
+		replayRan = true;
+		if (!n || !V) return 0;
+		if (dRXf.ensure(((size_t)n + 1) * 24, err) || dRPos.ensure(V * n * 8 + 32, err) || dRCol.ensure(V * n * 4 + 32, err) ||
+		    dRIdx.ensure(I * n * idxBytes + 32, err))
+			return VGB_ERR_CUDA;
+		VGB_CUDA(cudaMemcpyAsync(dRXf.p, xforms, (size_t)n * 24, cudaMemcpyHostToDevice, st));
+		const float* dInv = nullptr;
+		if (inv) {
+			VGB_CUDA(cudaMemcpyAsync(dRXf.as<float>() + 6 * (size_t)n, inv, 24, cudaMemcpyHostToDevice, st));
+			dInv = dRXf.as<float>() + 6 * (size_t)n;
+		}
+		const uint32_t rows = (n + REPLAY_CHUNK - 1) / REPLAY_CHUNK;
+		dim3 grid((unsigned)((V + 255) / 256), rows < 65535u ? rows : 65535u);
+		k_replay_vertices<<<grid, 256, 0, st>>>(dPos.as<float2>(), dCol.as<uint32_t>(), V, dRXf.as<float>(), n, dInv, dRPos.as<float2>(), dRCol.as<uint32_t>());
+		if (I) {
+			const uint64_t threads = (I * n + 7) / 8;
+			if (idxBytes == 2) k_replay_indices<uint16_t><<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(dIdx.as<uint16_t>(), I, V, n, dRIdx.as<uint16_t>());
+			else k_replay_indices<uint32_t><<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(dIdx.as<uint32_t>(), I, V, n, dRIdx.as<uint32_t>());
+		}
+		VGB_CUDA(cudaGetLastError());
+		return 0;
+	}
+
+	int replaySizes(vgb_sizes* out, std::string* err) override
+	{
+		if (!replayRan) {
+			if (err) *err = "no replay yet";
+			return VGB_ERR_STATE;
+		}
+		*out = sz;
+		out->num_vertices = sz.num_vertices * replayN;
+		out->num_indices = sz.num_indices * replayN;
+		out->num_meshes = sz.num_meshes * replayN;
+		out->kernel_launches = sz.num_indices ? 2 : 1;
+		return 0;
+	}
+
+	void replayPtrs(void** pos, void** color, void** index) override
+	{
+		if (pos) *pos = dRPos.p;
+		if (color) *color = dRCol.p;
+		if (index) *index = dRIdx.p;
+	}
+
+	int downloadReplay(float* pos, uint32_t* color, void* index, uint64_t vcap, uint64_t icap, std::string* err) override
+	{
+		if (!replayRan) {
+			if (err) *err = "no replay yet";
+			return VGB_ERR_STATE;
+		}
+		VGB_CUDA(cudaSetDevice(dev));
+		const uint64_t V = sz.num_vertices * replayN, I = sz.num_indices * replayN;
+		if (((pos || color) && vcap < V) || (index && icap < I)) {
+			if (err) *err = "capacity too small";
+			return VGB_ERR_CAPACITY;
+		}
+		if (pos && V) VGB_CUDA(cudaMemcpyAsync(pos, dRPos.p, V * 8, cudaMemcpyDeviceToHost, st));
+		if (color && V) VGB_CUDA(cudaMemcpyAsync(color, dRCol.p, V * 4, cudaMemcpyDeviceToHost, st));
+		if (index && I) VGB_CUDA(cudaMemcpyAsync(index, dRIdx.p, I * idxBytes, cudaMemcpyDeviceToHost, st));
 		VGB_CUDA(cudaStreamSynchronize(st));
 		return 0;
 	}

@@ -100,6 +100,10 @@ public:
 	virtual int downloadPaths(float* pts, uint64_t ptsCap, vgb_subpath* subs, uint32_t subCap, std::string* err) = 0;
 	virtual int setFinal(const vgb_final_cfg* cfg, std::string* err) = 0;
 	virtual int downloadFinal(int16_t* uv, uint64_t vcap, vgb_draw_cmd* cmds, uint32_t cmdCap, uint32_t* numCmds, void** uvDev, std::string* err) = 0;
+	virtual int replay(const float* xforms, uint32_t n, const float* inv, std::string* err) = 0;
+	virtual int replaySizes(vgb_sizes* out, std::string* err) = 0;
+	virtual void replayPtrs(void** pos, void** color, void** index) = 0;
+	virtual int downloadReplay(float* pos, uint32_t* color, void* index, uint64_t vcap, uint64_t icap, std::string* err) = 0;
 	virtual RunTimes times() = 0;
 	virtual void* stream() = 0;
 	virtual int mark(uint32_t slot, std::string* err) = 0;
