@@ -223,11 +223,53 @@ VGB_API int vgb_batch_draw_polyline(vgb_batch* b, uint32_t subpath, uint32_t op,
 /* the same draw for every polyline sub-path / every recorded path */
 VGB_API int vgb_batch_draw_all(vgb_batch* b, uint32_t op, uint32_t color, float width, uint32_t cap, uint32_t join);
 
+/* transform of the current path, settable until its first draw is recorded (later calls are
+ * no-ops): vg.cpp applies the state transform lazily at a path's first fill/stroke and reuses the
+ * result for its other draws (transformPath, vg.cpp:4957-4975) */
+VGB_API int vgb_batch_set_path_xform(vgb_batch* b, const float* xform6);
+VGB_API float vgb_batch_fringe(vgb_batch* b);
+
+/* ---- command-list front end ------------------------------------------------
+ * Decodes a vg-renderer CommandList byte stream -- CommandHeader{type,size} records padded to 16
+ * bytes as clAllocCommand writes them (vg.cpp:5694-5723), command ids CommandType::Enum
+ * (vg.cpp:177-247) -- and records it into the batch the way ctxSubmitCommandList executes it
+ * (vg.cpp:4273-4637): path commands, FillPathColor (convex), StrokePathColor, the state stack,
+ * transforms, global alpha and scissor culling.  Paints, concave fills, text, clip regions,
+ * tri-lists and nested lists are skipped and counted in stats->unsupported.  The batch's fringe
+ * (vgb_batch_reset) is Context::m_FringeWidth. */
+typedef struct vgb_cl_context {
+	float xform[6];       /* in: State::m_TransformMtx on entry; out: on exit (the list's state changes persist, vg.h:34-35) */
+	float scissor[4];     /* in/out: State::m_ScissorRect (x, y, w, h)                                */
+	float global_alpha;   /* in/out: State::m_GlobalAlpha                                             */
+	float tess_tolerance; /* Context::m_TesselationTolerance                                          */
+	float canvas_width, canvas_height;
+	uint32_t flags;       /* CommandListFlags: 2 = AllowCommandCulling (vg.h:380-388)                 */
+} vgb_cl_context;
+
+typedef struct vgb_cl_stats {
+	uint32_t commands;    /* records decoded                                         */
+	uint32_t paths;       /* BeginPath                                               */
+	uint32_t draws;       /* fills / strokes recorded into the batch                 */
+	uint32_t culled;      /* stroker commands skipped under a zero-sized scissor     */
+	uint32_t zero_alpha;  /* draws dropped because their colour ends up transparent  */
+	uint32_t unsupported; /* commands outside this path (see above)                  */
+	uint32_t state_depth; /* states left pushed when the list ended                  */
+	uint32_t reserved;
+} vgb_cl_stats;
+
+VGB_API int vgb_batch_submit_command_list(vgb_batch* b, const void* commands, uint32_t size, vgb_cl_context* ctx, vgb_cl_stats* stats);
+
 /* introspection of what was recorded: out6 = {paths, sub-paths, commands, data floats, draws, jobs};
  * the arrays (each nullable) receive one entry per sub-path / per job */
 VGB_API int vgb_batch_recorded_counts(vgb_batch* b, uint32_t* out6);
 VGB_API int vgb_batch_recorded_subpaths(vgb_batch* b, uint32_t* cmd_begin, uint32_t* cmd_end, uint32_t* data_begin, uint32_t* path_id);
 VGB_API int vgb_batch_recorded_jobs(vgb_batch* b, uint32_t* job_subpath, uint32_t* job_draw);
+
+/* the recorded streams themselves (each nullable; sizes from vgb_batch_recorded_counts): command
+ * bytes, data floats, per path {scale, tol, 2x3 transform}, per draw {op, colour, width, cap, join, path} */
+VGB_API int vgb_batch_recorded_streams(vgb_batch* b, uint8_t* cmd, float* data, float* path_scale, float* path_tol, float* path_xform6,
+                                       uint32_t* draw_op, uint32_t* draw_color, float* draw_width, uint8_t* draw_cap, uint8_t* draw_join,
+                                       uint32_t* draw_path);
 
 /* ---- execution ----------------------------------------------------------------------------
  * upload: host tables -> device (async on the batch stream).  run: all kernels; results stay in

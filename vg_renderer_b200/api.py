@@ -65,6 +65,28 @@ def make_final_cfg(max_vb_vertices=65536, vb_id=0, vb_count=0, cmd_vertices=0, i
     return c
 
 
+class ClContext(C.Structure):
+    """vgb_cl_context"""
+    _fields_ = [("xform", C.c_float * 6), ("scissor", C.c_float * 4), ("global_alpha", C.c_float), ("tess_tolerance", C.c_float),
+                ("canvas_width", C.c_float), ("canvas_height", C.c_float), ("flags", C.c_uint32)]
+
+
+class ClStats(C.Structure):
+    """vgb_cl_stats"""
+    _fields_ = [(k, C.c_uint32) for k in ("commands", "paths", "draws", "culled", "zero_alpha", "unsupported", "state_depth", "reserved")]
+
+
+def make_cl_context(xform=(1, 0, 0, 1, 0, 0), global_alpha=1.0, tess_tolerance=0.25, canvas=(1280.0, 720.0), scissor=None, flags=0):
+    c = ClContext()
+    for i, v in enumerate(xform):
+        c.xform[i] = v
+    sc = scissor if scissor is not None else (0.0, 0.0, canvas[0], canvas[1])
+    for i, v in enumerate(sc):
+        c.scissor[i] = v
+    c.global_alpha, c.tess_tolerance, c.canvas_width, c.canvas_height, c.flags = global_alpha, tess_tolerance, canvas[0], canvas[1], flags
+    return c
+
+
 class SubPath(C.Structure):
     _fields_ = [("first_vertex", C.c_uint32), ("num_vertices", C.c_uint32), ("is_closed", C.c_uint8)]
 
@@ -119,6 +141,11 @@ def load_library():
     L.vgb_batch_recorded_counts.argtypes = [vp, vp]
     L.vgb_batch_recorded_subpaths.argtypes = [vp, vp, vp, vp, vp]
     L.vgb_batch_recorded_jobs.argtypes = [vp, vp, vp]
+    L.vgb_batch_recorded_streams.argtypes = [vp] + [vp] * 11
+    L.vgb_batch_set_path_xform.argtypes = [vp, vp]
+    L.vgb_batch_fringe.restype = f
+    L.vgb_batch_fringe.argtypes = [vp]
+    L.vgb_batch_submit_command_list.argtypes = [vp, vp, u32, C.POINTER(ClContext), C.POINTER(ClStats)]
     L.vgb_batch_upload.argtypes = [vp]
     L.vgb_batch_run.argtypes = [vp, u32, u64]
     L.vgb_batch_sync.argtypes = [vp]
@@ -286,6 +313,31 @@ class Batch:
         self._chk(self.L.vgb_batch_recorded_jobs(self.h, _ptr(js), _ptr(jd)))
         return dict(num_paths=int(c[0]), num_subpaths=ns, num_cmds=int(c[2]), num_data=int(c[3]), num_draws=int(c[4]), num_jobs=nj,
                     cmd_begin=a[0][:ns], cmd_end=a[1][:ns], data_begin=a[2][:ns], path_id=a[3][:ns], job_subpath=js[:nj], job_draw=jd[:nj])
+
+    def recorded_streams(self):
+        """everything recorded, as arrays: cmd, data, path_scale, path_tol, path_xform[P,6], draw_{op,color,width,cap,join,path}"""
+        r = self.recorded()
+        P, D = r["num_paths"], r["num_draws"]
+        out = dict(cmd=np.zeros(max(r["num_cmds"], 1), np.uint8), data=np.zeros(max(r["num_data"], 1), np.float32),
+                   path_scale=np.zeros(max(P, 1), np.float32), path_tol=np.zeros(max(P, 1), np.float32),
+                   path_xform=np.zeros((max(P, 1), 6), np.float32), draw_op=np.zeros(max(D, 1), np.uint32),
+                   draw_color=np.zeros(max(D, 1), np.uint32), draw_width=np.zeros(max(D, 1), np.float32),
+                   draw_cap=np.zeros(max(D, 1), np.uint8), draw_join=np.zeros(max(D, 1), np.uint8), draw_path=np.zeros(max(D, 1), np.uint32))
+        self._chk(self.L.vgb_batch_recorded_streams(self.h, *[_ptr(out[k]) for k in (
+            "cmd", "data", "path_scale", "path_tol", "path_xform", "draw_op", "draw_color", "draw_width", "draw_cap", "draw_join", "draw_path")]))
+        n = dict(cmd=r["num_cmds"], data=r["num_data"], path_scale=P, path_tol=P, path_xform=P)
+        return {k: v[: n.get(k, D)] for k, v in out.items()} | r
+
+    def set_path_xform(self, xform6):
+        m = np.ascontiguousarray(xform6, np.float32).reshape(6)
+        return self._chk(self.L.vgb_batch_set_path_xform(self.h, _ptr(m)))
+
+    def submit_command_list(self, buf, ctx):
+        """decode a vg-renderer CommandList byte stream (bytes / uint8 array) into the batch; ctx: ClContext (updated in place)"""
+        a = np.frombuffer(bytes(buf), np.uint8) if not isinstance(buf, np.ndarray) else np.ascontiguousarray(buf, np.uint8)
+        st = ClStats()
+        self._chk(self.L.vgb_batch_submit_command_list(self.h, _ptr(a) if len(a) else None, len(a), C.byref(ctx), C.byref(st)))
+        return st
 
     # ---- execution ----
     def upload(self): return self._chk(self.L.vgb_batch_upload(self.h))

@@ -211,6 +211,22 @@ int vgb_batch_begin_path(vgb_batch* b, float scale, float tol, const float* xfor
 	return 0;
 }
 
+extern "C" void vgb_set_error_message(const char* msg) { t_err = msg ? msg : ""; } /* for the other host translation units */
+
+float vgb_batch_fringe(vgb_batch* b) { return b ? b->fringe : 0.0f; }
+
+int vgb_batch_set_path_xform(vgb_batch* b, const float* xform6)
+{
+	if (!b || !b->inPath || !xform6) return fail(VGB_ERR_INVALID, "set_path_xform outside a path");
+	if (!finite_all(xform6, 6)) return fail(VGB_ERR_NONFINITE, "non-finite transform");
+	if (b->drawn) return 0; /* vg.cpp transforms a path once, at its first fill/stroke (transformPath, vg.cpp:4957-4975) */
+	b->anyXform = true;
+	b->xformIdentityUpTo(b->pathScale.size());
+	memcpy(&b->pathXform[6 * (size_t)b->curPath], xform6, sizeof(float) * 6);
+	b->dirty = true;
+	return 0;
+}
+
 int vgb_batch_move_to(vgb_batch* b, float x, float y)
 {
 	const float d[2] = {x, y};
@@ -531,6 +547,36 @@ int vgb_batch_recorded_jobs(vgb_batch* b, uint32_t* js, uint32_t* jd)
 	for (size_t i = 0; i < b->jobSub.size(); ++i) {
 		if (js) js[i] = b->jobSub[i];
 		if (jd) jd[i] = b->jobDraw[i];
+	}
+	return 0;
+}
+
+int vgb_batch_recorded_streams(vgb_batch* b, uint8_t* cmd, float* data, float* scale, float* tol, float* xform6, uint32_t* drawOp, uint32_t* drawColor,
+                               float* drawWidth, uint8_t* drawCap, uint8_t* drawJoin, uint32_t* drawPath)
+{
+	if (!b) return fail(VGB_ERR_INVALID, "null batch");
+	if (b->bulkP8 || b->rawMode) return fail(VGB_ERR_STATE, "recorded_streams: bulk / polyline batches have no command streams");
+	b->closeSub();
+	if (cmd && !b->cmd.empty()) memcpy(cmd, b->cmd.data(), b->cmd.size());
+	if (data && !b->data.empty()) memcpy(data, b->data.data(), b->data.size() * sizeof(float));
+	const size_t np = b->pathScale.size();
+	for (size_t i = 0; i < np; ++i) {
+		if (scale) scale[i] = b->pathScale[i];
+		if (tol) tol[i] = b->pathTol[i];
+		if (xform6) {
+			static const float ident[6] = {1, 0, 0, 1, 0, 0};
+			const float* m = (b->anyXform && b->pathXform.size() >= 6 * (i + 1)) ? &b->pathXform[6 * i] : ident;
+			memcpy(xform6 + 6 * i, m, sizeof(float) * 6);
+		}
+	}
+	for (size_t i = 0; i < b->draws.size(); ++i) {
+		const DrawRec& d = b->draws[i];
+		if (drawOp) drawOp[i] = d.ocj & 0xFF;
+		if (drawCap) drawCap[i] = (uint8_t)((d.ocj >> 8) & 0xFF);
+		if (drawJoin) drawJoin[i] = (uint8_t)((d.ocj >> 16) & 0xFF);
+		if (drawColor) drawColor[i] = d.color;
+		if (drawWidth) drawWidth[i] = d.width;
+		if (drawPath) drawPath[i] = d.pathId;
 	}
 	return 0;
 }
