@@ -501,33 +501,63 @@ __device__ __forceinline__ void bulkStore(void* gdst, const void* ssrc, uint32_t
 __device__ __forceinline__ void bulkCommit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulkWaitRead() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 
-/* one WARP streams one array: lane 0 issues (and later waits for) the bulk copy of the 16-byte
- * aligned body, lanes 1..16 store the ragged head/tail (fewer than 16 bytes each) */
+/* where the 16-byte aligned body of an output range [gs, gs + count) of T lies, and its ragged ends */
 template<class T>
-__device__ __forceinline__ void copyOutWarp(T* __restrict__ gbase, uint64_t gs, uint32_t count, const T* sbuf, uint32_t lane)
+struct CopyPlan
 {
-	constexpr uint32_t K = 16 / sizeof(T);
-	const uint64_t ge = gs + count;
-	const uint64_t alignedBase = gs & ~(uint64_t)(K - 1);
-	uint64_t bodyBegin = (gs + K - 1) & ~(uint64_t)(K - 1);
-	uint64_t bodyEnd = ge & ~(uint64_t)(K - 1);
-	if (bodyEnd <= bodyBegin) {
-		bodyBegin = bodyEnd = ge; /* everything is ragged (count < 2K) */
+	uint64_t alignedBase, bodyBegin, bodyEnd;
+	uint32_t head, tail;
+	__device__ __forceinline__ CopyPlan(uint64_t gs, uint32_t count)
+	{
+		constexpr uint32_t K = 16 / sizeof(T);
+		const uint64_t ge = gs + count;
+		alignedBase = gs & ~(uint64_t)(K - 1);
+		bodyBegin = (gs + K - 1) & ~(uint64_t)(K - 1);
+		bodyEnd = ge & ~(uint64_t)(K - 1);
+		if (bodyEnd <= bodyBegin) {
+			bodyBegin = bodyEnd = ge; /* everything is ragged (count < 2K) */
+		}
+		head = (uint32_t)(bodyBegin - gs);
+		tail = (uint32_t)(ge - bodyEnd);
 	}
-	if (lane == 0) {
-		if (bodyEnd > bodyBegin) {
-			bulkStore(gbase + bodyBegin, sbuf + (bodyBegin - alignedBase), (uint32_t)((bodyEnd - bodyBegin) * sizeof(T)));
+};
+
+/* ragged ends of one stream: lanes 1.. take the head elements, lanes 17.. the tail elements, one pass */
+template<class T>
+__device__ __forceinline__ void copyRagged(T* __restrict__ gbase, uint64_t gs, const CopyPlan<T>& c, const T* sbuf, uint32_t lane)
+{
+	const uint32_t l = lane - 1;
+	const bool isHead = l < c.head;
+	const bool isTail = l >= 16 && l - 16 < c.tail;
+	if (isHead || isTail) {
+		const uint64_t e = isHead ? gs + l : c.bodyEnd + (l - 16);
+		gbase[e] = sbuf[e - c.alignedBase];
+	}
+}
+
+/* one WARP streams its three arrays: lanes 0, 1, 2 each issue (and later wait for) the bulk copy of
+ * one stream's aligned body; the ragged ends (fewer than 16 bytes each) are stored by lanes */
+template<class IDX>
+__device__ __forceinline__ void copyOutWarp3(float2* __restrict__ gPos, uint32_t* __restrict__ gCol, IDX* __restrict__ gIdx, uint64_t vs, uint64_t is,
+                                             uint32_t totV, uint32_t totI, const float2* sPos, const uint32_t* sCol, const IDX* sIdx, uint32_t lane)
+{
+	const CopyPlan<float2> cp(vs, totV);
+	const CopyPlan<uint32_t> cc(vs, totV);
+	const CopyPlan<IDX> ci(is, totI);
+	if (lane < 3) {
+		const void* src = lane == 0 ? (const void*)(sPos + (cp.bodyBegin - cp.alignedBase))
+		                : lane == 1 ? (const void*)(sCol + (cc.bodyBegin - cc.alignedBase)) : (const void*)(sIdx + (ci.bodyBegin - ci.alignedBase));
+		void* dst = lane == 0 ? (void*)(gPos + cp.bodyBegin) : lane == 1 ? (void*)(gCol + cc.bodyBegin) : (void*)(gIdx + ci.bodyBegin);
+		const uint32_t bytes = lane == 0 ? (uint32_t)(cp.bodyEnd - cp.bodyBegin) * 8u
+		                     : lane == 1 ? (uint32_t)(cc.bodyEnd - cc.bodyBegin) * 4u : (uint32_t)(ci.bodyEnd - ci.bodyBegin) * (uint32_t)sizeof(IDX);
+		if (bytes) {
+			bulkStore(dst, src, bytes);
 		}
 		bulkCommit();
 	}
-	const uint32_t head = (uint32_t)(bodyBegin - gs);
-	const uint32_t tail = (uint32_t)(ge - bodyEnd);
-	const uint32_t l = lane - 1;
-	if (l < head) {
-		gbase[gs + l] = sbuf[(gs - alignedBase) + l];
-	} else if (l >= 16 && l - 16 < tail) {
-		gbase[bodyEnd + (l - 16)] = sbuf[(bodyEnd - alignedBase) + (l - 16)];
-	}
+	copyRagged(gPos, vs, cp, sPos, lane);
+	copyRagged(gCol, vs, cc, sCol, lane);
+	copyRagged(gIdx, is, ci, sIdx, lane);
 }
 
 template<uint32_t OPS, int JT, int CT, class SINK>
@@ -957,10 +987,8 @@ __global__ void __launch_bounds__(128, VGB_EMIT_MIN_BLOCKS) k_group_emit(PieceAr
 	if (fits) {
 		fenceProxyAsync();
 		__syncwarp();
-		copyOutWarp<float2>(a.pos, bb.x, totV, sPos, lane);
-		copyOutWarp<uint32_t>(a.col, bb.x, totV, sCol, lane);
-		copyOutWarp<IDX>(reinterpret_cast<IDX*>(a.idx), bb.y, totI, sIdx, lane);
-		if (lane == 0) {
+		copyOutWarp3<IDX>(a.pos, a.col, reinterpret_cast<IDX*>(a.idx), bb.x, bb.y, totV, totI, sPos, sCol, sIdx, lane);
+		if (lane < 3) {
 			bulkWaitRead();
 		}
 	}

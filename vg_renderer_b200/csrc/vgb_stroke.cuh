@@ -681,29 +681,30 @@ __device__ __forceinline__ void emitStrokeAA(const JobCtx& J, const Piece& P, ui
 		S.connect(0, prev, isCap ? make_uint4(F + 1, F, e, e + 1) : joinIn4(left, F));
 		k = 18;
 	}
-	if (isCap) {
-		/* fan + fringe quads (1491-1510 / 1947-1968): an end cap swaps the 2nd and 3rd index of each triangle */
-		const uint32_t o2 = isEnd ? 4u : 2u, o3 = isEnd ? 2u : 4u;
-		for (uint32_t i = 0; i + 2 < n; ++i, k += 3) {
-			S.tri(k, F, F + 2 * i + o2, F + 2 * i + o3);
+	/* One index loop for both kinds, three triangles per iteration:
+	 *   join slice i (1651-1685 / 1807-1841):  (F+1, A+u2, A+u3) (A, A+w2, A+w3) (A, A+x2, A+x3), A = F+2+2i, 9 consecutive indices
+	 *   cap step i  (1491-1510 / 1947-1968):   fan (F, b+o2, b+o3) for i < nHC-2 at 3i, then the fringe quad
+	 *                                          (b, b+q2, b+q3) (b, b+r2, b+r3) at 3(nHC-2) + 6i, b = F+2i;
+	 *                                          an end cap swaps the 2nd and 3rd index of each triangle
+	 * so the few cap lanes of a warp ride in the join lanes' iterations instead of running their own loops. */
+	const uint32_t cntI = isCap ? n - 1 : n;
+	const uint32_t fanN = isCap ? n - 2 : n;
+	const uint32_t a0 = isCap ? F : F + 1;
+	uint32_t B = isCap ? F : F + 2;
+	const uint32_t c0b = isCap ? (isEnd ? 4u : 2u) : (left ? 0u : 2u), c0c = isCap ? (isEnd ? 2u : 4u) : (left ? 2u : 0u);
+	const uint32_t c1b = isCap ? (isEnd ? 3u : 1u) : (left ? 1u : 3u), c1c = isCap ? (isEnd ? 1u : 3u) : (left ? 3u : 1u);
+	const uint32_t c2b = isCap ? (isEnd ? 2u : 3u) : (left ? 3u : 2u), c2c = isCap ? (isEnd ? 3u : 2u) : (left ? 2u : 3u);
+	const uint32_t s0 = isCap ? 3u : 9u, s1 = isCap ? 6u : 9u;
+	uint32_t k0 = k, k1 = k + (isCap ? 3 * (n - 2) : 3u);
+	for (uint32_t i = 0; i < cntI; ++i, k0 += s0, k1 += s1, B += 2) {
+		if (i < fanN) {
+			S.tri(k0, a0, B + c0b, B + c0c);
 		}
-		const uint32_t q2 = isEnd ? 3u : 1u, q3 = isEnd ? 1u : 3u, r2 = isEnd ? 2u : 3u, r3 = isEnd ? 3u : 2u;
-		for (uint32_t i = 0; i + 1 < n; ++i, k += 6) {
-			const uint32_t b = F + 2 * i;
-			S.tri(k, b, b + q2, b + q3);
-			S.tri(k + 3, b, b + r2, b + r3);
-		}
-		return;
+		S.tri(k1, B, B + c1b, B + c1c);
+		S.tri(k1 + 3, B, B + c2b, B + c2c);
 	}
-	uint32_t A = F + 2;
-	const uint32_t u2 = left ? 0u : 2u, u3 = left ? 2u : 0u, w2 = left ? 1u : 3u, w3 = left ? 3u : 1u, x2 = left ? 3u : 2u, x3 = left ? 2u : 3u;
-	for (uint32_t i = 0; i < n; ++i, k += 9, A += 2) {
-		S.tri(k, F + 1, A + u2, A + u3);
-		S.tri(k + 3, A, A + w2, A + w3);
-		S.tri(k + 6, A, A + x2, A + x3);
-	}
-	if (P.flags & PF_CLOSING) {
-		S.connect(k, out4FromTail(0, jt, packTail(P), F + P.vcount), joinIn4(firstLeft, 0));
+	if (!isCap && (P.flags & PF_CLOSING)) {
+		S.connect(k + 9 * n, out4FromTail(0, jt, packTail(P), F + P.vcount), joinIn4(firstLeft, 0));
 	}
 }
 
