@@ -82,15 +82,18 @@ __host__ __device__ __forceinline__ uint32_t pieceCount(uint32_t op, uint32_t N)
 }
 
 /* side test + arc subdivision of one join (stroker.cpp:1528-1535, 1581-1596, 1737-1752) */
+/* cap = true: a ROUND CAP lane riding along (round joins only) for the one thing it shares with a
+ * join, its start angle atan2(l.y, l.x), l = perpCCW(d) -- the right-inner form of a01 below; the
+ * caller overwrites every other field afterwards */
 template<int JT>
-__device__ __forceinline__ void classifyJoinAA(const JobCtx& J, Piece& P)
+__device__ __forceinline__ void classifyJoinAA(const JobCtx& J, Piece& P, bool cap = false)
 {
 	const uint32_t jt = JT < 3 ? (uint32_t)JT : J.join; /* compile-time join type when the whole batch shares it */
 	P.v = extrusion(P.d01, P.d12);
 	const float vx = P.v.x * J.hsw_aa;
 	const float vy = P.v.y * J.hsw_aa;
 	const float proj = P.d12.x * vx + P.d12.y * vy;
-	const bool left = proj >= 0.0f;
+	const bool left = !cap && proj >= 0.0f;
 	if (left) {
 		P.flags |= PF_LEFT;
 	}
@@ -299,19 +302,13 @@ __device__ __forceinline__ Piece classify(const JobCtx& J, uint32_t q, const flo
 		const float2 pn = v[q < N - 1 ? q + 1 : (open ? q : 0u)];
 		P.p = v[q];
 		const float2 dA = vdir(pm, P.p), dB = vdir(P.p, pn);
-		if (isStart || isEnd) {
+		const uint32_t jt = JT < 3 ? (uint32_t)JT : J.join;
+		const bool isCap = isStart || isEnd;
+		/* with round joins a round cap takes its start angle from the joins' atan2 (same expression) */
+		const bool capRides = isCap && ct == VGB_CAP_ROUND && jt == VGB_JOIN_ROUND;
+		if (isCap) {
 			P.kind = isStart ? PK_CAP_START : PK_CAP_END;
 			P.d01 = isStart ? dB : dA;
-			P.flags = isEnd ? PF_HAS_PREV : 0u;
-			if (ct == VGB_CAP_ROUND) {
-				P.n = J.nHC;
-				P.vcount = 2 * J.nHC;
-				P.icount = isStart ? 9 * J.nHC - 12 : 9 * J.nHC + 6;
-				P.a01 = vgb_atan2(P.d01.x, -P.d01.y); /* startAngle = atan2(l.y, l.x), l = perpCCW(d) (1476, 1919) */
-			} else {
-				P.vcount = 4;
-				P.icount = isStart ? 6u : 24u;
-			}
 		} else {
 			P.kind = PK_JOIN;
 			P.d01 = dA;
@@ -322,7 +319,28 @@ __device__ __forceinline__ Piece classify(const JobCtx& J, uint32_t q, const flo
 			if (J.closed && q == N - 1) {
 				P.flags |= PF_CLOSING;
 			}
-			classifyJoinAA<JT>(J, P);
+		}
+		if (!isCap || capRides) {
+			classifyJoinAA<JT>(J, P, isCap);
+		}
+		if (isCap) {
+			P.flags = isEnd ? PF_HAS_PREV : 0u;
+			P.d12 = f2(0.0f, 0.0f);
+			P.v = f2(0.0f, 0.0f);
+			P.arcDa = 0.0f;
+			if (ct == VGB_CAP_ROUND) {
+				P.n = J.nHC;
+				P.vcount = 2 * J.nHC;
+				P.icount = isStart ? 9 * J.nHC - 12 : 9 * J.nHC + 6;
+				if (!capRides) {
+					P.a01 = vgb_atan2(P.d01.x, -P.d01.y); /* startAngle = atan2(l.y, l.x), l = perpCCW(d) (1476, 1919) */
+				}
+			} else {
+				P.n = 0;
+				P.a01 = 0.0f;
+				P.vcount = 4;
+				P.icount = isStart ? 6u : 24u;
+			}
 		}
 	} else if ((OPS & OPS_FILL_AA) && (!(OPS & ~OPS_FILL_AA) || J.op == VGB_OP_CONVEX_FILL_AA)) {
 		if (q < N - 2) {
@@ -646,9 +664,17 @@ __device__ __forceinline__ void emitStrokeAA(const JobCtx& J, const Piece& P, ui
 	const uint32_t vb = isCap ? 0u : 2u;
 	const uint32_t cnt = isCap ? n : n + 1;
 	const float capDen = (float)(n - 1);
+	/* (i*pi)/capDen: when capDen is a power of two (nHC = 2, 3, 5, 9 ...) the division is an exact scaling
+	 * and multiplying by the exact reciprocal 2^-e gives the same bits; other values keep the division */
+	const uint32_t denBits = __float_as_uint(capDen);
+	const bool denPow2 = (denBits & 0x007FFFFFu) == 0u;
+	const float capRcp = __uint_as_float(0x7F000000u - denBits);
 	const float bev = (!isCap && jt == VGB_JOIN_BEVEL) ? fabsf(s01.x * s12.x + s01.y * s12.y) * J.fringe : 0.0f;
 	for (uint32_t i = 0; i < cnt; ++i) {
-		const float t = isCap ? (float)i * VGB_PI / capDen : (float)i * P.arcDa;
+		float t = (float)i * (isCap ? VGB_PI : P.arcDa);
+		if (isCap) {
+			t = denPow2 ? t * capRcp : t / capDen;
+		}
 		const float a = P.a01 + (isEnd ? -t : t);
 		float dy, dx;
 		vgb_sincos(a, &dy, &dx);
