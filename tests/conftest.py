@@ -27,3 +27,19 @@ def gpu_batch():
     if vgb.device_count() < 1:
         pytest.fail("gpu-marked test on a box without a CUDA device")
     return vgb.Batch(0)
+
+
+# VGB_TEST_RERUN=1 python -m pytest tests -m gpu : every Batch.run() of the suite is issued twice, so that all
+# parity tests exercise the paths that only exist once the sizes of an upload are known (no mid-pipeline
+# read-backs) -- the round-end run uses the default (first-run) paths; tests/test_gpu_parity.py
+# has a dedicated re-run test as well.
+if os.environ.get("VGB_TEST_RERUN"):
+    import vg_renderer_b200.api as _api
+
+    _run_once = _api.Batch.run
+
+    def _run_twice(self, *a, **k):
+        _run_once(self, *a, **k)
+        return _run_once(self, *a, **k)
+
+    _api.Batch.run = _run_twice

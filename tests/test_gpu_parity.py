@@ -537,3 +537,42 @@ def test_replay_odd_sizes_and_errors(gpu_batch, ref):
             gpu_batch.replay(xf)
     finally:
         gpu_batch.set_final_layout(None)
+
+
+# ---- re-runs of an upload: sizes are reused, nothing is read back mid-pipeline ---------------------------
+def test_rerun_matches_first_run_and_reference(gpu_batch, ref):
+    cases = []
+    for cap, join in CAPJOIN:
+        cases.append(BatchTables.cubic_strokes(W.config3_cubics(700, first=41 * cap + join), width=3.0 + cap, cap=cap, join=join))
+    cases.append(mixed_recorder().tables())
+    cases.append(W.instance_tables(W.tiger_like(), 5))
+    for t in cases:
+        exp = ref.run_batch(t)
+        gpu_batch.reset(1.0)
+        gpu_batch.add_tables(t)
+        gpu_batch.run()
+        first = gpu_batch.download()
+        check_same(first, exp)
+        for _ in range(2):
+            gpu_batch.run()  # sizes known: no read-backs
+            check_same(gpu_batch.download(), exp)
+        gpu_batch.run(index_u32=True, vertex_base=77)
+        o32 = gpu_batch.download()
+        merged = exp["index"].astype(np.uint64) + np.repeat(exp["mesh_vtx_off"][:-1], np.diff(exp["mesh_idx_off"]).astype(np.int64)) + np.uint64(77)
+        np.testing.assert_array_equal(o32["index"].astype(np.uint64), merged)
+        np.testing.assert_array_equal(o32["mesh_vtx_off"], exp["mesh_vtx_off"])
+        np.testing.assert_array_equal(o32["mesh_idx_off"], exp["mesh_idx_off"])
+
+
+def test_rerun_large_batch_with_empty_meshes(gpu_batch, ref):
+    """many groups, meshes straddling group borders, empty meshes in the middle of the batch"""
+    p8 = W.config3_cubics(60000, first=123)
+    p8[1000:1010, 2:] = np.tile(p8[1000:1010, :2], 3)  # all four control points equal: single-point sub-paths -> empty meshes
+    t = BatchTables.cubic_strokes(p8, width=4.0, cap=1, join=1)
+    exp = ref.run_batch(t)
+    gpu_batch.reset(1.0)
+    gpu_batch.add_cubic_strokes(p8, width=4.0, cap=1, join=1)
+    gpu_batch.run()
+    gpu_batch.run()
+    check_same(gpu_batch.download(), exp)
+    assert int(np.sum(np.diff(exp["mesh_vtx_off"]) == 0)) >= 10
