@@ -11,13 +11,16 @@
  *   k_draw_prep        per-draw constants (hsw, da, nHC, nfix ...) with the shared fp32 math
  *   k_job_pieces       pieces per job (mesh) -> scan -> pieceStart;  k_job_prep: 48-byte job records
  *                      + per-piece job ids
- *   k_group_count      lane per piece: sizes -> per-warp-group (V,I) totals, hand-over words,
+ *   k_group_count      lane per piece, 2 groups per warp: sizes -> per-group (V,I) totals, hand-over words,
  *                      within-group mesh starts (geometry-free shortcut when sizes are provable)
  *   scan (u32x2->u64x2), k_mesh_off   group bases, mesh table
  *   k_group_emit       the hot kernel: a warp owns 32 pieces = one contiguous output range; lanes emit
  *                      vertices / colours / indices into a warp-private shared-memory image that
  *                      leaves through the TMA engine (cp.async.bulk), no block barrier anywhere
  *   k_fill_job_sizes, k_fill_emit   pure convex-AA-fill batches: closed-form sizes and addresses
+ *   k_seg_next/_double/_cmds/_mesh_base, k_fill_u32   final layout: greedy vertex-buffer
+ *                      segmentation by pointer doubling, draw-command table, per-mesh index bases, uv stream
+ *   k_replay_vertices, k_replay_indices   instance replay: cached meshes x n transforms
  *
  * Build: nvcc -gencode arch=compute_100a,code=sm_100a -fmad=false (see Makefile).  -fmad=false
  * plus vgb_math.h's __f*_rn intrinsics make every float result identical to the non-FMA CPU
@@ -44,6 +47,12 @@ namespace vgb
 		}                                                                                     \
 	} while (0)
 
+#ifndef VGB_EMIT_PREFETCH
+#define VGB_EMIT_PREFETCH 1
+#endif
+#ifndef VGB_EMIT_MIN_BLOCKS_SPEC
+#define VGB_EMIT_MIN_BLOCKS_SPEC 8
+#endif
 #ifndef VGB_EMIT_MIN_BLOCKS
 #define VGB_EMIT_MIN_BLOCKS 9
 #endif
@@ -786,42 +795,21 @@ __global__ void k_replay_vertices(const float2* __restrict__ pos, const uint32_t
 	}
 }
 
-/* the replayed index stream seen as one flat array: a thread produces 8 consecutive elements (one or
- * two 128-bit stores), walking the cached stream cyclically; merged uint32 indices move by V per copy */
-template<class IDX>
-__global__ void k_replay_indices(const IDX* __restrict__ src, uint64_t I, uint64_t V, uint32_t n, IDX* __restrict__ out)
+/* indices: a thread owns one cached word and writes it for a chunk of instances -- one coalesced load, then
+ * fully coalesced stores in every copy.  W = uint32 merged index (+ k*V per copy), uint16 local index, or a
+ * PAIR of uint16 local indices moved as one 32-bit word (when the cached stream has an even length, so that
+ * every copy starts 4-byte aligned) */
+template<class W, bool ADD>
+__global__ void k_replay_indices(const W* __restrict__ src, uint64_t I, uint64_t V, uint32_t n, W* __restrict__ out)
 {
-	const uint64_t total = I * n;
-	const uint64_t g0 = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) * 8;
-	if (g0 >= total) return;
-	uint64_t k = g0 / I, i = g0 - k * I;
-	IDX v[8];
-#pragma unroll
-	for (int e = 0; e < 8; ++e) {
-		v[e] = (IDX)(src[i] + (sizeof(IDX) == 4 ? (IDX)(k * V) : (IDX)0));
-		if (++i == I) {
-			i = 0;
-			++k;
+	const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= I) return;
+	const W v = src[i];
+	for (uint32_t k0 = blockIdx.y * REPLAY_CHUNK; k0 < n; k0 += gridDim.y * REPLAY_CHUNK) {
+		const uint32_t k1 = min(n, k0 + REPLAY_CHUNK);
+		for (uint32_t k = k0; k < k1; ++k) {
+			__stcs(out + (uint64_t)k * I + i, ADD ? (W)(v + (W)(k * V)) : v);
 		}
-		if (g0 + e + 1 >= total) { /* clamp the walk inside the last copy */
-			i = 0;
-			k = 0;
-		}
-	}
-	if (g0 + 8 <= total) {
-		if (sizeof(IDX) == 2) {
-			uint4 w;
-			w.x = (uint32_t)v[0] | ((uint32_t)v[1] << 16);
-			w.y = (uint32_t)v[2] | ((uint32_t)v[3] << 16);
-			w.z = (uint32_t)v[4] | ((uint32_t)v[5] << 16);
-			w.w = (uint32_t)v[6] | ((uint32_t)v[7] << 16);
-			__stcs(reinterpret_cast<uint4*>(out + g0), w);
-		} else {
-			__stcs(reinterpret_cast<uint4*>(out + g0), make_uint4(v[0], v[1], v[2], v[3]));
-			__stcs(reinterpret_cast<uint4*>(out + g0) + 1, make_uint4(v[4], v[5], v[6], v[7]));
-		}
-	} else {
-		for (int e = 0; e < 8 && g0 + e < total; ++e) out[g0 + e] = v[e];
 	}
 }
 
@@ -904,8 +892,11 @@ __global__ void __launch_bounds__(128, VGB_COUNT_MIN_BLOCKS) k_group_count(Piece
 
 /* BIGI: index image sized for ~40 indices per piece (uint32 output of fat pieces); otherwise half of
  * that for uint32, so that thin meshes keep 9 blocks per SM.  uint16 always uses the full count. */
+/* Resident blocks per SM: the (cap, join)-specialised AA-stroke kernels run best at 8 (64 registers, no
+ * spills; measured equal at 6-8, 2 % slower at 9), the general mixed-op kernel at 9 (it is the one that
+ * needs the extra warps to cover its longer dependent chains: tiger-like scene 1.29 vs 1.38 ms). */
 template<class IDX, uint32_t OPS, int JT, int CT, bool BIGI>
-__global__ void __launch_bounds__(128, VGB_EMIT_MIN_BLOCKS) k_group_emit(PieceArgs a)
+__global__ void __launch_bounds__(128, (OPS == OPS_STROKE_AA && JT < 3) ? VGB_EMIT_MIN_BLOCKS_SPEC : VGB_EMIT_MIN_BLOCKS) k_group_emit(PieceArgs a)
 {
 	constexpr uint32_t CIW = (sizeof(IDX) == 2 || BIGI) ? CIW_COUNT : CIW_COUNT / 2;
 	constexpr uint32_t KI = 16 / sizeof(IDX);
@@ -922,6 +913,18 @@ __global__ void __launch_bounds__(128, VGB_EMIT_MIN_BLOCKS) k_group_emit(PieceAr
 	}
 	const bool valid = g < a.numPieces;
 	const uint32_t j = valid ? a.pieceJob[g] : 0;
+#if VGB_EMIT_PREFETCH
+	/* the group base, the previous group's hand-over word and the mesh offsets are only needed after the
+	 * pieces are classified: start those loads now (into L1, no registers held) so that their latency
+	 * runs under the piece -> job record -> points chain instead of after it */
+	if (lane == 0) {
+		asm volatile("prefetch.global.L1 [%0];" ::"l"(a.blockBase + w));
+		if (w > 0) asm volatile("prefetch.global.L1 [%0];" ::"l"(a.blockTail + (w - 1)));
+	}
+	if (valid) {
+		asm volatile("prefetch.global.L1 [%0];" ::"l"(a.meshOff + j));
+	}
+#endif
 	JobCtx J;
 	Piece P;
 	P.kind = PK_NONE;
@@ -1659,9 +1662,14 @@ public:
 		dim3 grid((unsigned)((V + 255) / 256), rows < 65535u ? rows : 65535u);
 		k_replay_vertices<<<grid, 256, 0, st>>>(dPos.as<float2>(), dCol.as<uint32_t>(), V, dRXf.as<float>(), n, dInv, dRPos.as<float2>(), dRCol.as<uint32_t>());
 		if (I) {
-			const uint64_t threads = (I * n + 7) / 8;
-			if (idxBytes == 2) k_replay_indices<uint16_t><<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(dIdx.as<uint16_t>(), I, V, n, dRIdx.as<uint16_t>());
-			else k_replay_indices<uint32_t><<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(dIdx.as<uint32_t>(), I, V, n, dRIdx.as<uint32_t>());
+			const unsigned gy = rows < 65535u ? rows : 65535u;
+			if (idxBytes == 4) {
+				k_replay_indices<uint32_t, true><<<dim3((unsigned)((I + 255) / 256), gy), 256, 0, st>>>(dIdx.as<uint32_t>(), I, V, n, dRIdx.as<uint32_t>());
+			} else if (I % 2 == 0) {
+				k_replay_indices<uint32_t, false><<<dim3((unsigned)((I / 2 + 255) / 256), gy), 256, 0, st>>>(dIdx.as<uint32_t>(), I / 2, V, n, dRIdx.as<uint32_t>());
+			} else {
+				k_replay_indices<uint16_t, false><<<dim3((unsigned)((I + 255) / 256), gy), 256, 0, st>>>(dIdx.as<uint16_t>(), I, V, n, dRIdx.as<uint16_t>());
+			}
 		}
 		VGB_CUDA(cudaGetLastError());
 		return 0;
