@@ -19,6 +19,10 @@
 #include "vgb_math.h"
 #include "vgb.h"
 
+#ifndef VGB_FLAT_CONVERGE
+#define VGB_FLAT_CONVERGE 1
+#endif
+
 namespace vgb
 {
 /* number of floats each command consumes (POLYLINE: 1 + 2n, handled separately) */
@@ -97,7 +101,18 @@ struct SubPathWalker
 		float x1 = lx, y1 = ly, x2 = c1x, y2 = c1y, x3 = c2x, y3 = c2y, x4 = x, y4 = y;
 		const float tessTol = tol / (scale * scale);
 		const uint32_t S = stride;
+#if VGB_FLAT_CONVERGE
+		/* The lanes that enter together stay in the loop until all of them are done and meet at a vote once
+		 * per node: without it the two sides of the flat / split branch loop back on their own and the
+		 * flatness test itself runs twice per iteration with half the lanes each (ncu source page: 12 of 32
+		 * lanes at the loop head). */
+		const unsigned mask = __activemask();
+		bool done = false;
+#endif
 		for (;;) {
+#if VGB_FLAT_CONVERGE
+			if (!done) {
+#endif
 			const float dx = x4 - x1;
 			const float dy = y4 - y1;
 			const float d2 = fabsf((x2 - x4) * dy - (y2 - y4) * dx);
@@ -121,10 +136,14 @@ struct SubPathWalker
 				e[4 * S] = x34;  e[5 * S] = y34;
 				++sp;
 				x2 = x12; y2 = y12; x3 = x123; y3 = y123; x4 = x1234; y4 = y1234;
+			} else if (sp == 0) {
+				/* only reachable from a flat node: a non-flat root always has sp<10 */
+#if VGB_FLAT_CONVERGE
+				done = true;
+#else
+				break;
+#endif
 			} else {
-				if (sp == 0) {
-					break; /* only reachable from a flat node: a non-flat root always has sp<10 */
-				}
 				--sp;
 				const float* e = stk + (uint32_t)sp * 6u * S;
 				/* the popped sibling ends where the entry below it starts, or at the curve's end */
@@ -139,6 +158,12 @@ struct SubPathWalker
 				x2 = e[2 * S]; y2 = e[3 * S];
 				x3 = e[4 * S]; y3 = e[5 * S];
 			}
+#if VGB_FLAT_CONVERGE
+			}
+			if (__all_sync(mask, done)) {
+				break;
+			}
+#endif
 		}
 	}
 
