@@ -6,7 +6,8 @@
  * product path.  No reference source is copied here; this file only CALLS the reference API
  * (include/vg/path.h:19-38, include/vg/stroker.h:11-70) the way src/vg.cpp does
  * (ctxBeginPath 2969-2981, ctxStrokePathColor 3401-3492, ctxFillPathColor 3061-3179,
- * transformPath 4957-4975).
+ * transformPath 4957-4975).  The bx headers it is compiled against are this repo's shim (bx is neither
+ * vendored nor pinned by the reference): with respect to bx's math, "parity unpinned" (DESIGN.md section 2).
  */
 #include <vg/path.h>
 #include <vg/stroker.h>

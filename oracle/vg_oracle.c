@@ -24,7 +24,8 @@
  *
  * Numerics: bx is absent and unpinned, so transcendental functions come from
  * vg_renderer_b200/csrc/vgb_math.h (the same explicit fp32 routines the kernels and the _ref
- * build use).  Parity with bx's own approximations is therefore UNPINNED.
+ * build use).  With respect to bx's own approximations: "parity unpinned" (DESIGN.md section 2);
+ * with respect to the reference's sources compiled here (oracle/_ref): pinned.
  * Build with -ffp-contract=off (oracle/Makefile): every operation individually rounded.
  */
 #include "vg_oracle.h"
