@@ -237,7 +237,7 @@ static void pb_ellipse(PathBuf* p, float cx, float cy, float rx, float ry)
 {
 	const float avg = (rx + ry) * 0.5f;
 	const float da = vgb_acos((p->scale * avg) / ((p->scale * avg) + p->tol)) * 2.0f;
-	const uint32_t half = vgb_umax(2u, (uint32_t)vgb_ceil(VGB_PI / da));
+	const uint32_t half = vgb_umax(2u, vgb_f2u(vgb_ceil(VGB_PI / da)));
 	const uint32_t np = half * 2;
 	pb_move(p, cx + rx, cy);
 	const float dt = -VGB_PI2 / (float)np;
@@ -259,7 +259,7 @@ static void pb_rrect(PathBuf* p, float x, float y, float w, float h, float r)
 	}
 	r = r < mr ? r : mr;
 	const float da = vgb_acos((p->scale * r) / ((p->scale * r) + p->tol)) * 2.0f;
-	const uint32_t half = vgb_umax(2u, (uint32_t)vgb_ceil(VGB_PI / da));
+	const uint32_t half = vgb_umax(2u, vgb_f2u(vgb_ceil(VGB_PI / da)));
 	const uint32_t nq = (half >> 1) + 1;
 	const float dt = -VGB_PI_HALF / (float)(nq - 1);
 	const float cd = vgb_cos(dt), sd = vgb_sin(dt);
@@ -279,7 +279,7 @@ static void pb_rrect(PathBuf* p, float x, float y, float w, float h, float r)
 static void pb_corner(PathBuf* p, float cx, float cy, float r, float ca, float sa)
 {
 	const float hda = vgb_acos((p->scale * r) / ((p->scale * r) + p->tol));
-	const uint32_t half = vgb_umax(2u, (uint32_t)vgb_ceil(VGB_PI_HALF / hda));
+	const uint32_t half = vgb_umax(2u, vgb_f2u(vgb_ceil(VGB_PI_HALF / hda)));
 	const uint32_t nq = (half >> 1) + 1;
 	const float dt = -VGB_PI_HALF / (float)(nq - 1);
 	pb_spin(p, cx, cy, r, r, ca, sa, vgb_cos(dt), vgb_sin(dt), nq - 1);
@@ -338,7 +338,7 @@ static void pb_arc(PathBuf* p, float cx, float cy, float r, float a0, float a1, 
 		while (a1 < a0) a1 += VGB_PI2;
 	}
 	const float da = vgb_acos((p->scale * r) / ((p->scale * r) + p->tol)) * 2.0f;
-	const uint32_t np = vgb_umax(2u, (uint32_t)vgb_ceil(vgb_abs(a1 - a0) / da));
+	const uint32_t np = vgb_umax(2u, vgb_f2u(vgb_ceil(vgb_abs(a1 - a0) / da)));
 	const float dt = (a1 - a0) / (float)np;
 	const float ca = vgb_cos(a0), sa = vgb_sin(a0);
 	if (p->cur >= 0 && p->sp[p->cur].num_vertices != 0) {
@@ -483,7 +483,7 @@ static void stroke_aa(MeshBuf* m, const StrokerCfg* cfg, const v2* vtx, uint32_t
 	const float hsw = (width - fr) * 0.5f;
 	const float haa = hsw + fr;
 	const float da = vgb_acos((cfg->scale * hsw) / ((cfg->scale * hsw) + cfg->tol)) * 2.0f;
-	const uint32_t nhc = vgb_umax(2u, (uint32_t)vgb_ceil(VGB_PI / da));
+	const uint32_t nhc = vgb_umax(2u, vgb_f2u(vgb_ceil(VGB_PI / da)));
 	Cross prev, first;
 	int havePrev = 0, haveFirst = 0;
 	v2 d01;
@@ -559,10 +559,10 @@ static void stroke_aa(MeshBuf* m, const StrokerCfg* cfg, const v2* vtx, uint32_t
 				float a12 = vgb_atan2(s12.y, s12.x);
 				if (left) {
 					if (a12 < a01) a12 += VGB_PI2;
-					na = vgb_umax(2u, (uint32_t)((a12 - a01) / da));
+					na = vgb_umax(2u, vgb_f2u((a12 - a01) / da));
 				} else {
 					if (a12 > a01) a12 -= VGB_PI2;
-					na = vgb_umax(2u, (uint32_t)((a01 - a12) / da));
+					na = vgb_umax(2u, vgb_f2u((a01 - a12) / da));
 				}
 				step = (a12 - a01) / (float)na;
 			}
@@ -673,7 +673,7 @@ static void stroke_plain(MeshBuf* m, const StrokerCfg* cfg, const v2* vtx, uint3
 {
 	const float hsw = width * 0.5f;
 	const float da = vgb_acos((cfg->scale * hsw) / ((cfg->scale * hsw) + cfg->tol)) * 2.0f;
-	const uint32_t nhc = vgb_umax(2u, (uint32_t)vgb_ceil(VGB_PI / da));
+	const uint32_t nhc = vgb_umax(2u, vgb_f2u(vgb_ceil(VGB_PI / da)));
 	Cross prev, first;
 	int havePrev = 0, haveFirst = 0;
 	v2 d01;
@@ -732,10 +732,10 @@ static void stroke_plain(MeshBuf* m, const StrokerCfg* cfg, const v2* vtx, uint3
 				float a12 = vgb_atan2(s12.y, s12.x);
 				if (left) {
 					if (a12 < a01) a12 += VGB_PI2;
-					na = vgb_umax(2u, (uint32_t)((a12 - a01) / da));
+					na = vgb_umax(2u, vgb_f2u((a12 - a01) / da));
 				} else {
 					if (a12 > a01) a12 -= VGB_PI2;
-					na = vgb_umax(2u, (uint32_t)((a01 - a12) / da));
+					na = vgb_umax(2u, vgb_f2u((a01 - a12) / da));
 				}
 				step = (a12 - a01) / (float)na;
 			}

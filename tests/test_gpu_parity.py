@@ -576,3 +576,17 @@ def test_rerun_large_batch_with_empty_meshes(gpu_batch, ref):
     gpu_batch.run()
     check_same(gpu_batch.download(), exp)
     assert int(np.sum(np.diff(exp["mesh_vtx_off"]) == 0)) >= 10
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3, 4, 5, 6])
+def test_fuzz_random_paths_and_draws(gpu_batch, ref, seed):
+    """random polylines with duplicates / near-duplicates / collinear runs / hairpins, curves, shapes, arcs,
+    multi-sub-path paths x random ops, caps, joins, widths, scales, tolerances, transforms, fringes"""
+    from cases import fuzz_recorder
+    r = fuzz_recorder(seed, num_paths=160)
+    exp = ref.run_batch(r.tables())
+    r.replay(gpu_batch)
+    gpu_batch.run()
+    check_same(gpu_batch.download(), exp)
+    gpu_batch.run()  # re-run of the same upload
+    check_same(gpu_batch.download(), exp)

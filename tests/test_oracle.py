@@ -253,3 +253,31 @@ def test_transform_positions_restatement_vs_reference(orc):
         np.testing.assert_array_equal(ref.transform_positions(pos, m), orc.transform_positions(pos, m))
     ident = np.asarray([1, 0, 0, 1, 0, 0], np.float32)
     np.testing.assert_array_equal(orc.transform_positions(pos, ident), pos)
+
+
+@needs_ref
+@pytest.mark.parametrize("seed", [1, 2, 3, 4])
+def test_fuzz_restatement_vs_compiled_reference(orc, seed):
+    from cases import fuzz_recorder
+    t = fuzz_recorder(seed).tables()
+    a, b = RefLib("scalar").run_batch(t), orc.run_batch(t)
+    assert a["num_vertices"] > 20000
+    for k in ("mesh_vtx_off", "mesh_idx_off", "index", "color", "pos"):
+        np.testing.assert_array_equal(a[k], b[k], err_msg=k)
+
+
+@needs_ref
+def test_degenerate_width_below_fringe_counts(orc):
+    """AA stroke narrower than the fringe (vg.cpp never issues it, the per-object API can): hsw <= 0 drives
+    acos out of range, da becomes 0 or 2*pi and pi/da infinite.  `(uint32_t)inf` is undefined in C; the
+    reference's x86-64 build yields 0 (-> 2 cap points), a GPU conversion would saturate to 2^32-1.  All
+    float -> count conversions go through vgb_f2u (x86 semantics) on both sides: same meshes."""
+    ref = RefLib("scalar")
+    pts = [[0, 0], [40, 5], [60, 50], [10, 70], [5, 30]]
+    for scale, tol, fringe, width in ((2.0, 0.25, 2.0, 1.5), (1.0, 0.25, 2.0, 1.5), (1.0, 0.25, 2.0, 2.0), (3.7, 0.1, 2.0, 1.5), (1.0, 1.0, 0.5, 0.25)):
+        for cap, join, closed in itertools.product((0, 1, 2), (0, 1, 2), (False, True)):
+            a = ref.mesh(0, pts, closed, 0xFF204060, width, cap, join, scale, tol, fringe)
+            b = orc.mesh(0, pts, closed, 0xFF204060, width, cap, join, scale, tol, fringe)
+            assert len(a[0]) < 400
+            np.testing.assert_array_equal(a[0], b[0])
+            np.testing.assert_array_equal(a[2], b[2])

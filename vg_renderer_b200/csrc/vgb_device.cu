@@ -375,7 +375,7 @@ __global__ void k_draw_prep(const DrawRec* __restrict__ draws, uint32_t n, const
 		o.hsw = (r.width - fringe) * 0.5f;
 		o.hsw_aa = o.hsw + fringe;
 		o.da = vgb_acos((scale * o.hsw) / ((scale * o.hsw) + tol)) * 2.0f;
-		o.nHC = vgb_umax(2u, (uint32_t)vgb_ceil(VGB_PI / o.da));
+		o.nHC = vgb_umax(2u, vgb_f2u(vgb_ceil(VGB_PI / o.da)));
 		if (3.0f * o.da > VGB_PI + 1e-3f) {
 			o.ocj |= 1u << 24; /* nfix: see quickCountAA */
 		}
@@ -384,7 +384,7 @@ __global__ void k_draw_prep(const DrawRec* __restrict__ draws, uint32_t n, const
 		o.hsw = r.width * 0.5f;
 		o.hsw_aa = o.hsw;
 		o.da = vgb_acos((scale * o.hsw) / ((scale * o.hsw) + tol)) * 2.0f;
-		o.nHC = vgb_umax(2u, (uint32_t)vgb_ceil(VGB_PI / o.da));
+		o.nHC = vgb_umax(2u, vgb_f2u(vgb_ceil(VGB_PI / o.da)));
 	} else if (op == VGB_OP_STROKE_AA_THIN) {
 		/* stroker.cpp:1999 (half width = fringe) and the dispatch of 311-332: round cap -> square,
 		 * round join -> bevel */

@@ -215,7 +215,7 @@ struct SubPathWalker
 	{
 		const float avgR = (rx + ry) * 0.5f;
 		const float da = vgb_acos((scale * avgR) / ((scale * avgR) + tol)) * 2.0f;
-		const uint32_t nHalf = vgb_umax(2u, (uint32_t)vgb_ceil(VGB_PI / da));
+		const uint32_t nHalf = vgb_umax(2u, vgb_f2u(vgb_ceil(VGB_PI / da)));
 		const uint32_t numPoints = nHalf * 2;
 		add(cx + rx, cy);
 		const float dtheta = -VGB_PI2 / (float)numPoints;
@@ -246,7 +246,7 @@ struct SubPathWalker
 		}
 		r = fminf(r, max_r);
 		const float da = vgb_acos((scale * r) / ((scale * r) + tol)) * 2.0f;
-		const uint32_t nHalf = vgb_umax(2u, (uint32_t)vgb_ceil(VGB_PI / da));
+		const uint32_t nHalf = vgb_umax(2u, vgb_f2u(vgb_ceil(VGB_PI / da)));
 		const uint32_t nQ = (nHalf >> 1) + 1;
 		const float dtheta = -VGB_PI_HALF / (float)(nQ - 1);
 		const float cosd = vgb_cos(dtheta);
@@ -267,7 +267,7 @@ struct SubPathWalker
 	__device__ __forceinline__ void varyingCorner(float cx, float cy, float r, float ca, float sa)
 	{
 		const float halfDa = vgb_acos((scale * r) / ((scale * r) + tol));
-		const uint32_t nHalf = vgb_umax(2u, (uint32_t)vgb_ceil(VGB_PI_HALF / halfDa));
+		const uint32_t nHalf = vgb_umax(2u, vgb_f2u(vgb_ceil(VGB_PI_HALF / halfDa)));
 		const uint32_t nQ = (nHalf >> 1) + 1;
 		const float dtheta = -VGB_PI_HALF / (float)(nQ - 1);
 		quarter(cx, cy, r, ca, sa, vgb_cos(dtheta), vgb_sin(dtheta), nQ);
@@ -324,7 +324,7 @@ struct SubPathWalker
 			while (a1 < a0) a1 += VGB_PI2;
 		}
 		const float da = vgb_acos((scale * r) / ((scale * r) + tol)) * 2.0f;
-		const uint32_t numPoints = vgb_umax(2u, (uint32_t)vgb_ceil(fabsf(a1 - a0) / da));
+		const uint32_t numPoints = vgb_umax(2u, vgb_f2u(vgb_ceil(fabsf(a1 - a0) / da)));
 		const float dtheta = (a1 - a0) / (float)numPoints;
 		const float cosd = vgb_cos(dtheta);
 		const float sind = vgb_sin(dtheta);

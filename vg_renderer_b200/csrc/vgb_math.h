@@ -61,6 +61,20 @@ VGB_HD float vgb_ceil(float a) { return ceilf(a); }
 VGB_HD float vgb_floor(float a) { return floorf(a); }
 VGB_HD uint32_t vgb_umax(uint32_t a, uint32_t b) { return a > b ? a : b; }
 
+/* float -> uint32 as the reference's `(uint32_t)x` behaves in its x86-64 build (cvttss2si to a 64-bit
+ * register, low half kept): truncation for |x| < 2^63, and 0 for NaN, infinities and anything larger (the
+ * "integer indefinite" 0x8000000000000000).  Out-of-range conversions are undefined in C and SATURATE on
+ * the GPU (inf -> 0xFFFFFFFF), so a degenerate stroke (width below the fringe: da = 0, pi/da = inf) would
+ * otherwise get 2 cap points on the CPU and 4 billion on the device.  Every float -> count conversion of
+ * the path goes through here, on both sides. */
+VGB_HD uint32_t vgb_f2u(float x)
+{
+	if (!(fabsf(x) < 9.2233720368547758e18f)) {
+		return 0u;
+	}
+	return (uint32_t)(unsigned long long)(long long)x;
+}
+
 /* ---- sin / cos ---------------------------------------------------------------------
  * Polynomials are Horner chains of explicit fused multiply-adds: each step is ONE IEEE-754
  * fma, so the value is a pure function of the inputs on any conforming machine. */

@@ -114,12 +114,12 @@ __device__ __forceinline__ void classifyJoinAA(const JobCtx& J, Piece& P, bool c
 				if (a12 < a01) {
 					a12 += VGB_PI2;
 				}
-				n = vgb_umax(2u, (uint32_t)((a12 - a01) / J.da));
+				n = vgb_umax(2u, vgb_f2u((a12 - a01) / J.da));
 			} else {
 				if (a12 > a01) {
 					a12 -= VGB_PI2;
 				}
-				n = vgb_umax(2u, (uint32_t)((a01 - a12) / J.da));
+				n = vgb_umax(2u, vgb_f2u((a01 - a12) / J.da));
 			}
 			P.a01 = a01;
 			P.arcDa = (a12 - a01) / (float)n;
@@ -190,10 +190,10 @@ __device__ __forceinline__ void classifyRibbon(const JobCtx& J, uint32_t q, cons
 			float a12 = vgb_atan2(s12.y, s12.x);
 			if (left) {
 				if (a12 < a01) a12 += VGB_PI2;
-				n = vgb_umax(2u, (uint32_t)((a12 - a01) / J.da));
+				n = vgb_umax(2u, vgb_f2u((a12 - a01) / J.da));
 			} else {
 				if (a12 > a01) a12 -= VGB_PI2;
-				n = vgb_umax(2u, (uint32_t)((a01 - a12) / J.da));
+				n = vgb_umax(2u, vgb_f2u((a01 - a12) / J.da));
 			}
 			P.a01 = a01;
 			P.arcDa = (a12 - a01) / (float)n;
