@@ -176,6 +176,8 @@ VGB_API int vgb_batch_rounded_rect(vgb_batch* b, float x, float y, float w, floa
 VGB_API int vgb_batch_rounded_rect_varying(vgb_batch* b, float x, float y, float w, float h, float rtl, float rtr, float rbr, float rbl);
 VGB_API int vgb_batch_circle(vgb_batch* b, float x, float y, float r);
 VGB_API int vgb_batch_ellipse(vgb_batch* b, float x, float y, float rx, float ry);
+/* |a0|, |a1| <= 1e6 rad (VGB_ERR_INVALID beyond: pathArc's angle normalisation, path.cpp:635-645, stops
+ * making progress once 2*pi falls below the float spacing, i.e. the reference never returns) */
 VGB_API int vgb_batch_arc(vgb_batch* b, float x, float y, float r, float a0, float a1, uint32_t dir);
 VGB_API int vgb_batch_polyline(vgb_batch* b, const float* coords, uint32_t num_points);
 VGB_API int vgb_batch_close(vgb_batch* b);

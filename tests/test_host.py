@@ -96,6 +96,12 @@ def test_invalid_input_is_rejected():
     c = vgb.Batch(-1)
     with pytest.raises(vgb.VgbError):
         c.move_to(0, 0)  # outside begin_path
+    c.begin_path().move_to(0, 0)
+    for a0, a1 in ((1e9, 1.0), (0.5, -3e7)):
+        with pytest.raises(vgb.VgbError) as e:
+            c.arc(10, 10, 5, a0, a1, True)  # pathArc's `while (a > 2pi) a -= 2pi` never ends for such floats (path.cpp:635-645)
+        assert e.value.code == -1
+    c.arc(10, 10, 5, 1000.0, -999.0, False)  # large but harmless
 
 
 def test_arc_subpath_rule_and_polyline():

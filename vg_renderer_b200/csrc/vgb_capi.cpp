@@ -282,6 +282,10 @@ int vgb_batch_ellipse(vgb_batch* b, float x, float y, float rx, float ry)
 }
 int vgb_batch_arc(vgb_batch* b, float x, float y, float r, float a0, float a1, uint32_t dir)
 {
+	/* pathArc normalises its angles with `while (a > 2pi) a -= 2pi` (path.cpp:635-645): beyond ~1e8 the
+	 * subtraction no longer changes a float and the reference never returns; a device thread would spin
+	 * the same way.  Angles that large are refused at record time like non-finite coordinates are. */
+	if (b && (fabsf(a0) > 1.0e6f || fabsf(a1) > 1.0e6f)) return fail(VGB_ERR_INVALID, "arc angle magnitude above 1e6 rad");
 	const float d[6] = {x, y, r, a0, a1, dir == VGB_WINDING_CW ? 1.0f : 0.0f};
 	/* pathArc: lineTo when the path has a current sub-path, moveTo otherwise (path.cpp:663-667) */
 	return b->push(VGB_CMD_ARC, d, 6, !b->subOpen);
