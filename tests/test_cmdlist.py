@@ -109,3 +109,85 @@ def test_decoded_list_meshes_match_reference(sincos, gpu_batch, ref):
     out = gpu_batch.download()
     for k in ("mesh_vtx_off", "mesh_idx_off", "index", "color", "pos"):
         np.testing.assert_array_equal(out[k], exp[k], err_msg=k)
+
+
+def _random_list(seed, n_ops=400):
+    """random but well-formed command stream: every path command sits inside a BeginPath, pops never underflow"""
+    rng = np.random.default_rng(seed)
+    w = CL.Writer()
+    depth, in_path, has_pt, drawn = 0, False, False, False
+    for _ in range(n_ops):
+        u = rng.random()
+        if u < 0.12 or not in_path or (drawn and u < 0.52):  # geometry after a draw needs a new path (VG_CHECK, vg.cpp:2986)
+            w.begin_path()
+            in_path, has_pt, drawn = True, False, False
+        elif u < 0.45:
+            k = int(rng.integers(0, 9))
+            f = lambda lo=-200, hi=400: float(np.float32(rng.uniform(lo, hi)))
+            if k == 0 or not has_pt:
+                w.move_to(f(), f())
+            elif k == 1:
+                w.line_to(f(), f())
+            elif k == 2:
+                w.cubic_to(f(), f(), f(), f(), f(), f())
+            elif k == 3:
+                w.quadratic_to(f(), f(), f(), f())
+            elif k == 4:
+                w.arc_to(f(), f(), f(), f(), f(1, 40))
+            elif k == 5:
+                w.arc(f(), f(), f(2, 90), f(0, 6), f(0, 6), bool(rng.integers(0, 2)))
+            elif k == 6:
+                w.polyline(rng.uniform(0, 300, 2 * int(rng.integers(1, 6))))
+            elif k == 7:
+                w.close_path()
+            else:
+                w.line_to(f(), f())
+            has_pt = True
+        elif u < 0.52:
+            k = int(rng.integers(0, 5))
+            f = lambda lo=0, hi=300: float(np.float32(rng.uniform(lo, hi)))
+            [lambda: w.rect(f(), f(), f(1, 200), f(1, 200)), lambda: w.rounded_rect(f(), f(), f(5, 200), f(5, 200), f(0, 40)),
+             lambda: w.circle(f(), f(), f(1, 90)), lambda: w.ellipse(f(), f(), f(1, 90), f(1, 90)),
+             lambda: w.rounded_rect_varying(f(), f(), f(20, 200), f(20, 200), f(0, 30), f(0, 30), f(0, 30), f(0, 30))][k]()
+            has_pt = True
+        elif u < 0.66:
+            drawn = True
+            w.stroke(int(rng.integers(0, 1 << 32)), float(np.float32(rng.choice([0.1, 0.5, 1.0, 2.5, 8.0, 300.0]))),
+                     CL.stroke_flags(int(rng.integers(0, 3)), int(rng.integers(0, 3)), bool(rng.integers(0, 2)), bool(rng.random() < 0.2)))
+        elif u < 0.74:
+            drawn = True
+            w.fill(int(rng.integers(0, 1 << 32)), CL.fill_flags(concave=bool(rng.random() < 0.15), aa=bool(rng.integers(0, 2))))
+        elif u < 0.80:
+            if depth < 20:
+                w.push_state()
+                depth += 1
+        elif u < 0.85:
+            if depth > 0:
+                w.pop_state()
+                depth -= 1
+        elif u < 0.97:
+            k = int(rng.integers(0, 8))
+            f = lambda lo, hi: float(np.float32(rng.uniform(lo, hi)))
+            [lambda: w.translate(f(-50, 50), f(-50, 50)), lambda: w.scale(f(0.3, 2.5), f(0.3, 2.5)), lambda: w.rotate(f(-7, 7)),
+             lambda: w.mult([f(-1.5, 1.5) for _ in range(4)] + [f(-30, 30), f(-30, 30)], bool(rng.integers(0, 2))),
+             lambda: w.global_alpha(f(0, 1)), lambda: w.set_scissor(f(-100, 600), f(-100, 400), f(0, 3), f(0, 300)),
+             lambda: w.intersect_scissor(f(-100, 600), f(-100, 400), f(0, 500), f(0, 300)), lambda: w.reset_scissor()][k]()
+        else:
+            w.identity() if rng.random() < 0.5 else w.set_view_box(0, 0, float(np.float32(rng.uniform(100, 2000))), float(np.float32(rng.uniform(100, 2000))))
+    return w
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_random_lists_equal_model_recording(sincos, seed):
+    w = _random_list(seed)
+    cull = bool(seed % 2)
+    model = CL.Model(sincos, fringe=1.0, cull=cull).run(w.ops)
+    expect = vgb.Batch(-1)
+    model.rec.replay(expect)
+    got = vgb.Batch(-1)
+    ctx = vgb.make_cl_context(flags=2 if cull else 0)
+    st = got.submit_command_list(w.bytes(), ctx)
+    recorded_equal(got.recorded_streams(), expect.recorded_streams())
+    for k, v in model.stats.items():
+        assert getattr(st, k) == v, k
+    assert st.state_depth == len(model.stack) - 1
