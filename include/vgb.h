@@ -237,7 +237,8 @@ VGB_API float vgb_batch_fringe(vgb_batch* b);
  * (vg.cpp:177-247) -- and records it into the batch the way ctxSubmitCommandList executes it
  * (vg.cpp:4273-4637): path commands, FillPathColor (convex), StrokePathColor, the state stack,
  * transforms, global alpha and scissor culling.  Paints, concave fills, text, clip regions,
- * tri-lists and nested lists are skipped and counted in stats->unsupported.  The batch's fringe
+ * and tri-lists are skipped and counted in stats->unsupported; nested lists are executed when the caller
+ * provides the context's list table (vgb_cl_context::lists).  The batch's fringe
  * (vgb_batch_reset) is Context::m_FringeWidth. */
 typedef struct vgb_cl_context {
 	float xform[6];       /* in: State::m_TransformMtx on entry; out: on exit (the list's state changes persist, vg.h:34-35) */
@@ -245,8 +246,21 @@ typedef struct vgb_cl_context {
 	float global_alpha;   /* in/out: State::m_GlobalAlpha                                             */
 	float tess_tolerance; /* Context::m_TesselationTolerance                                          */
 	float canvas_width, canvas_height;
-	uint32_t flags;       /* CommandListFlags: 2 = AllowCommandCulling (vg.h:380-388)                 */
+	uint32_t flags;       /* CommandListFlags of THIS list: 2 = AllowCommandCulling (vg.h:380-388)   */
+	/* nested lists (SubmitCommandList, vg.cpp:4620-4626): the context's command lists by handle index;
+	 * a handle outside the table (or an entry with commands == NULL) is an invalid handle and is skipped
+	 * as the reference skips it; max_depth = ContextConfig::m_MaxCommandListDepth (0 = the default 16) */
+	uint32_t num_lists;
+	const struct vgb_cl_list* lists;
+	uint32_t max_depth;
+	uint32_t reserved;
 } vgb_cl_context;
+
+typedef struct vgb_cl_list {
+	const void* commands; /* CommandList::m_CommandBuffer    */
+	uint32_t size;        /* CommandList::m_CommandBufferPos */
+	uint32_t flags;       /* CommandList::m_Flags            */
+} vgb_cl_list;
 
 typedef struct vgb_cl_stats {
 	uint32_t commands;    /* records decoded                                         */
@@ -256,7 +270,7 @@ typedef struct vgb_cl_stats {
 	uint32_t zero_alpha;  /* draws dropped because their colour ends up transparent  */
 	uint32_t unsupported; /* commands outside this path (see above)                  */
 	uint32_t state_depth; /* states left pushed when the list ended                  */
-	uint32_t reserved;
+	uint32_t nested;      /* SubmitCommandList commands executed                     */
 } vgb_cl_stats;
 
 VGB_API int vgb_batch_submit_command_list(vgb_batch* b, const void* commands, uint32_t size, vgb_cl_context* ctx, vgb_cl_stats* stats);

@@ -97,6 +97,11 @@ class Writer:
         self._cmd(T_MULT, struct.pack("<6fI", *m, int(post)))
         return self
 
+    def submit(self, list_id):  # clSubmitCommandList, vg.cpp:2959-2966
+        self.ops.append((SUBMIT_LIST, (int(list_id),)))
+        self._cmd(SUBMIT_LIST, struct.pack("<H", list_id))
+        return self
+
     def bytes(self):
         return bytes(self.buf)
 
@@ -109,13 +114,15 @@ class Model:
     """float32 restatement of what the reference's executor does with the ops of a Writer."""
 
     def __init__(self, sincos, xform=(1, 0, 0, 1, 0, 0), global_alpha=1.0, tol=0.25, fringe=1.0, canvas=(1280.0, 720.0), scissor=None,
-                 cull=False):
+                 cull=False, lists=None, max_depth=16):
+        self.lists = lists or {}  # handle index -> (ops, flags): the lists a SubmitCommandList may name
+        self.depth, self.max_depth = 0, max_depth
         self.sincos = sincos  # a -> (sin a, cos a) with the build's shared math
         self.rec = Recorder(fringe=fringe)
         self.fringe, self.tol, self.canvas, self.cull = F(fringe), tol, (F(canvas[0]), F(canvas[1])), cull
         sc = scissor if scissor is not None else (0.0, 0.0, canvas[0], canvas[1])
         self.stack = [dict(m=[F(v) for v in xform], alpha=F(global_alpha), sc=[F(v) for v in sc])]
-        self.stats = dict(draws=0, culled=0, zero_alpha=0, unsupported=0, paths=0)
+        self.stats = dict(draws=0, culled=0, zero_alpha=0, unsupported=0, paths=0, nested=0)
         self.skip = False
         self.drawn = False
         self.path = None
@@ -136,7 +143,19 @@ class Model:
             self.path["xform"] = [float(v) for v in self.s["m"]]
             self.drawn = True
 
-    def run(self, ops):
+    def run(self, ops, cull=None):
+        """one execution of one list (vg.cpp:4273-4637); skipCmds and the culling flag are per execution"""
+        if self.depth >= self.max_depth:
+            return self
+        self.depth += 1
+        outer = (self.skip, self.cull)
+        self.skip, self.cull = False, (self.cull if cull is None else cull)
+        self._run(ops)
+        self.skip, self.cull = outer
+        self.depth -= 1
+        return self
+
+    def _run(self, ops):
         r = self.rec
         for t, v in ops:
             if self.skip and FILL_COLOR <= t <= STROKE_IMAGE:
@@ -198,8 +217,15 @@ class Model:
                 self.stats["unsupported"] += 1
             elif t == END_CLIP:
                 self.in_clip = False
+            elif t == SUBMIT_LIST:
+                if not self.lists:
+                    self.stats["unsupported"] += 1
+                elif v[0] in self.lists:
+                    self.stats["nested"] += 1
+                    child_ops, child_flags = self.lists[v[0]]
+                    self.run(child_ops, cull=bool(child_flags & 2))
             elif t in (FILL_GRADIENT, FILL_IMAGE, STROKE_GRADIENT, STROKE_IMAGE, TRI_LIST, LINEAR_GRADIENT, BOX_GRADIENT, RADIAL_GRADIENT,
-                       IMAGE_PATTERN, TEXT, TEXT_BOX, SUBMIT_LIST, RESET_CLIP):
+                       IMAGE_PATTERN, TEXT, TEXT_BOX, RESET_CLIP):
                 self.stats["unsupported"] += 1
             elif t == PUSH_STATE:
                 self.stack.append(dict(m=list(self.s["m"]), alpha=self.s["alpha"], sc=list(self.s["sc"])))

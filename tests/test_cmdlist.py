@@ -191,3 +191,35 @@ def test_random_lists_equal_model_recording(sincos, seed):
     for k, v in model.stats.items():
         assert getattr(st, k) == v, k
     assert st.state_depth == len(model.stack) - 1
+
+
+def test_nested_lists(sincos):
+    icon = CL.Writer().push_state().scale(0.5, 0.5).begin_path().rounded_rect(0, 0, 40, 40, 6).fill(0xFF336699, CL.fill_flags())
+    icon.stroke(0xFF000000, 2.0, CL.stroke_flags(1, 1, True)).pop_state().translate(50, 0)  # leaves a translation behind
+    row = CL.Writer().submit(3).submit(3).submit(9).rotate(0.2).submit(3)  # 9: not a list of the context -> skipped
+    deep = CL.Writer().translate(1, 1).begin_path().circle(0, 0, 3).fill(0xFFFFFFFF, CL.fill_flags(aa=False)).submit(7)  # submits itself
+    culled = CL.Writer().set_scissor(0, 0, 0.2, 0.2).begin_path().rect(0, 0, 5, 5).fill(0xFF00FF00, CL.fill_flags())  # AllowCommandCulling
+    lists = {3: (icon, 0), 5: (row, 0), 7: (deep, 0), 8: (culled, 2)}
+    top = CL.Writer().translate(10, 20).submit(5).push_state().scale(2, 2).submit(5).pop_state().submit(7).submit(8)
+    top.begin_path().rect(1, 1, 9, 9).fill(0xFFABCDEF, CL.fill_flags())  # drawn: the culling of list 8 ended with it
+
+    model = CL.Model(sincos, lists={k: (w.ops, fl) for k, (w, fl) in lists.items()}).run(top.ops)
+    expect = vgb.Batch(-1)
+    model.rec.replay(expect)
+    got = vgb.Batch(-1)
+    ctx = vgb.make_cl_context(lists={k: (w.bytes(), fl) for k, (w, fl) in lists.items()})
+    st = got.submit_command_list(top.bytes(), ctx)
+    recorded_equal(got.recorded_streams(), expect.recorded_streams())
+    for k, v in model.stats.items():
+        assert getattr(st, k) == v, k
+    assert st.nested == 2 + 6 + 16 + 1  # top: 5, 5 | each row: 3 x list 3 | 7 from the top + its 15 executions each submitting itself | 8
+    assert st.culled == 1 and st.draws == 2 * 6 + 15 + 1
+    np.testing.assert_array_equal(np.asarray(list(ctx.xform), np.float32), np.asarray(model.s["m"], np.float32))
+    # without a list table nesting is reported as unsupported, nothing else changes
+    plain = vgb.Batch(-1)
+    st2 = plain.submit_command_list(top.bytes(), vgb.make_cl_context())
+    assert st2.unsupported == 4 and st2.nested == 0 and st2.draws == 1
+    # a depth limit of 1 executes the top list only
+    lim = vgb.Batch(-1)
+    st3 = lim.submit_command_list(top.bytes(), vgb.make_cl_context(lists={k: (w.bytes(), fl) for k, (w, fl) in lists.items()}, max_depth=1))
+    assert st3.draws == 1 and st3.nested == 4

@@ -65,19 +65,39 @@ def make_final_cfg(max_vb_vertices=65536, vb_id=0, vb_count=0, cmd_vertices=0, i
     return c
 
 
+class ClList(C.Structure):
+    """vgb_cl_list: one of the context's command lists (for SubmitCommandList)"""
+    _fields_ = [("commands", C.c_void_p), ("size", C.c_uint32), ("flags", C.c_uint32)]
+
+
 class ClContext(C.Structure):
     """vgb_cl_context"""
     _fields_ = [("xform", C.c_float * 6), ("scissor", C.c_float * 4), ("global_alpha", C.c_float), ("tess_tolerance", C.c_float),
-                ("canvas_width", C.c_float), ("canvas_height", C.c_float), ("flags", C.c_uint32)]
+                ("canvas_width", C.c_float), ("canvas_height", C.c_float), ("flags", C.c_uint32), ("num_lists", C.c_uint32),
+                ("lists", C.POINTER(ClList)), ("max_depth", C.c_uint32), ("reserved", C.c_uint32)]
 
 
 class ClStats(C.Structure):
     """vgb_cl_stats"""
-    _fields_ = [(k, C.c_uint32) for k in ("commands", "paths", "draws", "culled", "zero_alpha", "unsupported", "state_depth", "reserved")]
+    _fields_ = [(k, C.c_uint32) for k in ("commands", "paths", "draws", "culled", "zero_alpha", "unsupported", "state_depth", "nested")]
 
 
-def make_cl_context(xform=(1, 0, 0, 1, 0, 0), global_alpha=1.0, tess_tolerance=0.25, canvas=(1280.0, 720.0), scissor=None, flags=0):
+def make_cl_context(xform=(1, 0, 0, 1, 0, 0), global_alpha=1.0, tess_tolerance=0.25, canvas=(1280.0, 720.0), scissor=None, flags=0,
+                    lists=None, max_depth=0):
+    """lists: {handle index: (bytes, flags)} -- the context's command lists a SubmitCommandList may name"""
     c = ClContext()
+    if lists:
+        n = max(lists) + 1
+        arr = (ClList * n)()
+        keep = []
+        for i, (buf, fl) in lists.items():
+            a = np.frombuffer(bytes(buf), np.uint8)
+            keep.append(a)
+            arr[i].commands = a.ctypes.data if len(a) else None
+            arr[i].size, arr[i].flags = len(a), fl
+        c.num_lists, c.lists = n, arr
+        c._keep = (arr, keep)  # the C struct only borrows the buffers
+    c.max_depth = max_depth
     for i, v in enumerate(xform):
         c.xform[i] = v
     sc = scissor if scissor is not None else (0.0, 0.0, canvas[0], canvas[1])

@@ -13,8 +13,9 @@
  *   StrokePathColor                     -> vgb_batch_stroke            (vg.cpp:3401-3492)
  *   Push/PopState, Transform*, SetViewBox, SetGlobalAlpha, *Scissor (culling only)
  *                                                                      (vg.cpp:3934-4127, 4927-4944)
- * Gradient / image-pattern paints, concave fills, text, clip regions, indexed tri-lists and nested
- * command lists are outside SURVEY 8's scope: they are skipped and counted in vgb_cl_stats.unsupported.
+ *   SubmitCommandList                   -> the named list, in place (vg.cpp:4620-4626, depth limit 4278-4281)
+ * Gradient / image-pattern paints, concave fills, text, clip regions and indexed tri-lists are outside
+ * SURVEY 8's scope: they are skipped and counted in vgb_cl_stats.unsupported.
  * Host code only; floats follow the reference's expression order (built with -ffp-contract=off).
  */
 #include "vgb.h"
@@ -76,21 +77,32 @@ int fail(int code, const char* msg)
 }
 } // namespace
 
-extern "C" int vgb_batch_submit_command_list(vgb_batch* b, const void* buffer, uint32_t size, vgb_cl_context* ctx, vgb_cl_stats* stats)
+namespace
 {
-	if (!b || !ctx || (!buffer && size)) return fail(VGB_ERR_INVALID, "null argument");
-	if (size % kAlign) return fail(VGB_ERR_INVALID, "command buffer size is not a multiple of 16");
+struct Run /* what one top-level submit shares with the lists it nests */
+{
+	vgb_batch* b;
+	vgb_cl_context* ctx;
 	vgb_cl_stats st;
-	memset(&st, 0, sizeof(st));
-	std::vector<State> stack(1);
-	memcpy(stack[0].mtx, ctx->xform, sizeof(float) * 6);
-	memcpy(stack[0].scissor, ctx->scissor, sizeof(float) * 4);
-	stack[0].globalAlpha = ctx->global_alpha;
-	updateState(&stack[0]);
-	const bool cullCmds = (ctx->flags & 2u) != 0; /* CommandListFlags::AllowCommandCulling, vg.cpp:4307 */
-	const float fringe = vgb_batch_fringe(b);
-	bool skipCmds = false;
-	bool inClip = false;
+	std::vector<State> stack;
+	float fringe;
+	bool inClip;
+	uint32_t depth, maxDepth;
+};
+
+int runList(Run& R, const void* buffer, uint32_t size, uint32_t listFlags)
+{
+	if (size % kAlign) return fail(VGB_ERR_INVALID, "command buffer size is not a multiple of 16");
+	if (R.depth >= R.maxDepth) return 0; /* vg.cpp:4278-4281: recursion limit reached, the list is not executed */
+	++R.depth;
+	vgb_batch* b = R.b;
+	vgb_cl_context* ctx = R.ctx;
+	vgb_cl_stats& st = R.st;
+	std::vector<State>& stack = R.stack;
+	bool& inClip = R.inClip;
+	const float fringe = R.fringe;
+	const bool cullCmds = (listFlags & 2u) != 0; /* CommandListFlags::AllowCommandCulling, vg.cpp:4307 */
+	bool skipCmds = false;                        /* local to one execution of one list, vg.cpp:4324 */
 	int rc = 0;
 
 	const uint8_t* cmd = (const uint8_t*)buffer;
@@ -197,9 +209,23 @@ extern "C" int vgb_batch_submit_command_list(vgb_batch* b, const void* buffer, u
 		} break;
 		case CL_FillPathGradient: case CL_FillPathImagePattern: case CL_StrokePathGradient: case CL_StrokePathImagePattern:
 		case CL_IndexedTriList: case CL_CreateLinearGradient: case CL_CreateBoxGradient: case CL_CreateRadialGradient:
-		case CL_CreateImagePattern: case CL_Text: case CL_TextBox: case CL_SubmitCommandList: case CL_ResetClip:
+		case CL_CreateImagePattern: case CL_Text: case CL_TextBox: case CL_ResetClip:
 			++st.unsupported;
 			break;
+		case CL_SubmitCommandList: { /* vg.cpp:4620-4626 */
+			if (!need(2)) { rc = BAD; break; }
+			const uint16_t id = rd<uint16_t>(p);
+			if (!ctx->lists) { /* no table given: nesting not available to this call */
+				++st.unsupported;
+				break;
+			}
+			if (id >= ctx->num_lists || !ctx->lists[id].commands) {
+				break; /* isCommandListHandleValid() false: skipped */
+			}
+			++st.nested;
+			rc = runList(R, ctx->lists[id].commands, ctx->lists[id].size, ctx->lists[id].flags);
+			s = &stack.back(); /* the nested list may have pushed / popped states */
+		} break;
 		case CL_BeginClip: inClip = true; ++st.unsupported; break;
 		case CL_EndClip: inClip = false; break;
 		case CL_PushState: /* vg.cpp:3934-3944 */
@@ -289,13 +315,35 @@ extern "C" int vgb_batch_submit_command_list(vgb_batch* b, const void* buffer, u
 		}
 		cmd = next;
 	}
+	--R.depth;
+#undef BAD
+	return rc;
+}
+} // namespace
+
+extern "C" int vgb_batch_submit_command_list(vgb_batch* b, const void* buffer, uint32_t size, vgb_cl_context* ctx, vgb_cl_stats* stats)
+{
+	if (!b || !ctx || (!buffer && size)) return fail(VGB_ERR_INVALID, "null argument");
+	Run R;
+	R.b = b;
+	R.ctx = ctx;
+	memset(&R.st, 0, sizeof(R.st));
+	R.stack.resize(1);
+	memcpy(R.stack[0].mtx, ctx->xform, sizeof(float) * 6);
+	memcpy(R.stack[0].scissor, ctx->scissor, sizeof(float) * 4);
+	R.stack[0].globalAlpha = ctx->global_alpha;
+	updateState(&R.stack[0]);
+	R.fringe = vgb_batch_fringe(b);
+	R.inClip = false;
+	R.depth = 0;
+	R.maxDepth = ctx->max_depth ? ctx->max_depth : 16u; /* ContextConfig::m_MaxCommandListDepth default, vg.cpp:728 */
+	const int rc = runList(R, buffer, size, ctx->flags);
 	/* VG_CONFIG_COMMAND_LIST_PRESERVE_STATE is 0 by default (vg.h:34-35): state changes outlive the list */
-	const State& top = stack.back();
+	const State& top = R.stack.back();
 	memcpy(ctx->xform, top.mtx, sizeof(float) * 6);
 	memcpy(ctx->scissor, top.scissor, sizeof(float) * 4);
 	ctx->global_alpha = top.globalAlpha;
-	st.state_depth = (uint32_t)stack.size() - 1;
-	if (stats) *stats = st;
-#undef BAD
+	R.st.state_depth = (uint32_t)R.stack.size() - 1;
+	if (stats) *stats = R.st;
 	return rc;
 }
