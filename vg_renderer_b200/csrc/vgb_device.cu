@@ -7,6 +7,9 @@
  *   k_flatten_slots    thread per sub-path, ONE pass: walk commands, store (transformed) points into
  *                      the sub-path's recorder-sized slot (overflow arena + two-pass fallback
  *                      k_flatten<false/true> + scan)
+ *   k_cmd_index, k_cmd_flatten<count/emit>, k_cmd_sub_sizes   command-parallel flatten for scenes of long
+ *                      sub-paths (thread per command from the previous command's nominal end point; sub-paths
+ *                      whose end points survive the dedupe are exactly the sequential walk, the rest fall back)
  *   k_bulk_cubic_tables  bulk mode: all tables generated on the device from the caller's coordinates
  *   k_draw_prep        per-draw constants (hsw, da, nHC, nfix ...) with the shared fp32 math
  *   k_job_pieces       pieces per job (mesh) -> scan -> pieceStart;  k_job_prep: 48-byte job records
@@ -47,6 +50,9 @@ namespace vgb
 		}                                                                                     \
 	} while (0)
 
+#ifndef VGB_CMD_FLATTEN_DEFAULT
+#define VGB_CMD_FLATTEN_DEFAULT 1
+#endif
 #ifndef VGB_EMIT_PREFETCH
 #define VGB_EMIT_PREFETCH 1
 #endif
@@ -202,6 +208,7 @@ struct FlattenArgs
 	const uint32_t* subFirst; /* emit pass input (scanned)          */
 	uint8_t* subClosed;       /* emit pass output                   */
 	float2* pts;              /* emit pass output                   */
+	const uint8_t* subMode;   /* nullable; 1 = this sub-path is flattened per COMMAND (k_cmd_flatten): skip it here */
 };
 
 template<bool EMIT>
@@ -210,6 +217,7 @@ __global__ void __launch_bounds__(128) k_flatten(FlattenArgs a)
 	__shared__ float sStack[10 * 6 * 128];
 	const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
 	if (s >= a.numSub) return;
+	if (a.subMode != nullptr && a.subMode[s] != 0) return;
 	const SubRec r = a.subRec[s];
 	SubPathWalker<EMIT> w;
 	w.lx = w.ly = w.px = w.py = w.fx = w.fy = 0.0f;
@@ -228,6 +236,153 @@ __global__ void __launch_bounds__(128) k_flatten(FlattenArgs a)
 	} else {
 		a.subNum[s] = w.n;
 	}
+}
+
+/* ---- command-parallel flatten (two passes, dense output) -----------------------------------------
+ * A thread per COMMAND instead of per sub-path, for scenes of few long sub-paths (a thread per sub-path
+ * then is one wave of long serial chains).  What command c needs from its predecessors is only the path's
+ * last kept vertex E_c (P1 of a curve, the dedupe partner of its first vertex; path.cpp:93-97, 761-784).
+ * For moveTo / lineTo / cubicTo / quadTo the previous command's nominal end point is in the command data,
+ * and E_c equals it unless the epsilon-dedupe dropped that end point.  So every command is flattened on
+ * its own from the nominal E_c and reports whether its own end point was kept; a sub-path all of whose
+ * commands report so is exactly the sequential walk (tools/proto_command_parallel_flatten.py checks this
+ * against the oracle), any other sub-path -- and any with a command whose end point is computed (arcs,
+ * shapes, polylines) -- is left to k_flatten.  pathClose (path.cpp:707-726) is applied per sub-path from
+ * the first and the last nominal point. */
+struct CmdArgs
+{
+	FlattenArgs f;
+	uint32_t numCmd;
+	uint32_t* cmdSub;   /* per command: its sub-path                              */
+	uint32_t* cmdData;  /* per command: offset of its floats in data[]            */
+	uint32_t* cmdCount; /* per command: vertices it contributes                   */
+	uint32_t* cmdOff;   /* per command: first vertex inside its sub-path          */
+	uint8_t* cmdOk;     /* per command: its nominal end point was kept            */
+	uint8_t* subModeW;  /* per sub-path: 1 = handled here, 0 = left to k_flatten   */
+};
+
+__device__ __forceinline__ bool cmdIsSimple(uint32_t t)
+{
+	return t == VGB_CMD_MOVE_TO || t == VGB_CMD_LINE_TO || t == VGB_CMD_CUBIC_TO || t == VGB_CMD_QUAD_TO;
+}
+
+/* nominal end point of a simple command: the last two floats of its data */
+__device__ __forceinline__ float2 cmdEnd(uint32_t t, const float* __restrict__ d)
+{
+	const uint32_t n = cmdArity(t);
+	return make_float2(d[n - 2], d[n - 1]);
+}
+
+/* per sub-path: command -> (sub-path, data offset) and the static part of the eligibility */
+__global__ void k_cmd_index(CmdArgs a)
+{
+	const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+	if (s >= a.f.numSub) return;
+	const SubRec r = a.f.subRec[s];
+	uint32_t off = r.dataBegin;
+	bool ok = r.cmdEnd > r.cmdBegin && a.f.cmd[r.cmdBegin] == VGB_CMD_MOVE_TO;
+	for (uint32_t c = r.cmdBegin; c < r.cmdEnd; ++c) {
+		const uint32_t t = a.f.cmd[c];
+		a.cmdSub[c] = s;
+		a.cmdData[c] = off;
+		if (c > r.cmdBegin) {
+			const bool lastClose = t == VGB_CMD_CLOSE && c + 1 == r.cmdEnd;
+			ok = ok && (lastClose || (cmdIsSimple(t) && t != VGB_CMD_MOVE_TO));
+		}
+		if (t == VGB_CMD_POLYLINE) {
+			off += 1u + 2u * __float_as_uint(a.f.data[off]);
+		} else {
+			off += cmdArity(t);
+		}
+	}
+	a.subModeW[s] = ok ? 1 : 0;
+}
+
+template<bool EMIT>
+__global__ void __launch_bounds__(128) k_cmd_flatten(CmdArgs a)
+{
+	__shared__ float sStack[10 * 6 * 128];
+	const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+	if (c >= a.numCmd) return;
+	const uint32_t s = a.cmdSub[c];
+	if (a.subModeW[s] == 0) return;
+	const SubRec r = a.f.subRec[s];
+	const uint32_t t = a.f.cmd[c];
+	if (t == VGB_CMD_CLOSE) {
+		if (!EMIT) {
+			a.cmdCount[c] = 0;
+			a.cmdOk[c] = 1;
+		}
+		return;
+	}
+	const float* d = a.f.data + a.cmdData[c];
+	const bool isMove = c == r.cmdBegin;
+	SubPathWalker<EMIT> w;
+	w.px = w.py = w.fx = w.fy = 0.0f;
+	w.lx = w.ly = 0.0f;
+	w.n = 0;
+	if (!isMove) {
+		const float2 e = cmdEnd(a.f.cmd[c - 1], a.f.data + a.cmdData[c - 1]);
+		w.lx = e.x;
+		w.ly = e.y;
+		w.n = 1; /* the sub-path is not empty: the dedupe against (lx, ly) applies */
+	}
+	w.closed = false;
+	w.scale = a.f.pathScale[r.pathId];
+	w.tol = a.f.pathTol[r.pathId];
+	w.m = (EMIT && a.f.pathXform) ? a.f.pathXform + 6 * (size_t)r.pathId : nullptr;
+	uint32_t off = 0;
+	if (EMIT) {
+		off = a.cmdOff[c];
+		w.out = a.f.pts + a.f.subFirst[s] + off - (isMove ? 0u : 1u);
+		w.limit = (a.f.subNum[s] - off) + (isMove ? 0u : 1u); /* a vertex dropped by pathClose is never stored */
+	} else {
+		w.out = nullptr;
+		w.limit = 0;
+	}
+	w.stk = sStack + threadIdx.x;
+	w.stride = 128;
+	w.run(a.f.cmd, c, c + 1, d);
+	if (!EMIT) {
+		const float2 e = cmdEnd(t, d);
+		a.cmdCount[c] = w.n - (isMove ? 0u : 1u);
+		a.cmdOk[c] = (w.lx == e.x && w.ly == e.y) ? 1 : 0;
+	}
+}
+
+/* per sub-path: all end points kept? -> vertex offsets of its commands, its size, pathClose */
+__global__ void k_cmd_sub_sizes(CmdArgs a)
+{
+	const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+	if (s >= a.f.numSub) return;
+	if (a.subModeW[s] == 0) return;
+	const SubRec r = a.f.subRec[s];
+	uint32_t total = 0;
+	bool ok = true;
+	for (uint32_t c = r.cmdBegin; c < r.cmdEnd; ++c) {
+		ok = ok && a.cmdOk[c] != 0;
+		a.cmdOff[c] = total;
+		total += a.cmdCount[c];
+	}
+	if (!ok) {
+		a.subModeW[s] = 0; /* an end point was deduped away: the sequential walk decides */
+		return;
+	}
+	bool closed = false;
+	const uint32_t lastCmd = r.cmdEnd - 1;
+	if (a.f.cmd[lastCmd] == VGB_CMD_CLOSE && total > 2) { /* pathClose, path.cpp:707-726 */
+		closed = true;
+		const float2 first = cmdEnd(VGB_CMD_MOVE_TO, a.f.data + r.dataBegin);
+		const float2 last = cmdEnd(a.f.cmd[lastCmd - 1], a.f.data + a.cmdData[lastCmd - 1]);
+		const float dx = last.x - first.x;
+		const float dy = last.y - first.y;
+		const float distSqr = dx * dx + dy * dy;
+		if (distSqr < VGB_EPSILON) {
+			--total;
+		}
+	}
+	a.f.subNum[s] = total;
+	a.f.subClosed[s] = closed ? 1 : 0;
 }
 
 /* Single-pass flatten: every sub-path owns a slot of the point buffer sized by the recorder, so
@@ -1104,6 +1259,8 @@ public:
 	uint32_t kNumPts = 0, kNumPieces = 0;
 	uint64_t kTotals[2] = {0, 0};
 	bool slotMode = false;   /* single-pass flatten into recorder-sized slots */
+	bool cmdMode = false;    /* command-parallel flatten (scenes of long sub-paths) */
+	DevBuf dCmdSub, dCmdData, dCmdCount, dCmdOff, dCmdOk, dSubMode;
 	bool slotsUsed = false;  /* the last run's point buffer is slotted (not dense) */
 	uint32_t totalSlots = 0;
 	/* outputs */
@@ -1134,7 +1291,7 @@ public:
 		DevBuf* all[] = {&dSubRec, &dCmd, &dData, &dScale, &dTol, &dXform, &dDraws, &dJobSub, &dJobDraw, &dSubNum, &dSubFirst,
 		                 &dSubClosed, &dPts, &dDD, &dJobPieces, &dPieceStart, &dJobRec, &dPieceJob, &dBlockTotals, &dBlockBase,
 		                 &dMeshTotals, &dMeshOff, &dScanTmp, &dBlockTail, &dSlotFirst, &dCounters, &dDenseFirst, &dDensePts, &dBulkErr, &dMeshSplit, &dPos, &dCol, &dIdx,
-		                 &dSegNext[0], &dSegNext[1], &dSegStarts, &dSegHdr, &dSegCmds, &dMeshBase, &dUV, &dRXf, &dRPos, &dRCol, &dRIdx};
+		                 &dCmdSub, &dCmdData, &dCmdCount, &dCmdOff, &dCmdOk, &dSubMode, &dSegNext[0], &dSegNext[1], &dSegStarts, &dSegHdr, &dSegCmds, &dMeshBase, &dUV, &dRXf, &dRPos, &dRCol, &dRIdx};
 		for (DevBuf* b : all) b->release();
 		for (auto& e : ev) if (e) cudaEventDestroy(e);
 		for (auto& e : userEv) if (e) cudaEventDestroy(e);
@@ -1177,6 +1334,7 @@ public:
 		ht = t;
 		rawMode = t.rawPts != nullptr;
 		slotMode = false;
+		cmdMode = false;
 		numSub = t.numSub;
 		numJobs = t.numJobs;
 		numDraws = t.numDraws;
@@ -1217,6 +1375,16 @@ public:
 			rc |= up(dData, t.data, t.numData, err);
 			if (hasXform) rc |= up(dXform, t.pathXform, 6 * (size_t)t.numPaths, err);
 			slotMode = t.subSlotFirst != nullptr && t.numSub > 0 && getenv("VGB_TWO_PASS_FLATTEN") == nullptr;
+			/* long sub-paths (8+ commands each on average; with VGB_CMD_FLATTEN=1: 4+): flatten per command.
+			 * Measured on the tiger-like scene (13 commands per sub-path, x300 instances): flatten 1.13 -> 0.97 ms;
+			 * short sub-paths keep the single-pass slot flatten.  VGB_CMD_FLATTEN=0 switches it off. */
+			{
+				const char* e = getenv("VGB_CMD_FLATTEN");
+				const bool dflt = VGB_CMD_FLATTEN_DEFAULT != 0;
+				const uint64_t minCmds = (e && e[0] == '1') ? 4ull : 8ull;
+				cmdMode = t.numSub > 0 && (uint64_t)t.numCmd >= minCmds * t.numSub && (e ? e[0] == '1' : dflt);
+				if (cmdMode) slotMode = false;
+			}
 			if (slotMode) {
 				totalSlots = t.subSlotFirst[t.numSub];
 				rc |= up(dSlotFirst, t.subSlotFirst, (size_t)t.numSub + 1, err);
@@ -1305,6 +1473,7 @@ public:
 			fa.subFirst = dSubFirst.as<uint32_t>();
 			fa.subClosed = dSubClosed.as<uint8_t>();
 			fa.pts = nullptr;
+			fa.subMode = nullptr;
 			const uint32_t fb = (numSub + 127) / 128;
 			slotsUsed = false;
 			if (slotMode) {
@@ -1325,6 +1494,27 @@ public:
 				slotsUsed = true;
 				numPts = 0xFFFFFFFFu; /* read back later together with the piece count */
 			} else {
+				CmdArgs ca;
+				const uint32_t numCmd = ht.numCmd;
+				const uint32_t cb = (numCmd + 127) / 128;
+				if (cmdMode) {
+					if (dCmdSub.ensure((size_t)numCmd * 4, err) || dCmdData.ensure((size_t)numCmd * 4, err) || dCmdCount.ensure((size_t)numCmd * 4, err) ||
+					    dCmdOff.ensure((size_t)numCmd * 4, err) || dCmdOk.ensure(numCmd, err) || dSubMode.ensure(numSub, err))
+						return VGB_ERR_CUDA;
+					fa.subMode = dSubMode.as<uint8_t>();
+					ca.f = fa;
+					ca.numCmd = numCmd;
+					ca.cmdSub = dCmdSub.as<uint32_t>();
+					ca.cmdData = dCmdData.as<uint32_t>();
+					ca.cmdCount = dCmdCount.as<uint32_t>();
+					ca.cmdOff = dCmdOff.as<uint32_t>();
+					ca.cmdOk = dCmdOk.as<uint8_t>();
+					ca.subModeW = dSubMode.as<uint8_t>();
+					k_cmd_index<<<fb, 128, 0, st>>>(ca);
+					k_cmd_flatten<false><<<cb, 128, 0, st>>>(ca);
+					k_cmd_sub_sizes<<<fb, 128, 0, st>>>(ca);
+					launches += 3;
+				}
 				k_flatten<false><<<fb, 128, 0, st>>>(fa);
 				++launches;
 				if (scan<ScanOps<uint32_t>>(dSubNum.as<uint32_t>(), numSub, dSubFirst.as<uint32_t>(), err)) return VGB_ERR_CUDA;
@@ -1335,6 +1525,11 @@ public:
 				}
 				if (dPts.ensure((size_t)numPts * 8 + 16, err)) return VGB_ERR_CUDA;
 				fa.pts = dPts.as<float2>();
+				if (cmdMode) {
+					ca.f = fa;
+					k_cmd_flatten<true><<<cb, 128, 0, st>>>(ca);
+					++launches;
+				}
 				k_flatten<true><<<fb, 128, 0, st>>>(fa);
 				++launches;
 				VGB_CUDA(cudaGetLastError());
