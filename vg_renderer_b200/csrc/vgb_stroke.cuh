@@ -10,7 +10,7 @@
  *       pieces 0..N-3 = fan triangles (3 indices, no vertex), then N vertex pieces
  *       (2 vertices + one fringe quad) -- exactly the reference's [fan][quads] index order.
  * Piece sizes depend on data (round joins: n = max(2, uint(dAngle/da))), so sizes are counted
- * (k_piece_count), scanned, then emitted (k_piece_emit) -- both call classify() below, which
+ * (k_group_count), scanned, then emitted (k_group_emit) -- both call classify() below, which
  * is therefore the single place where every count decision lives.
  *
  * All float expressions follow the reference's evaluation order operation by operation and the
@@ -467,8 +467,7 @@ struct Sink
 };
 
 /* ---- AA stroke pieces ---------------------------------------------------------------- */
-/* everything a cap needs, detached from its owner thread (k_piece_emit hands caps to one warp so
- * that the other warps never execute cap code) */
+/* everything a butt / square cap needs, gathered from its lane (round caps go through emitStrokeAA) */
 struct CapRec
 {
 	float2 p, d;      /* end point and direction of the adjacent segment        */
