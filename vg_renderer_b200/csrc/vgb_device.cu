@@ -665,71 +665,63 @@ __device__ __forceinline__ void bulkStore(void* gdst, const void* ssrc, uint32_t
 __device__ __forceinline__ void bulkCommit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulkWaitRead() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 
-/* where the 16-byte aligned body of an output range [gs, gs + count) of T lies, and its ragged ends */
-template<class T>
-struct CopyPlan
-{
-	uint64_t alignedBase, bodyBegin, bodyEnd;
-	uint32_t head, tail;
-	__device__ __forceinline__ CopyPlan(uint64_t gs, uint32_t count)
-	{
-		constexpr uint32_t K = 16 / sizeof(T);
-		const uint64_t ge = gs + count;
-		alignedBase = gs & ~(uint64_t)(K - 1);
-		bodyBegin = (gs + K - 1) & ~(uint64_t)(K - 1);
-		bodyEnd = ge & ~(uint64_t)(K - 1);
-		if (bodyEnd <= bodyBegin) {
-			bodyBegin = bodyEnd = ge; /* everything is ragged (count < 2K) */
-		}
-		head = (uint32_t)(bodyBegin - gs);
-		tail = (uint32_t)(ge - bodyEnd);
-	}
-};
-
-/* ragged ends of one stream: lanes 1.. take the head elements, lanes 17.. the tail elements, one pass */
-template<class T>
-__device__ __forceinline__ void copyRagged(T* __restrict__ gbase, uint64_t gs, const CopyPlan<T>& c, const T* sbuf, uint32_t lane)
-{
-	const uint32_t l = lane - 1;
-	const bool isHead = l < c.head;
-	const bool isTail = l >= 16 && l - 16 < c.tail;
-	if (isHead || isTail) {
-		const uint64_t e = isHead ? gs + l : c.bodyEnd + (l - 16);
-		gbase[e] = sbuf[e - c.alignedBase];
-	}
-}
-
-/* one WARP streams its three arrays: lanes 0, 1, 2 each issue (and later wait for) the bulk copy of
- * one stream's aligned body; the ragged ends (fewer than 16 bytes each) are stored by lanes */
+/* One WARP streams its three arrays out of its staging image.  The image holds element e of a stream
+ * at sbuf[lo + e], lo = (global element index of e = 0) mod K, K = elements per 16 bytes, so 16-byte
+ * chunks of the image line up with 16-byte chunks of HBM.  The aligned body [b0, b1) of each stream
+ * leaves with ONE cp.async.bulk; the ragged ends (fewer than K elements each) are stored by lanes.
+ * The three plans are evaluated side by side, one stream per group of lanes (32-bit arithmetic on
+ * image coordinates; the only 64-bit quantity is the stream's 16-byte aligned global address):
+ *   lanes 0-1   positions  (K = 2: one head, one tail element at most)      issuer: lane 0
+ *   lanes 2-7   colours    (K = 4: up to three each)                        issuer: lane 2
+ *   lanes 8-23  indices    (K = 8 or 4: up to seven each)                   issuer: lane 8 */
 template<class IDX>
 __device__ __forceinline__ void copyOutWarp3(float2* __restrict__ gPos, uint32_t* __restrict__ gCol, IDX* __restrict__ gIdx, uint64_t vs, uint64_t is,
                                              uint32_t totV, uint32_t totI, const float2* sPos, const uint32_t* sCol, const IDX* sIdx, uint32_t lane)
 {
-	const CopyPlan<float2> cp(vs, totV);
-	const CopyPlan<uint32_t> cc(vs, totV);
-	const CopyPlan<IDX> ci(is, totI);
-	if (lane < 3) {
-		const void* src = lane == 0 ? (const void*)(sPos + (cp.bodyBegin - cp.alignedBase))
-		                : lane == 1 ? (const void*)(sCol + (cc.bodyBegin - cc.alignedBase)) : (const void*)(sIdx + (ci.bodyBegin - ci.alignedBase));
-		void* dst = lane == 0 ? (void*)(gPos + cp.bodyBegin) : lane == 1 ? (void*)(gCol + cc.bodyBegin) : (void*)(gIdx + ci.bodyBegin);
-		const uint32_t bytes = lane == 0 ? (uint32_t)(cp.bodyEnd - cp.bodyBegin) * 8u
-		                     : lane == 1 ? (uint32_t)(cc.bodyEnd - cc.bodyBegin) * 4u : (uint32_t)(ci.bodyEnd - ci.bodyBegin) * (uint32_t)sizeof(IDX);
-		if (bytes) {
-			bulkStore(dst, src, bytes);
+	constexpr uint32_t KI = 16 / sizeof(IDX);
+	const uint32_t sid = lane < 2 ? 0u : (lane < 8 ? 1u : 2u);
+	const uint32_t r = lane - (sid == 0 ? 0u : (sid == 1 ? 2u : 8u)); /* role inside the stream's lanes */
+	const uint32_t K = sid == 0 ? 2u : (sid == 1 ? 4u : KI);
+	const uint32_t half = sid == 0 ? 1u : (sid == 1 ? 3u : 8u);
+	const uint32_t sh = sid == 0 ? 3u : (sid == 1 ? 2u : (sizeof(IDX) == 2 ? 1u : 2u)); /* log2(element bytes) */
+	const uint64_t gs = sid == 2 ? is : vs;
+	const uint32_t count = sid == 2 ? totI : totV;
+	const uint32_t lo = (uint32_t)gs & (K - 1);
+	const uint32_t end = lo + count;
+	const uint32_t b0 = lo ? K : 0u;
+	const uint32_t b1 = end & ~(K - 1);
+	const bool body = b1 > b0;
+	/* shared / global BYTE addresses of image coordinate 0 */
+	const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(sid == 0 ? (const void*)sPos : (sid == 1 ? (const void*)sCol : (const void*)sIdx));
+	char* gbase = (sid == 0 ? (char*)gPos : (sid == 1 ? (char*)gCol : (char*)gIdx)) + ((gs - lo) << sh);
+	if (r == 0 && lane < 9) {
+		if (body) {
+			asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gbase + (b0 << sh)), "r"(sbase + (b0 << sh)), "r"((b1 - b0) << sh)
+			             : "memory");
 		}
 		bulkCommit();
 	}
-	copyRagged(gPos, vs, cp, sPos, lane);
-	copyRagged(gCol, vs, cc, sCol, lane);
-	copyRagged(gIdx, is, ci, sIdx, lane);
+	/* ragged ends: head elements [lo, min(b0, end)), tail elements [max(b0, b1), end) */
+	const bool isHead = r < half;
+	const uint32_t e = isHead ? lo + r : (body ? b1 : b0) + (r - half);
+	const bool ok = lane < 24 && (isHead ? e < (b0 < end ? b0 : end) : e < end);
+	if (ok) {
+		if (sid == 0) {
+			reinterpret_cast<float2*>(gbase)[e] = sPos[e];
+		} else if (sid == 1) {
+			reinterpret_cast<uint32_t*>(gbase)[e] = sCol[e];
+		} else {
+			reinterpret_cast<IDX*>(gbase)[e] = sIdx[e];
+		}
+	}
 }
 
 template<uint32_t OPS, int JT, int CT, class SINK>
-__device__ __forceinline__ void emitPiece(const PieceArgs& a, const JobCtx& J, const Piece& P, uint32_t F, uint4 prev, const SINK& S)
+__device__ __forceinline__ void emitPiece(const float2* __restrict__ pts, const JobCtx& J, const Piece& P, uint32_t F, uint4 prev, const SINK& S)
 {
 	if ((OPS & OPS_OTHER) && (J.op == VGB_OP_STROKE || J.op == VGB_OP_STROKE_AA_THIN)) {
 		if (P.kind == PK_JOIN) {
-			const bool firstLeft = (P.flags & PF_CLOSING) ? firstJoinLeft(J, a.pts) : false;
+			const bool firstLeft = (P.flags & PF_CLOSING) ? firstJoinLeft(J, pts) : false;
 			emitRibbonJoin(J, P, F, prev, firstLeft, S);
 		} else {
 			emitRibbonCap(J, P, F, prev, S);
@@ -746,10 +738,30 @@ __device__ __forceinline__ void emitPiece(const PieceArgs& a, const JobCtx& J, c
 	}
 	if (false) {
 	} else if ((OPS & OPS_FILL_AA) && P.kind == PK_FILL_VTX) {
-		emitFillVtx(J, P, a.pts, S);
+		emitFillVtx(J, P, pts, S);
 	} else if ((OPS & OPS_FILL_AA) && P.kind == PK_FILL_FAN) {
 		emitFillFan(P, S);
 	}
+}
+
+template<uint32_t OPS, int JT, int CT, class SINK>
+__device__ __forceinline__ void emitAny(const float2* __restrict__ pts, const JobCtx& J, const Piece& P, uint32_t F, uint4 prev, const SINK& S)
+{
+	if ((OPS & OPS_STROKE_AA) && (!(OPS & ~OPS_STROKE_AA) || J.op == VGB_OP_STROKE_AA)) {
+		/* joins and round caps share one code path (see emitStrokeAA) */
+		const bool firstLeft = (P.flags & PF_CLOSING) ? firstJoinLeft(J, pts) : false;
+		emitStrokeAA<JT, CT>(J, P, F, prev, firstLeft, S);
+	} else {
+		emitPiece<OPS, JT, CT>(pts, J, P, F, prev, S);
+	}
+}
+
+/* the same through the plain-pointer sink, out of line: it only runs for warps whose pieces do not fit
+ * the staging image, and must not cost the common path registers or instruction-cache footprint */
+template<uint32_t OPS, int JT, int CT, class SINK>
+__device__ __forceinline__ void emitAnyCold(const float2* __restrict__ pts, const JobCtx& J, const Piece& P, uint32_t F, uint4 prev, const SINK& S)
+{
+	emitAny<OPS, JT, CT>(pts, J, P, F, prev, S);
 }
 
 /* =========================================================================================
@@ -1117,38 +1129,36 @@ __global__ void __launch_bounds__(128, (OPS == OPS_STROKE_AA && JT < 3) ? VGB_EM
 	uint32_t idxBase = sizeof(IDX) == 2 ? 0u : (uint32_t)(mo.x + a.vertexBase);
 	if (sizeof(IDX) == 2 && BIGI && valid) idxBase = a.meshBase[j];
 	const bool fits = totV <= CVW && totI <= CIW; /* warp-uniform */
-	uint8_t* stage = sStage + wib * WBYTES;
-	float2* sPos = reinterpret_cast<float2*>(stage);
-	uint32_t* sCol = reinterpret_cast<uint32_t*>(stage + POS_BYTES);
-	IDX* sIdx = reinterpret_cast<IDX*>(stage + POS_BYTES + COL_BYTES);
-	Sink<IDX, !(OPS & OPS_OTHER)> S;
-	S.base = idxBase;
 	if (fits) {
+		/* the staging image: typed shared-memory stores, packed index words */
+		uint8_t* stage = sStage + wib * WBYTES;
+		float2* sPos = reinterpret_cast<float2*>(stage);
+		uint32_t* sCol = reinterpret_cast<uint32_t*>(stage + POS_BYTES);
+		IDX* sIdx = reinterpret_cast<IDX*>(stage + POS_BYTES + COL_BYTES);
+		SinkS<IDX, !(OPS & OPS_OTHER)> S;
+		S.base = idxBase;
 		S.pos = sPos + (uint32_t)(bb.x & 1) + vl;
 		S.col = sCol + (uint32_t)(bb.x & 3) + vl;
 		S.idx = sIdx + (uint32_t)(bb.y & (KI - 1)) + il;
-	} else {
-		/* a warp whose pieces exceed the staging image writes straight to HBM */
-		S.pos = a.pos + bb.x + vl;
-		S.col = a.col + bb.x + vl;
-		S.idx = reinterpret_cast<IDX*>(a.idx) + bb.y + il;
-	}
-	if (valid) {
-		if ((OPS & OPS_STROKE_AA) && (!(OPS & ~OPS_STROKE_AA) || J.op == VGB_OP_STROKE_AA)) {
-			/* joins and round caps share one code path (see emitStrokeAA) */
-			const bool firstLeft = (P.flags & PF_CLOSING) ? firstJoinLeft(J, a.pts) : false;
-			emitStrokeAA<JT, CT>(J, P, F, prev, firstLeft, S);
-		} else {
-			emitPiece<OPS, JT, CT>(a, J, P, F, prev, S);
+		S.par = ((uint32_t)bb.y + il) & 1u;
+		if (valid) {
+			emitAny<OPS, JT, CT>(a.pts, J, P, F, prev, S);
 		}
-	}
-	if (fits) {
 		fenceProxyAsync();
 		__syncwarp();
 		copyOutWarp3<IDX>(a.pos, a.col, reinterpret_cast<IDX*>(a.idx), bb.x, bb.y, totV, totI, sPos, sCol, sIdx, lane);
-		if (lane < 3) {
+		if (lane == 0 || lane == 2 || lane == 8) {
 			bulkWaitRead();
 		}
+	} else if (valid) {
+		/* a warp whose pieces exceed the staging image writes straight to HBM */
+		Sink<IDX, !(OPS & OPS_OTHER)> S;
+		S.base = idxBase;
+		S.par = 0;
+		S.pos = a.pos + bb.x + vl;
+		S.col = a.col + bb.x + vl;
+		S.idx = reinterpret_cast<IDX*>(a.idx) + bb.y + il;
+		emitAnyCold<OPS, JT, CT>(a.pts, J, P, F, prev, S);
 	}
 }
 

@@ -407,6 +407,17 @@ __device__ __forceinline__ uint4 joinIn4(bool left, uint32_t F)
 	return left ? make_uint4(F, F + 1, F + 2, F + 3) : make_uint4(F + 3, F + 2, F + 1, F);
 }
 
+/* ---- sinks: where a piece's vertices / colours / indices go -------------------------------------
+ * Two of them with one interface, so that the address space of every store is known at compile time
+ * (a sink whose pointers are chosen at run time between shared and global memory makes every store a
+ * generic ST with 64-bit address arithmetic -- round-1 profile: 89 generic ST.E, no STS):
+ *   Sink   scalar stores through plain pointers: the rare warp whose pieces exceed the staging image
+ *          writes straight to HBM through it;
+ *   SinkS  the warp-private staging image in SHARED memory (STS with immediate offsets); uint16 indices
+ *          leave as packed 32-bit words: an index sequence is formed as "logical" words (i0,i1) (i2,i3) ..
+ *          and a lane whose sequence starts at an odd uint16 position stores the funnel-shifted words
+ *          (i1,i2) (i3,i4) .. plus the two odd halves, through the same code (the PRMT selector is the
+ *          only thing that differs between lanes), so parity never diverges a warp. */
 template<class IDX, bool ALIGNED = true>
 struct Sink
 {
@@ -414,6 +425,7 @@ struct Sink
 	uint32_t* col;
 	IDX* idx;
 	uint32_t base; /* added to every index value (0 for per-mesh uint16) */
+	uint32_t par;  /* unused here (SinkS: parity of idx) */
 
 	__device__ __forceinline__ void V(uint32_t k, float x, float y, uint32_t c) const
 	{
@@ -443,8 +455,7 @@ struct Sink
 		const uint32_t pa[4] = {p.x, p.y, p.z, p.w}, ca[4] = {c.x, c.y, c.z, c.w};
 #pragma unroll
 		for (int i = 0; i + 1 < W; ++i) {
-			tri(k + 6 * i, pa[i], pa[i + 1], ca[i + 1]);
-			tri(k + 6 * i + 3, pa[i], ca[i + 1], ca[i]);
+			tri2(k + 6 * i, pa[i], pa[i + 1], ca[i + 1], pa[i], ca[i + 1], ca[i]);
 		}
 	}
 	__device__ __forceinline__ void I(uint32_t k, uint32_t v) const { idx[k] = (IDX)(v + base); }
@@ -454,15 +465,125 @@ struct Sink
 		I(k + 1, b);
 		I(k + 2, c);
 	}
+	/* two consecutive triangles */
+	__device__ __forceinline__ void tri2(uint32_t k, uint32_t a, uint32_t b, uint32_t c, uint32_t d, uint32_t e, uint32_t f) const
+	{
+		tri(k, a, b, c);
+		tri(k + 3, d, e, f);
+	}
 	/* the 18-index strip between two cross-sections (stroker.cpp:1557-1564 and siblings) */
 	__device__ __forceinline__ void connect(uint32_t k, uint4 p, uint4 c) const
 	{
-		tri(k + 0, p.x, p.y, c.y);
-		tri(k + 3, p.x, c.y, c.x);
-		tri(k + 6, p.y, p.z, c.z);
-		tri(k + 9, p.y, c.z, c.y);
-		tri(k + 12, p.z, p.w, c.w);
-		tri(k + 15, p.z, c.w, c.z);
+		tri2(k + 0, p.x, p.y, c.y, p.x, c.y, c.x);
+		tri2(k + 6, p.y, p.z, c.z, p.y, c.z, c.y);
+		tri2(k + 12, p.z, p.w, c.w, p.z, c.w, c.z);
+	}
+};
+
+__device__ __forceinline__ uint32_t pk16(uint32_t lo, uint32_t hi) { return __byte_perm(lo, hi, 0x5410); }
+
+template<class IDX, bool ALIGNED = true>
+struct SinkS
+{
+	float2* pos;   /* all three point into the warp's staging image in shared memory */
+	uint32_t* col;
+	IDX* idx;
+	uint32_t base;
+	uint32_t par;  /* uint16 only: idx sits at an odd uint16 position (of its 32-bit word) */
+
+	__device__ __forceinline__ void V(uint32_t k, float x, float y, uint32_t c) const
+	{
+		pos[k] = make_float2(x, y);
+		col[k] = c;
+	}
+	__device__ __forceinline__ void VP(uint32_t k, float x0, float y0, uint32_t c0_, float x1, float y1, uint32_t c1_) const
+	{
+		if (ALIGNED) {
+			*reinterpret_cast<float4*>(pos + k) = make_float4(x0, y0, x1, y1);
+			*reinterpret_cast<uint2*>(col + k) = make_uint2(c0_, c1_);
+		} else {
+			pos[k] = make_float2(x0, y0);
+			pos[k + 1] = make_float2(x1, y1);
+			col[k] = c0_;
+			col[k + 1] = c1_;
+		}
+	}
+	template<int W>
+	__device__ __forceinline__ void bridge(uint32_t k, uint4 p, uint4 c) const
+	{
+		const uint32_t pa[4] = {p.x, p.y, p.z, p.w}, ca[4] = {c.x, c.y, c.z, c.w};
+#pragma unroll
+		for (int i = 0; i + 1 < W; ++i) {
+			tri2(k + 6 * i, pa[i], pa[i + 1], ca[i + 1], pa[i], ca[i + 1], ca[i]);
+		}
+	}
+	__device__ __forceinline__ void I(uint32_t k, uint32_t v) const { idx[k] = (IDX)(v + base); }
+
+	/* NW logical words (2*NW - HALF indices, HALF = the last word carries one index only) at uint16 position k */
+	template<int NW, bool HALF>
+	__device__ __forceinline__ void words(uint32_t k, const uint32_t (&w)[NW]) const
+	{
+		const uint32_t odd = (par + k) & 1u;
+		const uint32_t sel = odd ? 0x5432u : 0x3210u;
+		uint16_t* q = reinterpret_cast<uint16_t*>(idx) + k;
+		uint32_t* wq = reinterpret_cast<uint32_t*>(q + odd);
+#pragma unroll
+		for (int j = 0; j + 1 < NW; ++j) {
+			wq[j] = __byte_perm(w[j], w[j + 1], sel);
+		}
+		if (HALF) {
+			/* even: the lone index follows the words; odd: the first index precedes them (the lone one
+			 * went out as the high half of the last funnel-shifted word) */
+			const uint32_t h = odd ? w[0] : w[NW - 1];
+			q[odd ? 0 : 2 * (NW - 1)] = (uint16_t)h;
+		} else if (odd) {
+			q[0] = (uint16_t)w[0];
+			q[2 * NW - 1] = (uint16_t)(w[NW - 1] >> 16);
+		} else {
+			wq[NW - 1] = w[NW - 1];
+		}
+	}
+	__device__ __forceinline__ void tri(uint32_t k, uint32_t a, uint32_t b, uint32_t c) const
+	{
+		if (sizeof(IDX) == 2) {
+			a += base; b += base; c += base;
+			const uint32_t w[2] = {pk16(a, b), c};
+			words<2, true>(k, w);
+		} else {
+			I(k, a);
+			I(k + 1, b);
+			I(k + 2, c);
+		}
+	}
+	__device__ __forceinline__ void tri2(uint32_t k, uint32_t a, uint32_t b, uint32_t c, uint32_t d, uint32_t e, uint32_t f) const
+	{
+		if (sizeof(IDX) == 2) {
+			a += base; b += base; c += base; d += base; e += base; f += base;
+			const uint32_t w[3] = {pk16(a, b), pk16(c, d), pk16(e, f)};
+			words<3, false>(k, w);
+		} else {
+			I(k, a);
+			I(k + 1, b);
+			I(k + 2, c);
+			I(k + 3, d);
+			I(k + 4, e);
+			I(k + 5, f);
+		}
+	}
+	/* 18 indices: p.x,p.y,c.y | p.x,c.y,c.x | p.y,p.z,c.z | p.y,c.z,c.y | p.z,p.w,c.w | p.z,c.w,c.z */
+	__device__ __forceinline__ void connect(uint32_t k, uint4 p, uint4 c) const
+	{
+		if (sizeof(IDX) == 2) {
+			p.x += base; p.y += base; p.z += base; p.w += base;
+			c.x += base; c.y += base; c.z += base; c.w += base;
+			const uint32_t w[9] = {pk16(p.x, p.y), pk16(c.y, p.x), pk16(c.y, c.x), pk16(p.y, p.z), pk16(c.z, p.y),
+			                       pk16(c.z, c.y), pk16(p.z, p.w), pk16(c.w, p.z), pk16(c.w, c.z)};
+			words<9, false>(k, w);
+		} else {
+			tri2(k + 0, p.x, p.y, c.y, p.x, c.y, c.x);
+			tri2(k + 6, p.y, p.z, c.z, p.y, c.z, c.y);
+			tri2(k + 12, p.z, p.w, c.w, p.z, c.w, c.z);
+		}
 	}
 };
 
@@ -516,8 +637,7 @@ __device__ __forceinline__ void emitCapAA(const CapRec& R, const SINK& S)
 		const uint32_t q2 = isEnd ? 3u : 1u, q3 = isEnd ? 1u : 3u, r2 = isEnd ? 2u : 3u, r3 = isEnd ? 3u : 2u;
 		for (uint32_t i = 0; i < n - 1; ++i, k += 6) {
 			const uint32_t b = F + 2 * i;
-			S.tri(k, b, b + q2, b + q3);
-			S.tri(k + 3, b, b + r2, b + r3);
+			S.tri2(k, b, b + q2, b + q3, b, b + r2, b + r3);
 		}
 		return;
 	}
@@ -536,11 +656,9 @@ __device__ __forceinline__ void emitCapAA(const CapRec& R, const SINK& S)
 	}
 	if (isEnd) {
 		S.connect(0, R.prev, make_uint4(F, F + 1, F + 2, F + 3));
-		S.tri(18, F, F + 1, F + 2);
-		S.tri(21, F, F + 2, F + 3);
+		S.tri2(18, F, F + 1, F + 2, F, F + 2, F + 3);
 	} else {
-		S.tri(0, F, F + 2, F + 1);
-		S.tri(3, F, F + 3, F + 2);
+		S.tri2(0, F, F + 2, F + 1, F, F + 3, F + 2);
 	}
 }
 
@@ -608,8 +726,7 @@ __device__ __forceinline__ void emitJoinAA(const JobCtx& J, const Piece& P, uint
 		const uint32_t u2 = left ? 0u : 2u, u3 = left ? 2u : 0u, w2 = left ? 1u : 3u, w3 = left ? 3u : 1u, x2 = left ? 3u : 2u, x3 = left ? 2u : 3u;
 		for (uint32_t i = 0; i < n; ++i, k += 9, A += 2) {
 			S.tri(k, F + 1, A + u2, A + u3);
-			S.tri(k + 3, A, A + w2, A + w3);
-			S.tri(k + 6, A, A + x2, A + x3);
+			S.tri2(k + 3, A, A + w2, A + w3, A, A + x2, A + x3);
 		}
 	}
 	if (P.flags & PF_CLOSING) {
@@ -725,8 +842,7 @@ __device__ __forceinline__ void emitStrokeAA(const JobCtx& J, const Piece& P, ui
 		if (i < fanN) {
 			S.tri(k0, a0, B + c0b, B + c0c);
 		}
-		S.tri(k1, B, B + c1b, B + c1c);
-		S.tri(k1 + 3, B, B + c2b, B + c2c);
+		S.tri2(k1, B, B + c1b, B + c1c, B, B + c2b, B + c2c);
 	}
 	if (!isCap && (P.flags & PF_CLOSING)) {
 		S.connect(k + 9 * n, out4FromTail(0, jt, packTail(P), F + P.vcount), joinIn4(firstLeft, 0));
@@ -764,11 +880,9 @@ __device__ __forceinline__ void emitFillVtx(const JobCtx& J, const Piece& P, con
 	S.VP(0, P.p.x + ex, P.p.y + ey, J.color, P.p.x - ex, P.p.y - ey, J.c0);
 	const uint32_t f = 2 * P.li;
 	if (P.li + 1 < J.N) {
-		S.tri(0, f, f + 1, f + 3);
-		S.tri(3, f, f + 3, f + 2);
+		S.tri2(0, f, f + 1, f + 3, f, f + 3, f + 2);
 	} else {
-		S.tri(0, f, f + 1, 1);
-		S.tri(3, f, 1, 0);
+		S.tri2(0, f, f + 1, 1, f, 1, 0);
 	}
 }
 /* ---- plain / thin ribbons: hand-over and emission ------------------------------------------ */
