@@ -7,8 +7,12 @@
  * include the reference's own <vg/path.h> / <vg/stroker.h> instead -- the symbols are the same
  * (tests/test_abi.py compares the mangled names with the compiled reference's).
  *
- * Only the hot-path objects are provided.  Concave fills (libtess2) stay on the CPU reference:
- * strokerConcaveFill* are NOT exported here (out of scope).
+ * Concave fills (include/vg/stroker.h:73-85; libtess2 sweep line, inherently serial, out of scope --
+ * SURVEY.md 2 row 5) are exported as well so that src/vg.cpp LINKS unchanged (its call sites:
+ * vg.cpp:3133-3155, 3246-3264, 3357-3379): Begin/AddContour record nothing and End/EndAA return false
+ * with an empty mesh, which is the reference's own "decomposition failed" result -- vg.cpp:3158-3159,
+ * 3266, 3381 then skip the draw.  A build that needs concave fills keeps src/stroker.cpp's concave
+ * half + libtess2 on the CPU.
  */
 #ifndef VGB_DROPIN_HPP
 #define VGB_DROPIN_HPP
@@ -35,6 +39,7 @@ typedef uint32_t Color;
 struct LineCap { enum Enum : uint32_t { Butt = 0, Round = 1, Square = 2 }; };
 struct LineJoin { enum Enum : uint32_t { Miter = 0, Round = 1, Bevel = 2 }; };
 struct Winding { enum Enum : uint32_t { CCW = 0, CW = 1 }; };
+struct FillRule { enum Enum : uint32_t { NonZero = 0, EvenOdd = 1 }; };
 struct Mesh
 {
 	const float* m_PosBuffer;
@@ -85,6 +90,10 @@ void strokerPolylineStrokeAA(Stroker* stroker, Mesh* mesh, const float* vertexLi
 void strokerPolylineStrokeAAThin(Stroker* stroker, Mesh* mesh, const float* vertexList, uint32_t numVertices, bool isClosed, Color color, LineCap::Enum lineCap, LineJoin::Enum lineJoin);
 void strokerConvexFill(Stroker* stroker, Mesh* mesh, const float* vertexList, uint32_t numVertices);
 void strokerConvexFillAA(Stroker* stroker, Mesh* mesh, const float* vertexList, uint32_t numVertices, uint32_t color);
+bool strokerConcaveFillBegin(Stroker* stroker);
+void strokerConcaveFillAddContour(Stroker* stroker, const float* vertexList, uint32_t numVertices);
+bool strokerConcaveFillEnd(Stroker* stroker, Mesh* mesh, FillRule::Enum fillRule);
+bool strokerConcaveFillEndAA(Stroker* stroker, Mesh* mesh, uint32_t color, FillRule::Enum fillRule);
 #endif
 }
 

@@ -150,13 +150,27 @@ class _Lib:
         return out
 
 
+# "dropin": ref_capi.cpp linked against libvgb200.so's vg:: symbols instead of the reference's path.cpp +
+# stroker.cpp (the link-level drop-in test; needs a GPU at run time)
+_REF_NAMES = {"scalar": "libvgref.so", "sse": "libvgref_sse.so", "libm": "libvgref_libm.so", "dropin": "libvgref_dropin.so"}
+
+
 class RefLib(_Lib):
     """The compiled reference (oracle/_ref). kind: scalar (golden) | sse | libm."""
     prefix = "vgref"
 
     def __init__(self, kind="scalar"):
-        name = {"scalar": "libvgref.so", "sse": "libvgref_sse.so", "libm": "libvgref_libm.so"}[kind]
-        super().__init__(os.path.join(HERE, "_ref", name))
+        super().__init__(os.path.join(HERE, "_ref", _REF_NAMES[kind]))
+
+    def touch_all(self):
+        """calls every vg::pathXXX / vg::strokerXXX symbol once (ref_capi.cpp:vgref_touch_all) -> 15 counters"""
+        out = np.zeros(15, np.uint32)
+        f = self.lib.vgref_touch_all
+        f.restype = C.c_int
+        rc = f(_p(out, C.c_uint32))
+        if rc != 0:
+            raise RuntimeError(f"vgref_touch_all rc={rc}")
+        return out
 
 
 class OracleLib(_Lib):
@@ -168,5 +182,4 @@ class OracleLib(_Lib):
 
 
 def have_ref(kind="scalar"):
-    name = {"scalar": "libvgref.so", "sse": "libvgref_sse.so", "libm": "libvgref_libm.so"}[kind]
-    return os.path.exists(os.path.join(HERE, "_ref", name))
+    return os.path.exists(os.path.join(HERE, "_ref", _REF_NAMES[kind]))

@@ -97,7 +97,73 @@ uint32_t vgref_variant(void)
 #if defined(BX_SHIM_LIBM) && BX_SHIM_LIBM
 	v |= 2;
 #endif
+#if defined(VGREF_DROPIN) && VGREF_DROPIN
+	v |= 4; /* this file linked against libvgb200.so's vg:: symbols instead of path.cpp + stroker.cpp */
+#endif
 	return v;
+}
+
+/* Calls EVERY symbol of include/vg/path.h:19-38 and include/vg/stroker.h:11-85 once, on a fresh Path /
+ * Stroker pair created through a bx allocator (the link-level drop-in test executes this in the build
+ * that is linked against libvgb200.so).  out[0..7] = points, sub-paths, and V/I of a plain stroke, an AA
+ * stroke, a thin stroke; out[8..11] = V/I of a fan fill and an AA fill; out[12] = concave result bits
+ * (Begin | End << 1 | EndAA << 2), out[13..14] = V/I of the concave AA mesh. */
+int vgref_touch_all(uint32_t* out)
+{
+	vg::Path* p = vg::createPath(&s_alloc);
+	vg::Stroker* s = vg::createStroker(&s_alloc);
+	vg::pathReset(p, 1.0f, 0.25f);
+	vg::strokerReset(s, 1.0f, 0.25f, 1.0f);
+	vg::pathMoveTo(p, 10.0f, 10.0f);
+	vg::pathLineTo(p, 60.0f, 15.0f);
+	vg::pathCubicTo(p, 80.0f, 0.0f, 120.0f, 90.0f, 150.0f, 40.0f);
+	vg::pathQuadraticTo(p, 170.0f, 10.0f, 200.0f, 60.0f);
+	vg::pathArcTo(p, 230.0f, 90.0f, 200.0f, 140.0f, 12.0f);
+	vg::pathClose(p);
+	vg::pathRect(p, 300.0f, 10.0f, 40.0f, 30.0f);
+	vg::pathRoundedRect(p, 300.0f, 60.0f, 80.0f, 50.0f, 9.0f);
+	vg::pathRoundedRectVarying(p, 300.0f, 130.0f, 80.0f, 50.0f, 4.0f, 8.0f, 12.0f, 0.0f);
+	vg::pathCircle(p, 450.0f, 40.0f, 25.0f);
+	vg::pathEllipse(p, 450.0f, 120.0f, 35.0f, 20.0f);
+	vg::pathMoveTo(p, 520.0f, 20.0f);
+	vg::pathArc(p, 560.0f, 60.0f, 30.0f, 0.3f, 2.8f, vg::Winding::CW);
+	const float poly[8] = {600.0f, 10.0f, 640.0f, 30.0f, 620.0f, 70.0f, 590.0f, 50.0f};
+	vg::pathMoveTo(p, 600.0f, 10.0f);
+	vg::pathPolyline(p, poly, 4);
+	const float* v = vg::pathGetVertices(p);
+	const uint32_t nv = vg::pathGetNumVertices(p);
+	const vg::SubPath* sp = vg::pathGetSubPaths(p);
+	const uint32_t ns = vg::pathGetNumSubPaths(p);
+	out[0] = nv;
+	out[1] = ns;
+	vg::Mesh m;
+	const float* v0 = v + 2 * (size_t)sp[0].m_FirstVertexID;
+	const uint32_t n0 = sp[0].m_NumVertices;
+	vg::strokerPolylineStroke(s, &m, v0, n0, sp[0].m_IsClosed, 5.0f, vg::LineCap::Round, vg::LineJoin::Round);
+	out[2] = m.m_NumVertices; out[3] = m.m_NumIndices;
+	vg::strokerPolylineStrokeAA(s, &m, v0, n0, sp[0].m_IsClosed, 0xFF2040FFu, 5.0f, vg::LineCap::Square, vg::LineJoin::Bevel);
+	out[4] = m.m_NumVertices; out[5] = m.m_NumIndices;
+	vg::strokerPolylineStrokeAAThin(s, &m, v0, n0, sp[0].m_IsClosed, 0xFF2040FFu, vg::LineCap::Butt, vg::LineJoin::Miter);
+	out[6] = m.m_NumVertices; out[7] = m.m_NumIndices;
+	const float* v2 = v + 2 * (size_t)sp[2].m_FirstVertexID; /* the rounded rect: convex */
+	vg::strokerConvexFill(s, &m, v2, sp[2].m_NumVertices);
+	out[8] = m.m_NumVertices; out[9] = m.m_NumIndices;
+	vg::strokerConvexFillAA(s, &m, v2, sp[2].m_NumVertices, 0xFF00FF00u);
+	out[10] = m.m_NumVertices; out[11] = m.m_NumIndices;
+	uint32_t bits = vg::strokerConcaveFillBegin(s) ? 1u : 0u;
+	vg::strokerConcaveFillAddContour(s, v0, n0);
+	vg::Mesh c;
+	memset(&c, 0, sizeof(c));
+	bits |= vg::strokerConcaveFillEnd(s, &c, vg::FillRule::NonZero) ? 2u : 0u;
+	vg::strokerConcaveFillBegin(s);
+	vg::strokerConcaveFillAddContour(s, v0, n0);
+	memset(&c, 0, sizeof(c));
+	bits |= vg::strokerConcaveFillEndAA(s, &c, 0xFFFFFFFFu, vg::FillRule::EvenOdd) ? 4u : 0u;
+	out[12] = bits;
+	out[13] = c.m_NumVertices; out[14] = c.m_NumIndices;
+	vg::destroyStroker(s);
+	vg::destroyPath(p);
+	return 0;
 }
 
 /* flatten ONE path. returns 0, or -1 on bad command / -5 if a capacity is too small */

@@ -12,9 +12,9 @@ from oracle.pyref import have_ref
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
-# mangled names of include/vg/path.h:19-38 + include/vg/stroker.h:11-70 (generated from the
-# compiled reference with `nm -D oracle/_ref/libvgref.so | grep _ZN2vg`; concave-fill and
-# text entry points are out of scope and not exported by libvgb200)
+# mangled names of include/vg/path.h:19-38 + include/vg/stroker.h:11-85 (generated from the
+# compiled reference with `nm -D oracle/_ref/libvgref.so | grep _ZN2vg`).  The four concave-fill entry
+# points are exported too (they report "not decomposed", see include/vgb_dropin.hpp) so that vg.cpp links.
 VG_SYMBOLS = """
 _ZN2vg10createPathEPN2bx10AllocatorIE _ZN2vg11destroyPathEPNS_4PathE _ZN2vg9pathResetEPNS_4PathEff
 _ZN2vg10pathMoveToEPNS_4PathEff _ZN2vg10pathLineToEPNS_4PathEff _ZN2vg11pathCubicToEPNS_4PathEffffff
@@ -28,6 +28,9 @@ _ZN2vg21strokerPolylineStrokeEPNS_7StrokerEPNS_4MeshEPKfjbfNS_7LineCap4EnumENS_8
 _ZN2vg23strokerPolylineStrokeAAEPNS_7StrokerEPNS_4MeshEPKfjbjfNS_7LineCap4EnumENS_8LineJoin4EnumE
 _ZN2vg27strokerPolylineStrokeAAThinEPNS_7StrokerEPNS_4MeshEPKfjbjNS_7LineCap4EnumENS_8LineJoin4EnumE
 _ZN2vg17strokerConvexFillEPNS_7StrokerEPNS_4MeshEPKfj _ZN2vg19strokerConvexFillAAEPNS_7StrokerEPNS_4MeshEPKfjj
+_ZN2vg23strokerConcaveFillBeginEPNS_7StrokerE _ZN2vg28strokerConcaveFillAddContourEPNS_7StrokerEPKfj
+_ZN2vg21strokerConcaveFillEndEPNS_7StrokerEPNS_4MeshENS_8FillRule4EnumE
+_ZN2vg23strokerConcaveFillEndAAEPNS_7StrokerEPNS_4MeshEjNS_8FillRule4EnumE
 """.split()
 
 
@@ -57,10 +60,27 @@ def test_dropin_symbols_match_reference_mangling():
         ref = exported(os.path.join(ROOT, "oracle", "_ref", "libvgref.so"))
         for s in VG_SYMBOLS:
             assert s in ref, f"{s} is not what the compiled reference exports"
-        # everything path.h / stroker.h declares except the out-of-scope concave entry points
+        # everything path.h / stroker.h declares: all 32 entry points
         ref_vg = {s for s in ref if s.startswith("_ZN2vg") and ("path" in s or "Path" in s or "troker" in s)}
-        missing = {s for s in ref_vg - sym if "Concave" not in s}
+        assert len(VG_SYMBOLS) == 32
+        missing = ref_vg - sym
         assert not missing, missing
+
+
+def test_dropin_link():
+    """LINK-LEVEL drop-in (oracle/Makefile: libvgref_dropin.so): the translation unit that drives the reference
+    through <vg/path.h> / <vg/stroker.h> linked with -z defs against libvgb200.so INSTEAD of path.cpp +
+    stroker.cpp.  The link having succeeded is the test; here: every vg:: symbol it imports is one that
+    libvgb200 exports, and it depends on libvgb200.so, not on the reference build."""
+    path = os.path.join(ROOT, "oracle", "_ref", "libvgref_dropin.so")
+    if not os.path.exists(path):
+        pytest.skip("oracle/_ref/libvgref_dropin.so not built (needs /root/reference and libvgb200.so)")
+    und = subprocess.run(["nm", "-D", "--undefined-only", path], capture_output=True, text=True, check=True).stdout
+    imports = {l.split()[-1] for l in und.splitlines() if "_ZN2vg" in l}
+    assert len(imports) >= 32 and imports <= exported(vgb.lib_path()), imports - exported(vgb.lib_path())
+    assert set(VG_SYMBOLS) <= imports  # vgref_touch_all calls every one of them
+    needed = subprocess.run(["readelf", "-d", path], capture_output=True, text=True).stdout
+    assert "libvgb200.so" in needed and "libvgref.so" not in needed
 
 
 def test_no_oracle_or_reference_linkage():

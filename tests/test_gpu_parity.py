@@ -590,3 +590,23 @@ def test_fuzz_random_paths_and_draws(gpu_batch, ref, seed):
     check_same(gpu_batch.download(), exp)
     gpu_batch.run()  # re-run of the same upload
     check_same(gpu_batch.download(), exp)
+
+
+def test_dropin_linked_build_equals_reference(ref):
+    """Link-level drop-in, EXECUTED: oracle/ref_capi.cpp -- the code that drives vg::pathXXX / vg::strokerXXX the
+    way vg.cpp does -- built a second time against libvgb200.so's vg:: symbols (oracle/Makefile, -z defs) must
+    produce what the build against the reference's own path.cpp + stroker.cpp produces.  Exercises all 32
+    symbols, the bx::AllocatorI bridge (bxRealloc) and the borrowed-view ownership rules."""
+    from oracle.pyref import RefLib, have_ref
+    if not have_ref("dropin"):
+        pytest.skip("oracle/_ref/libvgref_dropin.so not built")
+    d = RefLib("dropin")
+    assert d.variant() & 4 and not ref.variant() & 4
+    a, b = d.touch_all(), ref.touch_all()
+    np.testing.assert_array_equal(a[:12], b[:12])
+    assert a[12] == 0 and a[13] == 0 and a[14] == 0   # concave: reported as not decomposed (vg.cpp skips the draw)
+    assert b[12] & 6                                  # the reference's libtess2 path does decompose it
+    # whole batches through both builds of the same caller
+    for t in (mixed_recorder().tables(), BatchTables.cubic_strokes(W.config3_cubics(300, first=3), width=4.0, cap=1, join=1),
+              BatchTables.rounded_rect_fills(W.config4_rrects(50, 32))):
+        check_same(d.run_batch(t), ref.run_batch(t))

@@ -560,18 +560,20 @@ __global__ void k_job_pieces(const uint32_t* __restrict__ jobSub, const uint32_t
 	jobPieces[j] = pieceCount(draws[jobDraw[j]].ocj & 0xFF, subNum[jobSub[j]]);
 }
 
-/* per job: the 48-byte record the piece kernels read, and the job id of each of its pieces.
- * One warp handles 32 jobs; for every job of the warp all 32 lanes write its piece range, so the
- * pieceJob stores are coalesced whatever the job lengths are. */
+/* per job: the 48-byte record the piece kernels read, and for each of its pieces the record
+ * {job id, index of the piece's own polyline vertex in pts[]} -- with the point index in hand a piece
+ * kernel starts the job-record load and the point load together (one dependent round trip less than
+ * piece -> job record -> points).  One warp handles 32 jobs; for every job of the warp all 32 lanes
+ * write its piece range, so the stores are coalesced whatever the job lengths are. */
 __global__ void __launch_bounds__(256) k_job_prep(const uint32_t* __restrict__ jobSub, const uint32_t* __restrict__ jobDraw, uint32_t numJobs,
                                                   const uint32_t* __restrict__ subFirst, const uint32_t* __restrict__ subNum,
                                                   const uint8_t* __restrict__ subClosed, const DrawDerived* __restrict__ dd,
                                                   const uint32_t* __restrict__ pieceStart, JobRec* __restrict__ jobRec,
-                                                  uint32_t* __restrict__ pieceJob)
+                                                  uint2* __restrict__ pieceRec)
 {
 	const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
 	const uint32_t lane = threadIdx.x & 31;
-	uint32_t ps = 0, pe = 0;
+	uint32_t ps = 0, pe = 0, first = 0, fan = 0;
 	if (j < numJobs) {
 		const uint32_t sp = jobSub[j];
 		const DrawDerived d = dd[jobDraw[j]];
@@ -582,6 +584,9 @@ __global__ void __launch_bounds__(256) k_job_prep(const uint32_t* __restrict__ j
 		r.flags = (uint32_t)(subClosed[sp] & 1) | (((d.ocj >> 24) & 1u) << 1) | (op << 8) | (cap << 16) | (join << 24);
 		ps = pieceStart[j];
 		pe = pieceStart[j + 1];
+		first = r.first;
+		/* fills: N-2 fan-triangle pieces (no vertex of their own) precede the N vertex pieces */
+		fan = (op == VGB_OP_CONVEX_FILL_AA || op == VGB_OP_CONVEX_FILL) && r.N >= 2 ? r.N - 2 : 0u;
 		r.pieceStart = ps;
 		r.hsw = d.hsw;
 		r.hsw_aa = d.hsw_aa;
@@ -597,8 +602,13 @@ __global__ void __launch_bounds__(256) k_job_prep(const uint32_t* __restrict__ j
 	for (uint32_t l = 0; l < 32; ++l) {
 		const uint32_t s0 = __shfl_sync(0xffffffffu, ps, l);
 		const uint32_t e0 = __shfl_sync(0xffffffffu, pe, l);
-		for (uint32_t k = s0 + lane; k < e0; k += 32) {
-			pieceJob[k] = jw + l;
+		if (e0 > s0) {
+			const uint32_t f0 = __shfl_sync(0xffffffffu, first, l);
+			const uint32_t n0 = __shfl_sync(0xffffffffu, fan, l);
+			for (uint32_t k = s0 + lane; k < e0; k += 32) {
+				const uint32_t q = k - s0;
+				pieceRec[k] = make_uint2(jw + l, f0 + (q >= n0 ? q - n0 : 0u));
+			}
 		}
 	}
 }
@@ -606,7 +616,7 @@ __global__ void __launch_bounds__(256) k_job_prep(const uint32_t* __restrict__ j
 struct PieceArgs
 {
 	uint32_t numPieces, numJobs;
-	const uint32_t* pieceJob; /* per piece */
+	const uint2* pieceRec;    /* per piece: {job, index of its polyline vertex} */
 	const JobRec* jobRec;     /* per job   */
 	const float2* pts;
 	/* count outputs */
@@ -784,6 +794,19 @@ static constexpr uint32_t CIW_COUNT = VGB_CIW;           /* staged indices per w
 
 __device__ __forceinline__ uint2 warpInclusive(uint2 v, uint32_t lane)
 {
+	/* both components in one word when no carry can cross (32 x 1023 < 2^16, 32 x 2047 < 2^16): one shuffle
+	 * and one add per step; fat pieces (wide strokes: long round caps / joins) take the two-component scan */
+	if (__all_sync(0xffffffffu, v.x <= 1023u && v.y <= 2047u)) {
+		uint32_t x = v.x | (v.y << 16);
+#pragma unroll
+		for (int d = 1; d < 32; d <<= 1) {
+			const uint32_t y = __shfl_up_sync(0xffffffffu, x, d);
+			if (lane >= (uint32_t)d) {
+				x += y;
+			}
+		}
+		return make_uint2(x & 0xFFFFu, x >> 16);
+	}
 #pragma unroll
 	for (int d = 1; d < 32; d <<= 1) {
 		const uint32_t x = __shfl_up_sync(0xffffffffu, v.x, d);
@@ -798,7 +821,7 @@ __device__ __forceinline__ uint2 warpInclusive(uint2 v, uint32_t lane)
 
 /* mesh table: (first vertex, first index) of job j = base of the group holding its first piece +
  * the within-group offset recorded by k_group_count; an empty job starts where the next piece starts */
-__global__ void k_mesh_off(const uint32_t* __restrict__ pieceStart, const uint32_t* __restrict__ pieceJob, uint32_t numJobs, uint32_t numPieces,
+__global__ void k_mesh_off(const uint32_t* __restrict__ pieceStart, const uint2* __restrict__ pieceRec, uint32_t numJobs, uint32_t numPieces,
                            uint32_t numGroups, const ulonglong2* __restrict__ groupBase, const uint2* __restrict__ meshLocal,
                            ulonglong2* __restrict__ meshOff)
 {
@@ -809,7 +832,7 @@ __global__ void k_mesh_off(const uint32_t* __restrict__ pieceStart, const uint32
 	if (g >= numPieces) {
 		o = groupBase[numGroups];
 	} else {
-		const uint2 l = meshLocal[pieceJob[g]];
+		const uint2 l = meshLocal[pieceRec[g].x];
 		o = groupBase[g >> 5];
 		o.x += l.x;
 		o.y += l.y;
@@ -980,6 +1003,99 @@ __global__ void k_replay_indices(const W* __restrict__ src, uint64_t I, uint64_t
 	}
 }
 
+/* ---- the polyline window of a warp: 32 consecutive pieces = (mostly) 32 consecutive points ----------
+ * Every lane loads ONLY its own point; its neighbours come from the adjacent lanes by shuffle when
+ * those hold the neighbouring piece of the same job.  What shuffles cannot give: the point before
+ * lane 0's and after lane 31's (loaded speculatively together with the lane's own point: `edge`) and
+ * the wrap-around neighbours of a closed polyline's first / last piece (a dependent load, rare). */
+struct Window
+{
+	float2 pm, pn;
+	bool linkedPrev; /* lane-1 holds this piece's predecessor */
+};
+
+__device__ __forceinline__ float2 shflUp2(float2 v)
+{
+	return make_float2(__shfl_up_sync(0xffffffffu, v.x, 1), __shfl_up_sync(0xffffffffu, v.y, 1));
+}
+__device__ __forceinline__ float2 shflDown2(float2 v)
+{
+	return make_float2(__shfl_down_sync(0xffffffffu, v.x, 1), __shfl_down_sync(0xffffffffu, v.y, 1));
+}
+__device__ __forceinline__ float2 shflIdx2(float2 v, int src)
+{
+	return make_float2(__shfl_sync(0xffffffffu, v.x, src), __shfl_sync(0xffffffffu, v.y, src));
+}
+
+/* the speculative edge load: lane 0's previous point, lane 31's next point (same address as the own
+ * point for every other lane, so it costs one predicated load) */
+__device__ __forceinline__ float2 loadEdge(const float2* __restrict__ pts, uint32_t pt, float2 p, uint32_t lane)
+{
+	float2 e = p;
+	if (lane == 0 || lane == 31) {
+		e = pts[lane == 0 ? (pt ? pt - 1 : 0u) : pt + 1];
+	}
+	return e;
+}
+
+/* all 32 lanes must call this (shuffles); results are meaningful for valid stroke pieces only */
+__device__ __forceinline__ Window windowOf(const float2* __restrict__ pts, const JobCtx& J, uint32_t j, uint32_t q, bool valid, float2 p, float2 edge,
+                                           uint32_t lane)
+{
+	const uint32_t jm = __shfl_up_sync(0xffffffffu, j, 1), jn = __shfl_down_sync(0xffffffffu, j, 1);
+	const unsigned vmask = __ballot_sync(0xffffffffu, valid);
+	Window w;
+	w.linkedPrev = valid && lane > 0 && jm == j;
+	const bool linkedNext = valid && lane < 31 && ((vmask >> (lane + 1)) & 1u) && jn == j;
+	const float2 pmS = shflUp2(p), pnS = shflDown2(p);
+	const uint32_t N = J.N;
+	w.pm = w.linkedPrev ? pmS : ((lane == 0 && q > 0) ? edge : p);
+	w.pn = linkedNext ? pnS : ((lane == 31 && q + 1 < N) ? edge : p);
+	if (valid && J.closed) {
+		const float2* v = pts + J.first;
+		if (q == 0) w.pm = v[N - 1];
+		if (q == N - 1) w.pn = v[0];
+	}
+	return w;
+}
+
+/* AA-stroke pieces of a whole warp: each lane computes ONE segment direction (its outgoing one) and takes
+ * the incoming one from the lane before it.  The direction nobody owns -- into lane 0's point, or into a
+ * closed polyline's first point -- is computed by a lane that has no outgoing segment of its own (an end
+ * cap, or a lane past the end); only when the warp has no such lane, or more than one orphan, do the
+ * orphans compute theirs separately.  Bit-identical to two vdir() per lane: same inputs, same function. */
+template<int JT, int CT>
+__device__ __forceinline__ Piece classifyWarpAA(const float2* __restrict__ pts, const JobCtx& J, uint32_t j, uint32_t q, bool valid, float2 p, float2 edge,
+                                                uint32_t lane)
+{
+	const Window w = windowOf(pts, J, j, q, valid, p, edge, lane);
+	const bool open = !J.closed;
+	const bool needA = valid && !(open && q == 0);
+	const bool needB = valid && !(open && q == J.N - 1);
+	const bool orphan = needA && !w.linkedPrev;
+	const unsigned om = __ballot_sync(0xffffffffu, orphan), fm = __ballot_sync(0xffffffffu, !needB);
+	const bool have = om != 0 && fm != 0; /* warp-uniform */
+	const int o = __ffs(om) - 1, f = __ffs(fm) - 1;
+	float2 x0 = p, x1 = w.pn;
+	if (have) {
+		const float2 a = shflIdx2(w.pm, o), b = shflIdx2(p, o);
+		if ((int)lane == f) {
+			x0 = a;
+			x1 = b;
+		}
+	}
+	const float2 d = vdir(x0, x1);
+	float2 dA = shflUp2(d);
+	if (have) {
+		const float2 t = shflIdx2(d, f);
+		if ((int)lane == o) dA = t;
+	}
+	if (orphan && !(have && (int)lane == o)) {
+		dA = vdir(w.pm, p);
+	}
+	return classifyStrokeAA<JT, CT>(J, q, p, dA, d);
+}
+
 /* each warp counts GC consecutive groups; the loads of all of them are issued before any is used
  * (the kernel is a chain of dependent loads: piece -> job record -> points) */
 #ifndef VGB_GC
@@ -995,43 +1111,37 @@ __global__ void __launch_bounds__(128, VGB_COUNT_MIN_BLOCKS) k_group_count(Piece
 {
 	const uint32_t lane = threadIdx.x & 31;
 	const uint32_t w0 = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * GC;
-	uint32_t g[GC], j[GC], ps[GC];
+	uint32_t g[GC], ps[GC];
+	uint2 rec[GC];
 	bool valid[GC];
 	JobCtx J[GC];
-	float2 pm[GC], pc[GC], pn[GC];
+	float2 pc[GC], pe[GC];
 #pragma unroll
 	for (uint32_t k = 0; k < GC; ++k) {
 		g[k] = (w0 + k) * 32 + lane;
 		valid[k] = g[k] < a.numPieces;
-		j[k] = valid[k] ? a.pieceJob[g[k]] : 0u;
+		rec[k] = valid[k] ? a.pieceRec[g[k]] : make_uint2(0u, 0u);
 	}
 #pragma unroll
 	for (uint32_t k = 0; k < GC; ++k) {
 		ps[k] = 0;
-		if (valid[k]) {
-			J[k] = loadJob(a, j[k], &ps[k]);
-		}
-	}
-#pragma unroll
-	for (uint32_t k = 0; k < GC; ++k) {
-		pm[k] = pc[k] = pn[k] = make_float2(0.0f, 0.0f);
-		if (valid[k] && ((OPS & OPS_STROKE_AA) && (!(OPS & ~OPS_STROKE_AA) || J[k].op == VGB_OP_STROKE_AA))) {
-			const uint32_t q = g[k] - ps[k], N = J[k].N;
-			const float2* v = a.pts + J[k].first;
-			pm[k] = v[q > 0 ? q - 1 : N - 1];
-			pc[k] = v[q];
-			pn[k] = v[q < N - 1 ? q + 1 : 0u];
-		}
+		J[k] = loadJob(a, rec[k].x, &ps[k]);
+		pc[k] = a.pts[rec[k].y];
+		pe[k] = loadEdge(a.pts, rec[k].y, pc[k], lane);
 	}
 #pragma unroll
 	for (uint32_t k = 0; k < GC; ++k) {
 		const uint32_t w = w0 + k;
+		const uint32_t q = g[k] - ps[k];
+		const bool aa = (OPS & OPS_STROKE_AA) && (!(OPS & ~OPS_STROKE_AA) || J[k].op == VGB_OP_STROKE_AA);
+		Window win;
+		if (OPS & OPS_STROKE_AA) {
+			win = windowOf(a.pts, J[k], rec[k].x, q, valid[k] && aa, pc[k], pe[k], lane);
+		}
 		uint32_t vc = 0, ic = 0, tail = 0;
 		if (valid[k]) {
 			Piece P;
-			const uint32_t q = g[k] - ps[k];
-			if (!((OPS & OPS_STROKE_AA) && (!(OPS & ~OPS_STROKE_AA) || J[k].op == VGB_OP_STROKE_AA) &&
-			      quickCountAA<JT, CT>(J[k], q, pm[k], pc[k], pn[k], lane == 31, P))) {
+			if (!(aa && quickCountAA<JT, CT>(J[k], q, win.pm, pc[k], win.pn, lane == 31, P))) {
 				P = classify<OPS, JT, CT>(J[k], q, a.pts);
 			}
 			vc = P.vcount;
@@ -1042,7 +1152,7 @@ __global__ void __launch_bounds__(128, VGB_COUNT_MIN_BLOCKS) k_group_count(Piece
 		 * inside its group; k_mesh_off adds the group base after the scan (no atomics, no per-mesh scan) */
 		const uint2 inc = warpInclusive(make_uint2(vc, ic), lane);
 		if (valid[k] && g[k] == ps[k]) {
-			a.meshTotals[j[k]] = make_uint2(inc.x - vc, inc.y - ic);
+			a.meshTotals[rec[k].x] = make_uint2(inc.x - vc, inc.y - ic);
 		}
 		const uint32_t tv = __shfl_sync(0xffffffffu, inc.x, 31);
 		const uint32_t ti = __shfl_sync(0xffffffffu, inc.y, 31);
@@ -1072,18 +1182,61 @@ __global__ void __launch_bounds__(128, (OPS == OPS_STROKE_AA && JT < 3) ? VGB_EM
 	static_assert(POS_BYTES % 16 == 0 && COL_BYTES % 16 == 0 && IDX_BYTES % 16 == 0, "16-byte aligned staging streams");
 	__shared__ __align__(16) uint8_t sStage[4 * WBYTES];
 
+	/* PERSISTENT warps: warp w of the grid takes groups w, w + W, w + 2W ...  What the NEXT group needs is
+	 * fetched while the current one is being emitted: its piece records travel in registers two groups
+	 * ahead (recB), and with the records of the group one ahead (recA) in hand the lines of its points, job
+	 * records, group base, hand-over word and mesh offsets are pulled into L2 -- so the dependent chain
+	 * piece record -> {job record, point} that every group used to wait for at its head is an L2 hit.
+	 * The wait for the previous group's bulk copy (its reads of the staging image) sits right before
+	 * the image is written again, i.e. the copy-out of group t overlaps the classification of t + 1. */
 	const uint32_t lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-	const uint32_t w = blockIdx.x * 4 + wib;
-	const uint32_t g = w * 32 + lane;
-	if (w * 32 >= a.numPieces) {
+	const uint32_t W = gridDim.x * 4;
+	const uint32_t numGroups = (a.numPieces + 31) >> 5;
+	uint32_t w = blockIdx.x * 4 + wib;
+	if (w >= numGroups) {
 		return; /* whole warp out of range */
 	}
+	uint8_t* stage = sStage + wib * WBYTES;
+	float2* sPos = reinterpret_cast<float2*>(stage);
+	uint32_t* sCol = reinterpret_cast<uint32_t*>(stage + POS_BYTES);
+	IDX* sIdx = reinterpret_cast<IDX*>(stage + POS_BYTES + COL_BYTES);
+	bool copyPending = false;
+	uint2 recA = make_uint2(0u, 0u), recB = make_uint2(0u, 0u);
+	{
+		const uint32_t g0 = w * 32 + lane;
+		if (g0 < a.numPieces) recA = a.pieceRec[g0];
+		const uint32_t g1 = g0 + W * 32;
+		if (w + W < numGroups && g1 < a.numPieces) recB = a.pieceRec[g1];
+	}
+	for (; w < numGroups; w += W) {
+	const uint32_t g = w * 32 + lane;
 	const bool valid = g < a.numPieces;
-	const uint32_t j = valid ? a.pieceJob[g] : 0;
+	const uint2 rec = recA;
+	const uint32_t j = rec.x;
+	recA = recB;
+	{
+		/* records of the group two ahead; L2 prefetch for the group one ahead */
+		const uint32_t w1 = w + W, w2 = w + 2 * W;
+		const uint32_t g2 = w2 * 32 + lane;
+		recB = make_uint2(0u, 0u);
+		if (w2 < numGroups && g2 < a.numPieces) recB = a.pieceRec[g2];
+#if VGB_EMIT_PREFETCH
+		if (w1 < numGroups) {
+			if (w1 * 32 + lane < a.numPieces) {
+				asm volatile("prefetch.global.L2 [%0];" ::"l"(a.pts + recA.y));
+				asm volatile("prefetch.global.L2 [%0];" ::"l"(a.jobRec + recA.x));
+				asm volatile("prefetch.global.L2 [%0];" ::"l"(a.meshOff + recA.x));
+			}
+			if (lane == 0) {
+				asm volatile("prefetch.global.L2 [%0];" ::"l"(a.blockBase + w1));
+				asm volatile("prefetch.global.L2 [%0];" ::"l"(a.blockTail + (w1 - 1)));
+			}
+		}
+#endif
+	}
 #if VGB_EMIT_PREFETCH
 	/* the group base, the previous group's hand-over word and the mesh offsets are only needed after the
-	 * pieces are classified: start those loads now (into L1, no registers held) so that their latency
-	 * runs under the piece -> job record -> points chain instead of after it */
+	 * pieces are classified: start those loads now (into L1, no registers held) */
 	if (lane == 0) {
 		asm volatile("prefetch.global.L1 [%0];" ::"l"(a.blockBase + w));
 		if (w > 0) asm volatile("prefetch.global.L1 [%0];" ::"l"(a.blockTail + (w - 1)));
@@ -1094,15 +1247,30 @@ __global__ void __launch_bounds__(128, (OPS == OPS_STROKE_AA && JT < 3) ? VGB_EM
 #endif
 	JobCtx J;
 	Piece P;
-	P.kind = PK_NONE;
-	P.vcount = P.icount = 0;
-	P.flags = 0;
 	uint32_t q = 0;
-	if (valid) {
+	if (OPS == OPS_STROKE_AA) {
+		/* pure AA-stroke batch: one point load per lane, neighbours and segment directions by shuffle */
 		uint32_t ps;
+		const float2 p = a.pts[rec.y];
+		const float2 edge = loadEdge(a.pts, rec.y, p, lane);
 		J = loadJob(a, j, &ps);
 		q = g - ps;
-		P = classify<OPS, JT, CT>(J, q, a.pts);
+		P = classifyWarpAA<JT, CT>(a.pts, J, j, q, valid, p, edge, lane);
+		if (!valid) {
+			P.kind = PK_NONE;
+			P.vcount = P.icount = 0;
+			P.flags = 0;
+		}
+	} else {
+		P.kind = PK_NONE;
+		P.vcount = P.icount = 0;
+		P.flags = 0;
+		if (valid) {
+			uint32_t ps;
+			J = loadJob(a, j, &ps);
+			q = g - ps;
+			P = classify<OPS, JT, CT>(J, q, a.pts);
+		}
 	}
 	const uint32_t myTail = valid ? packTail(P) : 0u;
 	uint32_t tw = __shfl_up_sync(0xffffffffu, myTail, 1);
@@ -1131,10 +1299,13 @@ __global__ void __launch_bounds__(128, (OPS == OPS_STROKE_AA && JT < 3) ? VGB_EM
 	const bool fits = totV <= CVW && totI <= CIW; /* warp-uniform */
 	if (fits) {
 		/* the staging image: typed shared-memory stores, packed index words */
-		uint8_t* stage = sStage + wib * WBYTES;
-		float2* sPos = reinterpret_cast<float2*>(stage);
-		uint32_t* sCol = reinterpret_cast<uint32_t*>(stage + POS_BYTES);
-		IDX* sIdx = reinterpret_cast<IDX*>(stage + POS_BYTES + COL_BYTES);
+		if (copyPending) {
+			/* the previous group's bulk copies must have READ the image before it is overwritten */
+			if (lane == 0 || lane == 2 || lane == 8) {
+				bulkWaitRead();
+			}
+			__syncwarp();
+		}
 		SinkS<IDX, !(OPS & OPS_OTHER)> S;
 		S.base = idxBase;
 		S.pos = sPos + (uint32_t)(bb.x & 1) + vl;
@@ -1147,9 +1318,7 @@ __global__ void __launch_bounds__(128, (OPS == OPS_STROKE_AA && JT < 3) ? VGB_EM
 		fenceProxyAsync();
 		__syncwarp();
 		copyOutWarp3<IDX>(a.pos, a.col, reinterpret_cast<IDX*>(a.idx), bb.x, bb.y, totV, totI, sPos, sCol, sIdx, lane);
-		if (lane == 0 || lane == 2 || lane == 8) {
-			bulkWaitRead();
-		}
+		copyPending = true;
 	} else if (valid) {
 		/* a warp whose pieces exceed the staging image writes straight to HBM */
 		Sink<IDX, !(OPS & OPS_OTHER)> S;
@@ -1159,6 +1328,10 @@ __global__ void __launch_bounds__(128, (OPS == OPS_STROKE_AA && JT < 3) ? VGB_EM
 		S.col = a.col + bb.x + vl;
 		S.idx = reinterpret_cast<IDX*>(a.idx) + bb.y + il;
 		emitAnyCold<OPS, JT, CT>(a.pts, J, P, F, prev, S);
+	}
+	} /* groups of this warp */
+	if (copyPending && (lane == 0 || lane == 2 || lane == 8)) {
+		bulkWaitRead(); /* the image must outlive its bulk copies */
 	}
 }
 
@@ -1185,7 +1358,7 @@ __global__ void __launch_bounds__(256) k_fill_emit(PieceArgs a)
 {
 	const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
 	if (g >= a.numPieces) return;
-	const uint32_t j = a.pieceJob[g];
+	const uint32_t j = a.pieceRec[g].x;
 	uint32_t ps;
 	const JobCtx J = loadJob(a, j, &ps);
 	const uint32_t i = g - ps, N = J.N;
@@ -1450,6 +1623,27 @@ public:
 		return 0;
 	}
 
+	/* the emit kernel is persistent: as many blocks as the device holds at once (occupancy x SMs x VGB_EMIT_WAVES,
+	 * default 1), each warp striding over the groups */
+	int numSMs = 0;
+	template<class IDX, uint32_t OPS, int JT, int CT, bool BIGI>
+	void launchEmit(const PieceArgs& pa, uint32_t gridBlocks)
+	{
+		static int perSM = 0;
+		static int waves = 0;
+		if (perSM == 0) {
+			if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_group_emit<IDX, OPS, JT, CT, BIGI>, (int)PPB, 0) != cudaSuccess || perSM < 1) perSM = 8;
+			const char* e = getenv("VGB_EMIT_WAVES");
+			waves = e ? atoi(e) : 1;
+			if (waves < 1) waves = 1;
+		}
+		if (numSMs == 0) {
+			if (cudaDeviceGetAttribute(&numSMs, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || numSMs < 1) numSMs = 148;
+		}
+		const uint32_t cap = (uint32_t)perSM * (uint32_t)numSMs * (uint32_t)waves;
+		k_group_emit<IDX, OPS, JT, CT, BIGI><<<gridBlocks < cap ? gridBlocks : cap, PPB, 0, st>>>(pa);
+	}
+
 	int run(uint32_t flags, uint64_t vertexBase, std::string* err) override
 	{
 		if (!uploaded) {
@@ -1603,17 +1797,17 @@ public:
 		PieceArgs pa;
 		memset(&pa, 0, sizeof(pa));
 		if (numPieces) {
-			if (dJobRec.ensure((size_t)numJobs * sizeof(JobRec), err) || dPieceJob.ensure((size_t)numPieces * 4, err) ||
+			if (dJobRec.ensure((size_t)numJobs * sizeof(JobRec), err) || dPieceJob.ensure((size_t)numPieces * 8, err) ||
 			    dBlockTotals.ensure((size_t)numBlocks * 8, err) || dBlockBase.ensure((size_t)(numBlocks + 1) * 16, err) ||
 			    dMeshTotals.ensure((size_t)numJobs * 8, err) || dBlockTail.ensure((size_t)numBlocks * 4, err))
 				return VGB_ERR_CUDA;
 			k_job_prep<<<(numJobs + 255) / 256, 256, 0, st>>>(dJobSub.as<uint32_t>(), dJobDraw.as<uint32_t>(), numJobs, dSubFirst.as<uint32_t>(),
 			                                                   dSubNum.as<uint32_t>(), dSubClosed.as<uint8_t>(), dDD.as<DrawDerived>(),
-			                                                   dPieceStart.as<uint32_t>(), dJobRec.as<JobRec>(), dPieceJob.as<uint32_t>());
+			                                                   dPieceStart.as<uint32_t>(), dJobRec.as<JobRec>(), dPieceJob.as<uint2>());
 			++launches;
 			pa.numPieces = numPieces;
 			pa.numJobs = numJobs;
-			pa.pieceJob = dPieceJob.as<uint32_t>();
+			pa.pieceRec = dPieceJob.as<uint2>();
 			pa.jobRec = dJobRec.as<JobRec>();
 			pa.pts = dPts.as<float2>();
 			pa.blockTail = dBlockTail.as<uint32_t>();
@@ -1636,7 +1830,7 @@ public:
 #undef VGB_COUNT_K
 			++launches;
 			if (scan<ScanOps<uint2>>(dBlockTotals.as<uint2>(), numBlocks, dBlockBase.as<ulonglong2>(), err)) return VGB_ERR_CUDA;
-			k_mesh_off<<<(numJobs + 1 + 255) / 256, 256, 0, st>>>(dPieceStart.as<uint32_t>(), dPieceJob.as<uint32_t>(), numJobs, numPieces, numBlocks,
+			k_mesh_off<<<(numJobs + 1 + 255) / 256, 256, 0, st>>>(dPieceStart.as<uint32_t>(), dPieceJob.as<uint2>(), numJobs, numPieces, numBlocks,
 			                                                       dBlockBase.as<ulonglong2>(), dMeshTotals.as<uint2>(), dMeshOff.as<ulonglong2>());
 			++launches;
 			} /* !fillOnly */
@@ -1702,8 +1896,8 @@ public:
 			const bool bigI = idxBytes == 4 ? (numBlocks > 0 && totals[1] / numBlocks > (uint64_t)(CIW_COUNT / 2) * 3 / 4) : finalRan;
 #define VGB_EMIT_K(T, O, J, C)                                                   \
 	do {                                                                         \
-		if (bigI) k_group_emit<T, O, J, C, true><<<gridBlocks, PPB, 0, st>>>(pa); \
-		else k_group_emit<T, O, J, C, false><<<gridBlocks, PPB, 0, st>>>(pa);     \
+		if (bigI) launchEmit<T, O, J, C, true>(pa, gridBlocks);                   \
+		else launchEmit<T, O, J, C, false>(pa, gridBlocks);                       \
 	} while (0)
 #define VGB_LAUNCH_EMIT(T)                                                                                  \
 	do {                                                                                                    \

@@ -66,4 +66,26 @@ VG_EXPORT void strokerPolylineStrokeAAThin(Stroker* stroker, Mesh* mesh, const f
 }
 VG_EXPORT void strokerConvexFill(Stroker* stroker, Mesh* mesh, const float* v, uint32_t n) { vgb_stroker_convex_fill(S(stroker), (vgb_mesh*)mesh, v, n); }
 VG_EXPORT void strokerConvexFillAA(Stroker* stroker, Mesh* mesh, const float* v, uint32_t n, uint32_t color) { vgb_stroker_convex_fill_aa(S(stroker), (vgb_mesh*)mesh, v, n, color); }
+
+/* Concave fills (include/vg/stroker.h:73-85): not tessellated here (libtess2 sweep line: serial, out of
+ * scope).  The symbols exist so that src/vg.cpp links; End/EndAA report the reference's own failure
+ * result (false, empty mesh), on which vg.cpp:3158-3159 (and its siblings near 3266 and 3381) skip the draw. */
+namespace
+{
+inline bool emptyMesh(Mesh* mesh)
+{
+	if (mesh) {
+		mesh->m_PosBuffer = nullptr;
+		mesh->m_ColorBuffer = nullptr;
+		mesh->m_IndexBuffer = nullptr;
+		mesh->m_NumVertices = 0;
+		mesh->m_NumIndices = 0;
+	}
+	return false;
+}
+}
+VG_EXPORT bool strokerConcaveFillBegin(Stroker*) { return false; }
+VG_EXPORT void strokerConcaveFillAddContour(Stroker*, const float*, uint32_t) {}
+VG_EXPORT bool strokerConcaveFillEnd(Stroker*, Mesh* mesh, FillRule::Enum) { return emptyMesh(mesh); }
+VG_EXPORT bool strokerConcaveFillEndAA(Stroker*, Mesh* mesh, uint32_t, FillRule::Enum) { return emptyMesh(mesh); }
 }

@@ -275,10 +275,83 @@ __device__ __forceinline__ bool quickCountAA(const JobCtx& J, uint32_t q, float2
 	return true;
 }
 
+/* AA-stroke piece q of job J from its point and the two segment directions around it (dA: incoming,
+ * dB: outgoing; a start cap ignores dA, an end cap dB).  One code path whatever the piece is. */
+template<int JT, int CT>
+__device__ __forceinline__ Piece classifyStrokeAA(const JobCtx& J, uint32_t q, float2 p, float2 dA, float2 dB)
+{
+	Piece P;
+	P.vcount = 0;
+	P.icount = 0;
+	P.n = 0;
+	P.flags = 0;
+	P.li = q;
+	P.a01 = 0.0f;
+	P.arcDa = 0.0f;
+	P.d12 = P.v = f2(0.0f, 0.0f);
+	P.p = p;
+	const uint32_t N = J.N;
+	const uint32_t ct = CT < 3 ? (uint32_t)CT : J.cap;
+	const uint32_t jt = JT < 3 ? (uint32_t)JT : J.join;
+	const bool open = !J.closed;
+	const bool isStart = open && q == 0, isEnd = open && q == N - 1;
+	const bool isCap = isStart || isEnd;
+	/* with round joins a round cap takes its start angle from the joins' atan2 (same expression) */
+	const bool capRides = isCap && ct == VGB_CAP_ROUND && jt == VGB_JOIN_ROUND;
+	if (isCap) {
+		P.kind = isStart ? PK_CAP_START : PK_CAP_END;
+		P.d01 = isStart ? dB : dA;
+	} else {
+		P.kind = PK_JOIN;
+		P.d01 = dA;
+		P.d12 = dB;
+		if (!(J.closed && q == 0)) {
+			P.flags |= PF_HAS_PREV;
+		}
+		if (J.closed && q == N - 1) {
+			P.flags |= PF_CLOSING;
+		}
+	}
+	if (!isCap || capRides) {
+		classifyJoinAA<JT>(J, P, isCap);
+	}
+	if (isCap) {
+		P.flags = isEnd ? PF_HAS_PREV : 0u;
+		P.d12 = f2(0.0f, 0.0f);
+		P.v = f2(0.0f, 0.0f);
+		P.arcDa = 0.0f;
+		if (ct == VGB_CAP_ROUND) {
+			P.n = J.nHC;
+			P.vcount = 2 * J.nHC;
+			P.icount = isStart ? 9 * J.nHC - 12 : 9 * J.nHC + 6;
+			if (!capRides) {
+				P.a01 = vgb_atan2(P.d01.x, -P.d01.y); /* startAngle = atan2(l.y, l.x), l = perpCCW(d) (1476, 1919) */
+			}
+		} else {
+			P.n = 0;
+			P.a01 = 0.0f;
+			P.vcount = 4;
+			P.icount = isStart ? 6u : 24u;
+		}
+	}
+	return P;
+}
+
 /* the single source of every count decision: piece q of job J */
 template<uint32_t OPS, int JT = 3, int CT = 3>
 __device__ __forceinline__ Piece classify(const JobCtx& J, uint32_t q, const float2* __restrict__ pts)
 {
+	const float2* v = pts + J.first;
+	const uint32_t N = J.N;
+	if ((OPS & OPS_STROKE_AA) && (!(OPS & ~OPS_STROKE_AA) || J.op == VGB_OP_STROKE_AA)) {
+		/* a start cap uses the outgoing direction, an end cap the incoming one (its other neighbour
+		 * index is clamped onto itself and gives the zero vector) */
+		const bool open = !J.closed;
+		const float2 pm = v[q > 0 ? q - 1 : (open ? 0u : N - 1)];
+		const float2 pn = v[q < N - 1 ? q + 1 : (open ? q : 0u)];
+		const float2 p = v[q];
+		return classifyStrokeAA<JT, CT>(J, q, p, vdir(pm, p), vdir(p, pn));
+	}
 	Piece P;
 	P.kind = PK_NONE;
 	P.vcount = 0;
@@ -289,59 +362,7 @@ __device__ __forceinline__ Piece classify(const JobCtx& J, uint32_t q, const flo
 	P.a01 = 0.0f;
 	P.arcDa = 0.0f;
 	P.p = P.d01 = P.d12 = P.v = f2(0.0f, 0.0f);
-	const float2* v = pts + J.first;
-	const uint32_t N = J.N;
-	if ((OPS & OPS_STROKE_AA) && (!(OPS & ~OPS_STROKE_AA) || J.op == VGB_OP_STROKE_AA)) {
-		/* one code path for the loads and both segment directions, whatever the piece is: a start
-		 * cap uses the outgoing direction, an end cap the incoming one (its other neighbour index is
-		 * clamped onto itself and gives the zero vector) */
-		const uint32_t ct = CT < 3 ? (uint32_t)CT : J.cap;
-		const bool open = !J.closed;
-		const bool isStart = open && q == 0, isEnd = open && q == N - 1;
-		const float2 pm = v[q > 0 ? q - 1 : (open ? 0u : N - 1)];
-		const float2 pn = v[q < N - 1 ? q + 1 : (open ? q : 0u)];
-		P.p = v[q];
-		const float2 dA = vdir(pm, P.p), dB = vdir(P.p, pn);
-		const uint32_t jt = JT < 3 ? (uint32_t)JT : J.join;
-		const bool isCap = isStart || isEnd;
-		/* with round joins a round cap takes its start angle from the joins' atan2 (same expression) */
-		const bool capRides = isCap && ct == VGB_CAP_ROUND && jt == VGB_JOIN_ROUND;
-		if (isCap) {
-			P.kind = isStart ? PK_CAP_START : PK_CAP_END;
-			P.d01 = isStart ? dB : dA;
-		} else {
-			P.kind = PK_JOIN;
-			P.d01 = dA;
-			P.d12 = dB;
-			if (!(J.closed && q == 0)) {
-				P.flags |= PF_HAS_PREV;
-			}
-			if (J.closed && q == N - 1) {
-				P.flags |= PF_CLOSING;
-			}
-		}
-		if (!isCap || capRides) {
-			classifyJoinAA<JT>(J, P, isCap);
-		}
-		if (isCap) {
-			P.flags = isEnd ? PF_HAS_PREV : 0u;
-			P.d12 = f2(0.0f, 0.0f);
-			P.v = f2(0.0f, 0.0f);
-			P.arcDa = 0.0f;
-			if (ct == VGB_CAP_ROUND) {
-				P.n = J.nHC;
-				P.vcount = 2 * J.nHC;
-				P.icount = isStart ? 9 * J.nHC - 12 : 9 * J.nHC + 6;
-				if (!capRides) {
-					P.a01 = vgb_atan2(P.d01.x, -P.d01.y); /* startAngle = atan2(l.y, l.x), l = perpCCW(d) (1476, 1919) */
-				}
-			} else {
-				P.n = 0;
-				P.a01 = 0.0f;
-				P.vcount = 4;
-				P.icount = isStart ? 6u : 24u;
-			}
-		}
+	if (false) {
 	} else if ((OPS & OPS_FILL_AA) && (!(OPS & ~OPS_FILL_AA) || J.op == VGB_OP_CONVEX_FILL_AA)) {
 		if (q < N - 2) {
 			P.kind = PK_FILL_FAN;
@@ -478,6 +499,8 @@ struct Sink
 		tri2(k + 6, p.y, p.z, c.z, p.y, c.z, c.y);
 		tri2(k + 12, p.z, p.w, c.w, p.z, c.w, c.z);
 	}
+	/* ... at the start of the piece's index sequence */
+	__device__ __forceinline__ void connect0(uint4 p, uint4 c) const { connect(0, p, c); }
 };
 
 __device__ __forceinline__ uint32_t pk16(uint32_t lo, uint32_t hi) { return __byte_perm(lo, hi, 0x5410); }
@@ -585,7 +608,142 @@ struct SinkS
 			tri2(k + 12, p.z, p.w, c.w, p.z, c.w, c.z);
 		}
 	}
+	/* the connect strip at the START of the piece's sequence (where joins and end caps have it): parity is the
+	 * lane's own (par), every store at an immediate offset */
+	__device__ __forceinline__ void connect0(uint4 p, uint4 c) const
+	{
+		if (sizeof(IDX) == 2) {
+			p.x += base; p.y += base; p.z += base; p.w += base;
+			c.x += base; c.y += base; c.z += base; c.w += base;
+			const uint32_t sel = par ? 0x5432u : 0x3210u;
+			uint16_t* q = reinterpret_cast<uint16_t*>(idx);
+			uint32_t* wq = reinterpret_cast<uint32_t*>(q + par);
+			const uint32_t w0 = pk16(p.x, p.y), w1 = pk16(c.y, p.x), w2 = pk16(c.y, c.x), w3 = pk16(p.y, p.z), w4 = pk16(c.z, p.y),
+			               w5 = pk16(c.z, c.y), w6 = pk16(p.z, p.w), w7 = pk16(c.w, p.z), w8 = pk16(c.w, c.z);
+			wq[0] = __byte_perm(w0, w1, sel);
+			wq[1] = __byte_perm(w1, w2, sel);
+			wq[2] = __byte_perm(w2, w3, sel);
+			wq[3] = __byte_perm(w3, w4, sel);
+			wq[4] = __byte_perm(w4, w5, sel);
+			wq[5] = __byte_perm(w5, w6, sel);
+			wq[6] = __byte_perm(w6, w7, sel);
+			wq[7] = __byte_perm(w7, w8, sel);
+			if (par) {
+				q[0] = (uint16_t)w0;
+				q[17] = (uint16_t)(w8 >> 16);
+			} else {
+				wq[8] = w8;
+			}
+		} else {
+			connect(0, p, c);
+		}
+	}
 };
+
+/* ---- index sequences of the AA stroke ----------------------------------------------------------- */
+/* round cap after its optional connect (start: stroker.cpp:1491-1510, end: 1947-1968):
+ * [fan (F, b+2, b+4) x (n-2)][quads x (n-1)], b = F+2i; an end cap swaps the 2nd and 3rd index of every triangle.
+ * Only the one or two cap lanes of a warp run this: plain 16/32-bit stores at two cursors, nothing clever. */
+template<class SINK>
+__device__ __forceinline__ void roundCapSteps(const SINK& S, uint32_t k, bool isEnd, uint32_t n, uint32_t F)
+{
+	const uint32_t o2 = isEnd ? 4u : 2u, o3 = isEnd ? 2u : 4u;
+	const uint32_t q2 = isEnd ? 3u : 1u, q3 = isEnd ? 1u : 3u, r2 = isEnd ? 2u : 3u, r3 = isEnd ? 3u : 2u;
+	uint32_t kf = k, kq = k + 3 * (n - 2);
+	for (uint32_t i = 0; i + 1 < n; ++i, kq += 6) {
+		const uint32_t b = F + 2 * i;
+		if (i + 2 < n) {
+			S.I(kf, F);
+			S.I(kf + 1, b + o2);
+			S.I(kf + 2, b + o3);
+			kf += 3;
+		}
+		S.I(kq, b);
+		S.I(kq + 1, b + q2);
+		S.I(kq + 2, b + q3);
+		S.I(kq + 3, b);
+		S.I(kq + 4, b + r2);
+		S.I(kq + 5, b + r3);
+	}
+}
+
+/* the 9 indices of join slice i (stroker.cpp:1673-1685 / 1828-1840): hub = F+1, A = F+2+2i;
+ * left inner: (hub, A, A+2) (A, A+1, A+3) (A, A+3, A+2), right inner: 2nd and 3rd index of each swapped */
+struct Slice9
+{
+	uint32_t v[9];
+};
+__device__ __forceinline__ Slice9 sliceIds(bool left, uint32_t hub, uint32_t A)
+{
+	const uint32_t A1 = A + 1, A2 = A + 2, A3 = A + 3;
+	Slice9 r;
+	r.v[0] = hub;
+	r.v[1] = left ? A : A2;
+	r.v[2] = left ? A2 : A;
+	r.v[3] = A;
+	r.v[4] = left ? A1 : A3;
+	r.v[5] = left ? A3 : A1;
+	r.v[6] = A;
+	r.v[7] = left ? A3 : A2;
+	r.v[8] = left ? A2 : A3;
+	return r;
+}
+
+/* a bevel / round join's n slices after its optional connect (k = 18 or 0), through any sink */
+template<class SINK>
+__device__ __forceinline__ void joinSlices(const SINK& S, uint32_t k, bool left, uint32_t n, uint32_t F)
+{
+	for (uint32_t i = 0; i < n; ++i, k += 9) {
+		const Slice9 s = sliceIds(left, F + 1, F + 2 + 2 * i);
+		S.tri(k, s.v[0], s.v[1], s.v[2]);
+		S.tri2(k + 3, s.v[3], s.v[4], s.v[5], s.v[6], s.v[7], s.v[8]);
+	}
+}
+
+/* ... and through the staging sink with uint16 indices: straight-line packed words.  k is 0 or 18, so the slices
+ * start with the lane's own parity (S.par), and every PAIR of slices (18 indices) keeps it: one aligned word
+ * pointer and one PRMT selector serve the whole sequence, all stores at immediate offsets; an odd last slice
+ * (9 indices) closes it. */
+template<bool AL>
+__device__ __forceinline__ void joinSlices(const SinkS<uint16_t, AL>& S, uint32_t k, bool left, uint32_t n, uint32_t F)
+{
+	const uint32_t odd = S.par;
+	const uint32_t sel = odd ? 0x5432u : 0x3210u;
+	uint16_t* q = S.idx + k;
+	uint32_t* wq = reinterpret_cast<uint32_t*>(q + odd);
+	const uint32_t hub = F + 1 + S.base;
+	uint32_t A = F + 2 + S.base;
+	uint32_t i = 0;
+	for (; i + 2 <= n; i += 2, A += 4, q += 18, wq += 9) {
+		const Slice9 a = sliceIds(left, hub, A), b = sliceIds(left, hub, A + 2);
+		const uint32_t w0 = pk16(a.v[0], a.v[1]), w1 = pk16(a.v[2], a.v[3]), w2 = pk16(a.v[4], a.v[5]), w3 = pk16(a.v[6], a.v[7]),
+		               w4 = pk16(a.v[8], b.v[0]), w5 = pk16(b.v[1], b.v[2]), w6 = pk16(b.v[3], b.v[4]), w7 = pk16(b.v[5], b.v[6]),
+		               w8 = pk16(b.v[7], b.v[8]);
+		wq[0] = __byte_perm(w0, w1, sel);
+		wq[1] = __byte_perm(w1, w2, sel);
+		wq[2] = __byte_perm(w2, w3, sel);
+		wq[3] = __byte_perm(w3, w4, sel);
+		wq[4] = __byte_perm(w4, w5, sel);
+		wq[5] = __byte_perm(w5, w6, sel);
+		wq[6] = __byte_perm(w6, w7, sel);
+		wq[7] = __byte_perm(w7, w8, sel);
+		if (odd) {
+			q[0] = (uint16_t)w0;
+			q[17] = (uint16_t)(w8 >> 16);
+		} else {
+			wq[8] = w8;
+		}
+	}
+	if (i < n) {
+		const Slice9 a = sliceIds(left, hub, A);
+		const uint32_t w0 = pk16(a.v[0], a.v[1]), w1 = pk16(a.v[2], a.v[3]), w2 = pk16(a.v[4], a.v[5]), w3 = pk16(a.v[6], a.v[7]), w4 = a.v[8];
+		wq[0] = __byte_perm(w0, w1, sel);
+		wq[1] = __byte_perm(w1, w2, sel);
+		wq[2] = __byte_perm(w2, w3, sel);
+		wq[3] = __byte_perm(w3, w4, sel);
+		q[odd ? 0 : 8] = (uint16_t)(odd ? w0 : w4);
+	}
+}
 
 /* ---- AA stroke pieces ---------------------------------------------------------------- */
 /* everything a butt / square cap needs, gathered from its lane (round caps go through emitStrokeAA) */
@@ -627,18 +785,10 @@ __device__ __forceinline__ void emitCapAA(const CapRec& R, const SINK& S)
 		}
 		if (isEnd) {
 			const uint32_t e = F + 2 * (n - 1);
-			S.connect(0, R.prev, make_uint4(F + 1, F, e, e + 1));
+			S.connect0(R.prev, make_uint4(F + 1, F, e, e + 1));
 			k = 18;
 		}
-		const uint32_t o2 = isEnd ? 4u : 2u, o3 = isEnd ? 2u : 4u;
-		for (uint32_t i = 0; i < n - 2; ++i, k += 3) {
-			S.tri(k, F, F + 2 * i + o2, F + 2 * i + o3);
-		}
-		const uint32_t q2 = isEnd ? 3u : 1u, q3 = isEnd ? 1u : 3u, r2 = isEnd ? 2u : 3u, r3 = isEnd ? 3u : 2u;
-		for (uint32_t i = 0; i < n - 1; ++i, k += 6) {
-			const uint32_t b = F + 2 * i;
-			S.tri2(k, b, b + q2, b + q3, b, b + r2, b + r3);
-		}
+		roundCapSteps(S, k, isEnd, n, F);
 		return;
 	}
 	const float2 ds = isEnd ? f2(-d.x, -d.y) : d; /* d-terms of the start-cap formulas */
@@ -655,11 +805,16 @@ __device__ __forceinline__ void emitCapAA(const CapRec& R, const SINK& S)
 		S.VP(2, p0.x - (lx + dx), p0.y - (ly + dy), R.color, p0.x - (lax + dax), p0.y - (lay + day), R.c0);
 	}
 	if (isEnd) {
-		S.connect(0, R.prev, make_uint4(F, F + 1, F + 2, F + 3));
-		S.tri2(18, F, F + 1, F + 2, F, F + 2, F + 3);
-	} else {
-		S.tri2(0, F, F + 2, F + 1, F, F + 3, F + 2);
+		S.connect0(R.prev, make_uint4(F, F + 1, F + 2, F + 3));
+		k = 18;
 	}
+	/* stroker.cpp:1443-1444 (start: 0,2,1, 0,3,2) / 1889-1890 (end: 0,1,2, 0,2,3) */
+	S.I(k, F);
+	S.I(k + 1, isEnd ? F + 1 : F + 2);
+	S.I(k + 2, isEnd ? F + 2 : F + 1);
+	S.I(k + 3, F);
+	S.I(k + 4, isEnd ? F + 2 : F + 3);
+	S.I(k + 5, isEnd ? F + 3 : F + 2);
 }
 
 /* stroker.cpp:1536-1847. firstLeft: side of the mesh's first join (closing connect only) */
@@ -679,7 +834,7 @@ __device__ __forceinline__ void emitJoinAA(const JobCtx& J, const Piece& P, uint
 		S.VP(0, p1.x + vax, p1.y + vay, J.c0, p1.x + vx, p1.y + vy, J.color);
 		S.VP(2, p1.x - vx, p1.y - vy, J.color, p1.x - vax, p1.y - vay, J.c0);
 		if (P.flags & PF_HAS_PREV) {
-			S.connect(0, prev, joinIn4(left, F));
+			S.connect0(prev, joinIn4(left, F));
 			k = 18;
 		}
 	} else {
@@ -718,16 +873,11 @@ __device__ __forceinline__ void emitJoinAA(const JobCtx& J, const Piece& P, uint
 			S.VP(2 + 2 * n, ax, ay, J.color, p1.x + s12.x * hsw_aa, p1.y + s12.y * hsw_aa, J.c0);
 		}
 		if (P.flags & PF_HAS_PREV) {
-			S.connect(0, prev, joinIn4(left, F));
+			S.connect0(prev, joinIn4(left, F));
 			k = 18;
 		}
-		/* slices (1673-1685 / 1828-1840): the right-inner case swaps the 2nd and 3rd index of each triangle */
-		uint32_t A = F + 2;
-		const uint32_t u2 = left ? 0u : 2u, u3 = left ? 2u : 0u, w2 = left ? 1u : 3u, w3 = left ? 3u : 1u, x2 = left ? 3u : 2u, x3 = left ? 2u : 3u;
-		for (uint32_t i = 0; i < n; ++i, k += 9, A += 2) {
-			S.tri(k, F + 1, A + u2, A + u3);
-			S.tri2(k + 3, A, A + w2, A + w3, A, A + x2, A + x3);
-		}
+		joinSlices(S, k, left, n, F);
+		k += 9 * n;
 	}
 	if (P.flags & PF_CLOSING) {
 		/* stroker.cpp:1970-1984: previous = this piece, first = piece 0 (its F is 0) */
@@ -817,35 +967,22 @@ __device__ __forceinline__ void emitStrokeAA(const JobCtx& J, const Piece& P, ui
 		}
 		S.VP(vb + 2 * i, ix, iy, J.color, p1.x + dx * hsw_aa, p1.y + dy * hsw_aa, J.c0);
 	}
-	uint32_t k = 0;
-	if (P.flags & PF_HAS_PREV) {
+	/* indices.  The connect strip of joins AND end caps is one straight-line block (packed words in the staging
+	 * sink); then the joins' slices, straight-line too, while the one or two cap lanes of the warp run their
+	 * fan / quad steps on their own. */
+	const bool hasPrev = (P.flags & PF_HAS_PREV) != 0;
+	if (hasPrev) {
 		const uint32_t e = F + 2 * (n - 1);
-		S.connect(0, prev, isCap ? make_uint4(F + 1, F, e, e + 1) : joinIn4(left, F));
-		k = 18;
+		S.connect0(prev, isCap ? make_uint4(F + 1, F, e, e + 1) : joinIn4(left, F));
 	}
-	/* One index loop for both kinds, three triangles per iteration:
-	 *   join slice i (1651-1685 / 1807-1841):  (F+1, A+u2, A+u3) (A, A+w2, A+w3) (A, A+x2, A+x3), A = F+2+2i, 9 consecutive indices
-	 *   cap step i  (1491-1510 / 1947-1968):   fan (F, b+o2, b+o3) for i < nHC-2 at 3i, then the fringe quad
-	 *                                          (b, b+q2, b+q3) (b, b+r2, b+r3) at 3(nHC-2) + 6i, b = F+2i;
-	 *                                          an end cap swaps the 2nd and 3rd index of each triangle
-	 * so the few cap lanes of a warp ride in the join lanes' iterations instead of running their own loops. */
-	const uint32_t cntI = isCap ? n - 1 : n;
-	const uint32_t fanN = isCap ? n - 2 : n;
-	const uint32_t a0 = isCap ? F : F + 1;
-	uint32_t B = isCap ? F : F + 2;
-	const uint32_t c0b = isCap ? (isEnd ? 4u : 2u) : (left ? 0u : 2u), c0c = isCap ? (isEnd ? 2u : 4u) : (left ? 2u : 0u);
-	const uint32_t c1b = isCap ? (isEnd ? 3u : 1u) : (left ? 1u : 3u), c1c = isCap ? (isEnd ? 1u : 3u) : (left ? 3u : 1u);
-	const uint32_t c2b = isCap ? (isEnd ? 2u : 3u) : (left ? 3u : 2u), c2c = isCap ? (isEnd ? 3u : 2u) : (left ? 2u : 3u);
-	const uint32_t s0 = isCap ? 3u : 9u, s1 = isCap ? 6u : 9u;
-	uint32_t k0 = k, k1 = k + (isCap ? 3 * (n - 2) : 3u);
-	for (uint32_t i = 0; i < cntI; ++i, k0 += s0, k1 += s1, B += 2) {
-		if (i < fanN) {
-			S.tri(k0, a0, B + c0b, B + c0c);
+	const uint32_t k = hasPrev ? 18u : 0u;
+	if (isCap) {
+		roundCapSteps(S, k, isEnd, n, F);
+	} else {
+		joinSlices(S, k, left, n, F);
+		if (P.flags & PF_CLOSING) {
+			S.connect(k + 9 * n, out4FromTail(0, jt, packTail(P), F + P.vcount), joinIn4(firstLeft, 0));
 		}
-		S.tri2(k1, B, B + c1b, B + c1c, B, B + c2b, B + c2c);
-	}
-	if (!isCap && (P.flags & PF_CLOSING)) {
-		S.connect(k + 9 * n, out4FromTail(0, jt, packTail(P), F + P.vcount), joinIn4(firstLeft, 0));
 	}
 }
 
