@@ -1,7 +1,2 @@
-set -x
-python -m pytest tests -m gpu -x -q 2>&1 | tail -5
-python tools/perf_probe.py 1000000 10
-VGB_EMIT_WAVES=2 python tools/perf_probe.py 1000000 10
-VGB_EMIT_WAVES=4 python tools/perf_probe.py 1000000 10
-VGB_EMIT_WAVES=1000 python tools/perf_probe.py 1000000 10
-ncu --set full --clock-control none --import-source on -k regex:k_group_emit -s 2 -c 1 -o gpurun_out/r2_d python tools/perf_probe.py 1000000 1 > gpurun_out/ncu_r2_d.log 2>&1
+python bench.py --steps 50 --warmup 5 > gpurun_out/bench_r2_b.json 2> gpurun_out/bench_r2_b.err
+tail -c 2500 gpurun_out/bench_r2_b.json

@@ -628,6 +628,7 @@ struct PieceArgs
 	const ulonglong2* meshOff;   /* numJobs + 1   */
 	uint64_t vertexBase;
 	const uint32_t* meshBase; /* final layout: per-mesh index base (nullptr otherwise) */
+	uint32_t* ticket;         /* emit: dynamic group tickets (zeroed by k_mesh_off) */
 	/* emit outputs */
 	float2* pos;
 	uint32_t* col;
@@ -823,9 +824,10 @@ __device__ __forceinline__ uint2 warpInclusive(uint2 v, uint32_t lane)
  * the within-group offset recorded by k_group_count; an empty job starts where the next piece starts */
 __global__ void k_mesh_off(const uint32_t* __restrict__ pieceStart, const uint2* __restrict__ pieceRec, uint32_t numJobs, uint32_t numPieces,
                            uint32_t numGroups, const ulonglong2* __restrict__ groupBase, const uint2* __restrict__ meshLocal,
-                           ulonglong2* __restrict__ meshOff)
+                           ulonglong2* __restrict__ meshOff, uint32_t* __restrict__ ticket)
 {
 	const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+	if (j == 0) *ticket = 0u; /* the emit kernel's group tickets */
 	if (j > numJobs) return;
 	const uint32_t g = j < numJobs ? pieceStart[j] : numPieces;
 	ulonglong2 o;
@@ -1192,7 +1194,7 @@ __global__ void __launch_bounds__(128, (OPS == OPS_STROKE_AA && JT < 3) ? VGB_EM
 	const uint32_t lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
 	const uint32_t W = gridDim.x * 4;
 	const uint32_t numGroups = (a.numPieces + 31) >> 5;
-	uint32_t w = blockIdx.x * 4 + wib;
+	uint32_t w = blockIdx.x * 4 + wib; /* the first group of every warp is static, the rest are tickets */
 	if (w >= numGroups) {
 		return; /* whole warp out of range */
 	}
@@ -1202,21 +1204,28 @@ __global__ void __launch_bounds__(128, (OPS == OPS_STROKE_AA && JT < 3) ? VGB_EM
 	IDX* sIdx = reinterpret_cast<IDX*>(stage + POS_BYTES + COL_BYTES);
 	bool copyPending = false;
 	uint2 recA = make_uint2(0u, 0u), recB = make_uint2(0u, 0u);
+	uint32_t w1, w2;
 	{
+		uint32_t t = 0;
+		if (lane == 0) t = atomicAdd(a.ticket, 2u);
+		t = __shfl_sync(0xffffffffu, t, 0);
+		w1 = W + t;
+		w2 = W + t + 1;
 		const uint32_t g0 = w * 32 + lane;
 		if (g0 < a.numPieces) recA = a.pieceRec[g0];
-		const uint32_t g1 = g0 + W * 32;
-		if (w + W < numGroups && g1 < a.numPieces) recB = a.pieceRec[g1];
+		const uint32_t g1 = w1 * 32 + lane;
+		if (w1 < numGroups && g1 < a.numPieces) recB = a.pieceRec[g1];
 	}
-	for (; w < numGroups; w += W) {
+	for (;;) {
 	const uint32_t g = w * 32 + lane;
 	const bool valid = g < a.numPieces;
 	const uint2 rec = recA;
 	const uint32_t j = rec.x;
 	recA = recB;
+	uint32_t ticket = 0;
 	{
-		/* records of the group two ahead; L2 prefetch for the group one ahead */
-		const uint32_t w1 = w + W, w2 = w + 2 * W;
+		/* the ticket of the group three ahead, the records of the group two ahead, L2 prefetch for the group one ahead */
+		if (lane == 0) ticket = atomicAdd(a.ticket, 1u);
 		const uint32_t g2 = w2 * 32 + lane;
 		recB = make_uint2(0u, 0u);
 		if (w2 < numGroups && g2 < a.numPieces) recB = a.pieceRec[g2];
@@ -1329,6 +1338,13 @@ __global__ void __launch_bounds__(128, (OPS == OPS_STROKE_AA && JT < 3) ? VGB_EM
 		S.idx = reinterpret_cast<IDX*>(a.idx) + bb.y + il;
 		emitAnyCold<OPS, JT, CT>(a.pts, J, P, F, prev, S);
 	}
+	/* next group: tickets keep the groups in flight a contiguous window of the output whatever the warps' pace */
+	w = w1;
+	w1 = w2;
+	w2 = W + __shfl_sync(0xffffffffu, ticket, 0);
+	if (w >= numGroups) {
+		break;
+	}
 	} /* groups of this warp */
 	if (copyPending && (lane == 0 || lane == 2 || lane == 8)) {
 		bulkWaitRead(); /* the image must outlive its bulk copies */
@@ -1433,7 +1449,7 @@ public:
 	/* intermediates */
 	DevBuf dSubNum, dSubFirst, dSubClosed, dPts, dDD, dJobPieces, dPieceStart, dJobRec, dPieceJob;
 	DevBuf dBlockTotals, dBlockBase, dMeshTotals, dMeshOff, dScanTmp, dBlockTail;
-	DevBuf dSlotFirst, dCounters, dDenseFirst, dDensePts, dBulkErr, dMeshSplit;
+	DevBuf dSlotFirst, dCounters, dDenseFirst, dDensePts, dBulkErr, dMeshSplit, dTicket;
 	bool bulkMode = false;
 	/* sizes of the uploaded batch, learnt by the first run (they are facts about the input, and the
 	 * kernels are deterministic): later runs of the SAME upload reuse them instead of draining the
@@ -1473,7 +1489,7 @@ public:
 		cudaSetDevice(dev);
 		DevBuf* all[] = {&dSubRec, &dCmd, &dData, &dScale, &dTol, &dXform, &dDraws, &dJobSub, &dJobDraw, &dSubNum, &dSubFirst,
 		                 &dSubClosed, &dPts, &dDD, &dJobPieces, &dPieceStart, &dJobRec, &dPieceJob, &dBlockTotals, &dBlockBase,
-		                 &dMeshTotals, &dMeshOff, &dScanTmp, &dBlockTail, &dSlotFirst, &dCounters, &dDenseFirst, &dDensePts, &dBulkErr, &dMeshSplit, &dPos, &dCol, &dIdx,
+		                 &dMeshTotals, &dMeshOff, &dScanTmp, &dBlockTail, &dSlotFirst, &dCounters, &dDenseFirst, &dDensePts, &dBulkErr, &dMeshSplit, &dTicket, &dPos, &dCol, &dIdx,
 		                 &dCmdSub, &dCmdData, &dCmdCount, &dCmdOff, &dCmdOk, &dSubMode, &dSegNext[0], &dSegNext[1], &dSegStarts, &dSegHdr, &dSegCmds, &dMeshBase, &dUV, &dRXf, &dRPos, &dRCol, &dRIdx};
 		for (DevBuf* b : all) b->release();
 		for (auto& e : ev) if (e) cudaEventDestroy(e);
@@ -1632,6 +1648,10 @@ public:
 		static int perSM = 0;
 		static int waves = 0;
 		if (perSM == 0) {
+			/* a persistent grid must be fully resident from the start: ask for the shared-memory carve-out its
+			 * 8-9 blocks per SM need (left to the driver's heuristic it settled, after a few launches, on a
+			 * smaller one, and half of the grid only started once the other half had taken every ticket) */
+			cudaFuncSetAttribute(k_group_emit<IDX, OPS, JT, CT, BIGI>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
 			if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_group_emit<IDX, OPS, JT, CT, BIGI>, (int)PPB, 0) != cudaSuccess || perSM < 1) perSM = 8;
 			const char* e = getenv("VGB_EMIT_WAVES");
 			waves = e ? atoi(e) : 1;
@@ -1641,6 +1661,7 @@ public:
 			if (cudaDeviceGetAttribute(&numSMs, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || numSMs < 1) numSMs = 148;
 		}
 		const uint32_t cap = (uint32_t)perSM * (uint32_t)numSMs * (uint32_t)waves;
+		if (getenv("VGB_DEBUG")) fprintf(stderr, "[vgb] emit grid: perSM %d numSMs %d waves %d blocks %u of %u\n", perSM, numSMs, waves, gridBlocks < cap ? gridBlocks : cap, gridBlocks);
 		k_group_emit<IDX, OPS, JT, CT, BIGI><<<gridBlocks < cap ? gridBlocks : cap, PPB, 0, st>>>(pa);
 	}
 
@@ -1816,6 +1837,8 @@ public:
 			pa.blockBase = dBlockBase.as<ulonglong2>();
 			pa.meshOff = dMeshOff.as<ulonglong2>();
 			pa.vertexBase = vertexBase;
+			if (dTicket.ensure(16, err)) return VGB_ERR_CUDA;
+			pa.ticket = dTicket.as<uint32_t>();
 			if (fillOnly) {
 				/* closed-form sizes: the mesh table is a plain scan of (2N, 9N-6); no count kernel */
 				if (scan<ScanOps<uint2>>(dMeshTotals.as<uint2>(), numJobs, dMeshOff.as<ulonglong2>(), err)) return VGB_ERR_CUDA;
@@ -1831,7 +1854,7 @@ public:
 			++launches;
 			if (scan<ScanOps<uint2>>(dBlockTotals.as<uint2>(), numBlocks, dBlockBase.as<ulonglong2>(), err)) return VGB_ERR_CUDA;
 			k_mesh_off<<<(numJobs + 1 + 255) / 256, 256, 0, st>>>(dPieceStart.as<uint32_t>(), dPieceJob.as<uint2>(), numJobs, numPieces, numBlocks,
-			                                                       dBlockBase.as<ulonglong2>(), dMeshTotals.as<uint2>(), dMeshOff.as<ulonglong2>());
+			                                                       dBlockBase.as<ulonglong2>(), dMeshTotals.as<uint2>(), dMeshOff.as<ulonglong2>(), dTicket.as<uint32_t>());
 			++launches;
 			} /* !fillOnly */
 			if (sizesKnown) {
