@@ -293,6 +293,38 @@ VGB_API int vgb_batch_recorded_streams(vgb_batch* b, uint8_t* cmd, float* data, 
  * merged buffer: the exclusive scan of per-rank totals).  */
 VGB_API int vgb_batch_upload(vgb_batch* b);
 VGB_API int vgb_batch_run(vgb_batch* b, uint32_t flags, uint64_t vertex_base);
+
+/* ---- several GPUs, one merged vertex / index space --------------------------------
+ * One process per GPU; ranks take disjoint path ranges and run independently.  The reference builds ONE
+ * vertex/index space per frame by rebasing each mesh's indices by the vertices that precede it
+ * (createDrawCommand_VertexColor, vg.cpp:5207-5244); across GPUs "what precedes" is the exclusive scan of
+ * the ranks' vertex totals.  A vgb_group is that communicator (NCCL over NVLink/NVSwitch, resolved at run
+ * time: libnccl.so.2).  vgb_group_unique_id is called by ONE rank; the 128 bytes reach the others by
+ * whatever launcher the host uses (torchrun store, MPI, a file) and every rank calls vgb_group_create.
+ *
+ * vgb_batch_run_merged: flatten + count, then an all-gather of the ranks' (vertex count, index count)
+ * -- 16 bytes per rank, enqueued on the batch's stream -- whose exclusive prefix, computed on the device,
+ * is added to this rank's merged uint32 indices (flags must carry VGB_RUN_INDEX_U32).  Asynchronous like
+ * vgb_batch_run: nothing returns to the host between count and emit.  vgb_batch_merged_info reads the
+ * result back: {vertex_base, index_base, total_vertices, total_indices} (synchronises).
+ *
+ * vgb_group_gather: payload placement -- every rank's pos / colour / index arrays are written into ONE
+ * buffer on `owner` at the rank's base (ncclSend/ncclRecv: peer copies over NVLink).  On the owner
+ * *pos/*color/*index are device pointers to the merged arrays (owned by the group, valid until the next
+ * gather or vgb_group_destroy), on the others they are set to NULL; ms = device time of the transfer.
+ * NVLink-bound (the owner's ingress), reported separately from the HBM roofline. */
+typedef struct vgb_group vgb_group;
+#define VGB_GROUP_ID_BYTES 128
+typedef struct vgb_merged
+{
+	uint64_t vertex_base, index_base, total_vertices, total_indices;
+} vgb_merged;
+VGB_API int vgb_group_unique_id(void* id128);
+VGB_API int vgb_group_create(vgb_group** out, int device, int rank, int nranks, const void* id128);
+VGB_API void vgb_group_destroy(vgb_group* g);
+VGB_API int vgb_batch_run_merged(vgb_batch* b, vgb_group* g, uint32_t flags);
+VGB_API int vgb_batch_merged_info(vgb_batch* b, vgb_merged* out);
+VGB_API int vgb_group_gather(vgb_group* g, vgb_batch* b, int owner, void** pos, void** color, void** index, vgb_merged* info, float* ms);
 VGB_API int vgb_batch_sync(vgb_batch* b);
 VGB_API int vgb_batch_get_sizes(vgb_batch* b, vgb_sizes* out);
 
@@ -352,6 +384,8 @@ VGB_API int vgb_batch_elapsed_ms(vgb_batch* b, uint32_t slot_a, uint32_t slot_b,
 /* pinned host memory helpers (cudaHostAlloc / cudaFreeHost) for the host-buffer path */
 VGB_API void* vgb_host_alloc(size_t bytes);
 VGB_API void vgb_host_free(void* p);
+/* plain device -> host copy of a pointer handed out by vgb_batch_device_ptrs / vgb_group_gather (blocking) */
+VGB_API int vgb_copy_to_host(void* dst, const void* src_device, size_t bytes);
 /* raw stream handle (cudaStream_t) of the batch, for callers that time with their own events */
 VGB_API void* vgb_batch_stream(vgb_batch* b);
 

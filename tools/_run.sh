@@ -1,2 +1,1 @@
-python bench.py --steps 50 --warmup 5 > gpurun_out/bench_r2_b.json 2> gpurun_out/bench_r2_b.err
-tail -c 2500 gpurun_out/bench_r2_b.json
+python -m pytest tests/test_dist.py tests/test_gpu_parity.py -m gpu -x -q 2>&1 | tail -15

@@ -111,6 +111,11 @@ class SubPath(C.Structure):
     _fields_ = [("first_vertex", C.c_uint32), ("num_vertices", C.c_uint32), ("is_closed", C.c_uint8)]
 
 
+class Merged(C.Structure):
+    """vgb_merged: this rank's place in the group's merged vertex / index space"""
+    _fields_ = [("vertex_base", C.c_uint64), ("index_base", C.c_uint64), ("total_vertices", C.c_uint64), ("total_indices", C.c_uint64)]
+
+
 class Mesh(C.Structure):
     _fields_ = [("pos", C.POINTER(C.c_float)), ("color", C.POINTER(C.c_uint32)), ("index", C.POINTER(C.c_uint16)),
                 ("num_vertices", C.c_uint32), ("num_indices", C.c_uint32)]
@@ -188,6 +193,13 @@ def load_library():
     L.vgb_host_free.argtypes = [vp]
     L.vgb_batch_stream.restype = vp
     L.vgb_batch_stream.argtypes = [vp]
+    # several GPUs, one merged vertex/index space
+    L.vgb_group_unique_id.argtypes = [vp]
+    L.vgb_group_create.argtypes = [C.POINTER(vp), i, i, i, vp]
+    L.vgb_group_destroy.argtypes = [vp]
+    L.vgb_batch_run_merged.argtypes = [vp, vp, u32]
+    L.vgb_batch_merged_info.argtypes = [vp, C.POINTER(Merged)]
+    L.vgb_group_gather.argtypes = [vp, vp, i] + [C.POINTER(vp)] * 3 + [C.POINTER(Merged), C.POINTER(f)]
     # per-object API
     L.vgb_path_create.restype = vp
     L.vgb_path_create.argtypes = [vp, vp]
@@ -366,6 +378,17 @@ class Batch:
         self.index_u32 = bool(index_u32)
         return self._chk(self.L.vgb_batch_run(self.h, INDEX_U32 if index_u32 else INDEX_U16, vertex_base))
 
+    def run_merged(self, group):
+        """run as one rank of `group`: merged uint32 indices, base from the in-library all-gather (asynchronous)"""
+        self.index_u32 = True
+        return self._chk(self.L.vgb_batch_run_merged(self.h, group.h, INDEX_U32))
+
+    def merged_info(self):
+        m = Merged()
+        self._chk(self.L.vgb_batch_merged_info(self.h, C.byref(m)))
+        return dict(vertex_base=int(m.vertex_base), index_base=int(m.index_base), total_vertices=int(m.total_vertices),
+                    total_indices=int(m.total_indices))
+
     def sync(self): return self._chk(self.L.vgb_batch_sync(self.h))
 
     def sizes(self):
@@ -453,6 +476,63 @@ class Batch:
         self._chk(self.L.vgb_batch_execute(self.h, INDEX_U32 if index_u32 else INDEX_U16, _ptr(pos), _ptr(col), _ptr(idx),
                                            len(pos), len(idx), None, None, C.byref(s)))
         return s
+
+
+class Group:
+    """vgb_group: the ranks (one process per GPU) that share ONE merged vertex / index space.
+    Group.unique_id() on one rank -> 128 bytes -> every rank (by the launcher's own means) -> Group(...)."""
+
+    @staticmethod
+    def unique_id():
+        L = load_library()
+        buf = (C.c_uint8 * 128)()
+        rc = L.vgb_group_unique_id(C.cast(buf, C.c_void_p))
+        if rc != 0:
+            raise VgbError(rc, L.vgb_last_error().decode())
+        return bytes(buf)
+
+    def __init__(self, device, rank, nranks, uid):
+        self.L = load_library()
+        self.rank, self.nranks = rank, nranks
+        h = C.c_void_p()
+        buf = (C.c_uint8 * 128).from_buffer_copy(bytes(uid))
+        rc = self.L.vgb_group_create(C.byref(h), device, rank, nranks, C.cast(buf, C.c_void_p))
+        if rc != 0:
+            raise VgbError(rc, self.L.vgb_last_error().decode())
+        self.h = h
+
+    def gather(self, batch, owner=0):
+        """payload of every rank -> ONE buffer on `owner` (NVLink peer copies).  -> dict(pos/color/index device
+        pointers on the owner, else None; info; ms = device time of the transfer)"""
+        p = [C.c_void_p() for _ in range(3)]
+        m, ms = Merged(), C.c_float()
+        rc = self.L.vgb_group_gather(self.h, batch.h, owner, *[C.byref(x) for x in p], C.byref(m), C.byref(ms))
+        if rc != 0:
+            raise VgbError(rc, self.L.vgb_last_error().decode())
+        return dict(pos=p[0].value, color=p[1].value, index=p[2].value, ms=ms.value, vertex_base=int(m.vertex_base), index_base=int(m.index_base),
+                    total_vertices=int(m.total_vertices), total_indices=int(m.total_indices))
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.vgb_group_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def copy_from_device(ptr, nbytes, dtype):
+    """device pointer -> numpy (test helper: cudaMemcpy through the library's own runtime)"""
+    L = load_library()
+    out = np.empty(nbytes // np.dtype(dtype).itemsize, dtype)
+    L.vgb_copy_to_host.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
+    rc = L.vgb_copy_to_host(_ptr(out), C.c_void_p(ptr), nbytes)
+    if rc != 0:
+        raise VgbError(rc, L.vgb_last_error().decode())
+    return out
 
 
 def pinned_empty(shape, dtype):

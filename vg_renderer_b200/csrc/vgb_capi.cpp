@@ -677,6 +677,68 @@ int vgb_batch_run(vgb_batch* b, uint32_t flags, uint64_t vertexBase)
 	return 0;
 }
 
+int vgb_group_unique_id(void* id128)
+{
+	std::string err;
+	const int rc = groupUniqueId(id128, &err);
+	return rc ? fail(rc, err.c_str()) : 0;
+}
+
+int vgb_group_create(vgb_group** out, int device, int rank, int nranks, const void* id128)
+{
+	std::string err;
+	const int rc = groupCreate(out, device, rank, nranks, id128, &err);
+	return rc ? fail(rc, err.c_str()) : 0;
+}
+
+void vgb_group_destroy(vgb_group* g) { groupDestroy(g); }
+
+int vgb_batch_run_merged(vgb_batch* b, vgb_group* g, uint32_t flags)
+{
+	NEED_PIPE(b);
+	if (!g) return fail(VGB_ERR_INVALID, "null group");
+	if (!(flags & VGB_RUN_INDEX_U32)) return fail(VGB_ERR_INVALID, "a merged index space needs uint32 indices: pass VGB_RUN_INDEX_U32");
+	if (b->dirty) {
+		const int rc = vgb_batch_upload(b);
+		if (rc) return rc;
+	}
+	std::string err;
+	const int rc = b->pipe->run(flags, 0, &err, groupHook(g));
+	return rc ? fail(rc, err.c_str()) : 0;
+}
+
+int vgb_batch_merged_info(vgb_batch* b, vgb_merged* out)
+{
+	NEED_PIPE(b);
+	if (!out) return fail(VGB_ERR_INVALID, "null argument");
+	uint64_t v[4];
+	std::string err;
+	const int rc = b->pipe->mergedInfo(v, nullptr, &err);
+	if (rc) return fail(rc, err.c_str());
+	out->vertex_base = v[0];
+	out->index_base = v[1];
+	out->total_vertices = v[2];
+	out->total_indices = v[3];
+	return 0;
+}
+
+int vgb_group_gather(vgb_group* g, vgb_batch* b, int owner, void** pos, void** color, void** index, vgb_merged* info, float* ms)
+{
+	NEED_PIPE(b);
+	if (!g) return fail(VGB_ERR_INVALID, "null group");
+	uint64_t v[4] = {0, 0, 0, 0};
+	std::string err;
+	const int rc = groupGather(g, b->pipe, 4, owner, pos, color, index, v, ms, &err);
+	if (rc) return fail(rc, err.c_str());
+	if (info) {
+		info->vertex_base = v[0];
+		info->index_base = v[1];
+		info->total_vertices = v[2];
+		info->total_indices = v[3];
+	}
+	return 0;
+}
+
 int vgb_batch_sync(vgb_batch* b)
 {
 	NEED_PIPE(b);
@@ -838,6 +900,13 @@ int vgb_batch_elapsed_ms(vgb_batch* b, uint32_t a, uint32_t c, float* ms)
 
 void* vgb_host_alloc(size_t bytes) { return hostAlloc(bytes); }
 void vgb_host_free(void* p) { hostFree(p); }
+
+int vgb_copy_to_host(void* dst, const void* src_device, size_t bytes)
+{
+	if (!dst || !src_device) return fail(VGB_ERR_INVALID, "null argument");
+	if (copyToHost(dst, src_device, bytes)) return fail(VGB_ERR_CUDA, "cudaMemcpy device -> host failed");
+	return 0;
+}
 void* vgb_batch_stream(vgb_batch* b) { return (b && b->pipe) ? b->pipe->stream() : nullptr; }
 
 /* =========================================================================================

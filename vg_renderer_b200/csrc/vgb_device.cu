@@ -484,6 +484,33 @@ __global__ void k_bulk_cubic_tables(const float* __restrict__ p8, uint32_t n, fl
 	jobDraw[i] = 0;
 }
 
+/* merged run: every rank's (V, I) -> this rank's exclusive base and the group totals.  One warp. */
+__global__ void k_rank_base(const uint64_t* __restrict__ rankTotals, uint32_t rank, uint32_t nranks, uint64_t* __restrict__ out)
+{
+	uint64_t bv = 0, bi = 0, tv = 0, ti = 0;
+	for (uint32_t r = threadIdx.x; r < nranks; r += 32) {
+		const uint64_t v = rankTotals[2 * r], i = rankTotals[2 * r + 1];
+		tv += v;
+		ti += i;
+		if (r < rank) {
+			bv += v;
+			bi += i;
+		}
+	}
+	for (int d = 16; d > 0; d >>= 1) {
+		bv += __shfl_xor_sync(0xffffffffu, bv, d);
+		bi += __shfl_xor_sync(0xffffffffu, bi, d);
+		tv += __shfl_xor_sync(0xffffffffu, tv, d);
+		ti += __shfl_xor_sync(0xffffffffu, ti, d);
+	}
+	if (threadIdx.x == 0) {
+		out[0] = bv;
+		out[1] = bi;
+		out[2] = tv;
+		out[3] = ti;
+	}
+}
+
 /* mesh table as two plain u64 arrays (what vgb_batch_download hands out) */
 __global__ void k_split_mesh_off(const ulonglong2* __restrict__ meshOff, uint32_t n, uint64_t* __restrict__ v, uint64_t* __restrict__ i)
 {
@@ -627,6 +654,7 @@ struct PieceArgs
 	const ulonglong2* blockBase; /* numBlocks + 1 */
 	const ulonglong2* meshOff;   /* numJobs + 1   */
 	uint64_t vertexBase;
+	const uint64_t* vertexBasePtr; /* merged run: this rank's base, computed on the device (nullptr otherwise) */
 	const uint32_t* meshBase; /* final layout: per-mesh index base (nullptr otherwise) */
 	uint32_t* ticket;         /* emit: dynamic group tickets (zeroed by k_mesh_off) */
 	/* emit outputs */
@@ -1303,7 +1331,7 @@ __global__ void __launch_bounds__(128, (OPS == OPS_STROKE_AA && JT < 3) ? VGB_EM
 	}
 	/* uint16: BIGI doubles as "final layout" (per-mesh base from the draw-command segmentation);
 	 * the plain per-mesh-local variant keeps base = 0 at compile time */
-	uint32_t idxBase = sizeof(IDX) == 2 ? 0u : (uint32_t)(mo.x + a.vertexBase);
+	uint32_t idxBase = sizeof(IDX) == 2 ? 0u : (uint32_t)(mo.x + a.vertexBase + (a.vertexBasePtr ? __ldg(a.vertexBasePtr) : 0ull));
 	if (sizeof(IDX) == 2 && BIGI && valid) idxBase = a.meshBase[j];
 	const bool fits = totV <= CVW && totI <= CIW; /* warp-uniform */
 	if (fits) {
@@ -1391,7 +1419,7 @@ __global__ void __launch_bounds__(256) k_fill_emit(PieceArgs a)
 	const float ex = e.x * aa, ey = e.y * aa;
 	reinterpret_cast<float4*>(a.pos + mo.x)[i] = make_float4(p.x + ex, p.y + ey, p.x - ex, p.y - ey);
 	reinterpret_cast<uint2*>(a.col + mo.x)[i] = make_uint2(J.color, J.c0);
-	const uint32_t base = sizeof(IDX) == 2 ? (a.meshBase != nullptr ? a.meshBase[j] : 0u) : (uint32_t)(mo.x + a.vertexBase);
+	const uint32_t base = sizeof(IDX) == 2 ? (a.meshBase != nullptr ? a.meshBase[j] : 0u) : (uint32_t)(mo.x + a.vertexBase + (a.vertexBasePtr ? __ldg(a.vertexBasePtr) : 0ull));
 	IDX* idx = reinterpret_cast<IDX*>(a.idx) + mo.y;
 	const uint32_t f = 2 * i;
 	if (i + 2 < N) {
@@ -1449,7 +1477,8 @@ public:
 	/* intermediates */
 	DevBuf dSubNum, dSubFirst, dSubClosed, dPts, dDD, dJobPieces, dPieceStart, dJobRec, dPieceJob;
 	DevBuf dBlockTotals, dBlockBase, dMeshTotals, dMeshOff, dScanTmp, dBlockTail;
-	DevBuf dSlotFirst, dCounters, dDenseFirst, dDensePts, dBulkErr, dMeshSplit, dTicket;
+	DevBuf dSlotFirst, dCounters, dDenseFirst, dDensePts, dBulkErr, dMeshSplit, dTicket, dRankTotals, dRankBase;
+	bool mergedRan = false;
 	bool bulkMode = false;
 	/* sizes of the uploaded batch, learnt by the first run (they are facts about the input, and the
 	 * kernels are deterministic): later runs of the SAME upload reuse them instead of draining the
@@ -1489,7 +1518,7 @@ public:
 		cudaSetDevice(dev);
 		DevBuf* all[] = {&dSubRec, &dCmd, &dData, &dScale, &dTol, &dXform, &dDraws, &dJobSub, &dJobDraw, &dSubNum, &dSubFirst,
 		                 &dSubClosed, &dPts, &dDD, &dJobPieces, &dPieceStart, &dJobRec, &dPieceJob, &dBlockTotals, &dBlockBase,
-		                 &dMeshTotals, &dMeshOff, &dScanTmp, &dBlockTail, &dSlotFirst, &dCounters, &dDenseFirst, &dDensePts, &dBulkErr, &dMeshSplit, &dTicket, &dPos, &dCol, &dIdx,
+		                 &dMeshTotals, &dMeshOff, &dScanTmp, &dBlockTail, &dSlotFirst, &dCounters, &dDenseFirst, &dDensePts, &dBulkErr, &dMeshSplit, &dTicket, &dRankTotals, &dRankBase, &dPos, &dCol, &dIdx,
 		                 &dCmdSub, &dCmdData, &dCmdCount, &dCmdOff, &dCmdOk, &dSubMode, &dSegNext[0], &dSegNext[1], &dSegStarts, &dSegHdr, &dSegCmds, &dMeshBase, &dUV, &dRXf, &dRPos, &dRCol, &dRIdx};
 		for (DevBuf* b : all) b->release();
 		for (auto& e : ev) if (e) cudaEventDestroy(e);
@@ -1665,7 +1694,7 @@ public:
 		k_group_emit<IDX, OPS, JT, CT, BIGI><<<gridBlocks < cap ? gridBlocks : cap, PPB, 0, st>>>(pa);
 	}
 
-	int run(uint32_t flags, uint64_t vertexBase, std::string* err) override
+	int run(uint32_t flags, uint64_t vertexBase, std::string* err, const MergeHook* merge = nullptr) override
 	{
 		if (!uploaded) {
 			if (err) *err = "run before upload";
@@ -1805,7 +1834,7 @@ public:
 			if (c[1]) {
 				/* the overflow arena was too small: redo this run with the two-pass flatten */
 				slotMode = false;
-				const int rc = run(flags, vertexBase, err);
+				const int rc = run(flags, vertexBase, err, merge);
 				return rc;
 			}
 			numPts = c[2];
@@ -1906,6 +1935,18 @@ public:
 			pa.meshBase = dMeshBase.as<uint32_t>();
 			finalRan = true;
 		}
+		mergedRan = false;
+		if (merge != nullptr && merge->allGatherU64 != nullptr) {
+			/* the one exchange step: all-gather of every rank's (V, I) on this stream, exclusive base on the device */
+			if (dRankTotals.ensure((size_t)merge->nranks * 16 + 16, err) || dRankBase.ensure(32, err)) return VGB_ERR_CUDA;
+			const int rc = merge->allGatherU64(merge->user, dMeshOff.as<ulonglong2>() + numJobs, dRankTotals.p, 2, (void*)st, err);
+			if (rc) return rc;
+			k_rank_base<<<1, 32, 0, st>>>(dRankTotals.as<uint64_t>(), (uint32_t)merge->rank, (uint32_t)merge->nranks, dRankBase.as<uint64_t>());
+			++launches;
+			VGB_CUDA(cudaGetLastError());
+			pa.vertexBasePtr = dRankBase.as<uint64_t>();
+			mergedRan = true;
+		}
 		VGB_CUDA(cudaEventRecord(ev[2], st));
 
 		/* ---- emit ---- */
@@ -1958,6 +1999,18 @@ public:
 		kTotals[0] = totals[0];
 		kTotals[1] = totals[1];
 		sizesKnown = true;
+		return 0;
+	}
+
+	int mergedInfo(uint64_t out[4], void** rankTotalsDev, std::string* err) override
+	{
+		if (!ran || !mergedRan) {
+			if (err) *err = "no merged run yet";
+			return VGB_ERR_STATE;
+		}
+		VGB_CUDA(cudaSetDevice(dev));
+		if (readback(out, dRankBase.p, 32, err)) return VGB_ERR_CUDA;
+		if (rankTotalsDev) *rankTotalsDev = dRankTotals.p;
 		return 0;
 	}
 
@@ -2253,5 +2306,10 @@ void* hostAlloc(size_t bytes)
 void hostFree(void* p)
 {
 	if (p) cudaFreeHost(p);
+}
+
+int copyToHost(void* dst, const void* srcDev, size_t bytes)
+{
+	return cudaMemcpy(dst, srcDev, bytes, cudaMemcpyDeviceToHost) == cudaSuccess ? 0 : VGB_ERR_CUDA;
 }
 } // namespace vgb

@@ -84,6 +84,19 @@ struct RunTimes
 	float total = 0, flatten = 0, strokeCount = 0, emit = 0;
 };
 
+/* merged vertex/index space over several GPUs: the one exchange step of the path.  After the
+ * count stage a rank knows its totals (V, I) -- on the device; the hook all-gathers the 16-byte pair of every
+ * rank into rankTotals on the pipeline's own stream (vgb_group.cpp: ncclAllGather), a one-warp kernel turns
+ * it into this rank's exclusive base, and the emit kernel adds that base to every index.  Nothing comes back
+ * to the host in between. */
+struct MergeHook
+{
+	int rank = 0, nranks = 1;
+	void* user = nullptr;
+	/* all-gather `count` uint64 from send (device) into recv (device, count * nranks) on `stream` */
+	int (*allGatherU64)(void* user, const void* send, void* recv, size_t count, void* stream, std::string* err) = nullptr;
+};
+
 /* device pipeline: owns the stream, the device buffers and the kernels */
 class Pipeline
 {
@@ -91,7 +104,10 @@ public:
 	static Pipeline* create(int device, std::string* err);
 	virtual ~Pipeline() {}
 	virtual int upload(const HostTables& t, std::string* err) = 0;
-	virtual int run(uint32_t flags, uint64_t vertexBase, std::string* err) = 0;
+	virtual int run(uint32_t flags, uint64_t vertexBase, std::string* err, const MergeHook* merge = nullptr) = 0;
+	/* after a merged run: {vertex base, index base, total vertices, total indices} of the group, and the device
+	 * array of every rank's (V, I) (2 * nranks uint64); synchronises the stream */
+	virtual int mergedInfo(uint64_t out[4], void** rankTotalsDev, std::string* err) = 0;
 	virtual int sync(std::string* err) = 0;
 	virtual void sizes(vgb_sizes* out) = 0;
 	virtual void devicePtrs(void** pos, void** color, void** index, void** mvo, void** mio, void** pts, void** subs) = 0;
@@ -111,8 +127,16 @@ public:
 };
 
 int deviceCount();
+/* vgb_group.cpp */
+int groupUniqueId(void* id128, std::string* err);
+int groupCreate(vgb_group** out, int device, int rank, int nranks, const void* id128, std::string* err);
+void groupDestroy(vgb_group* g);
+const MergeHook* groupHook(vgb_group* g);
+int groupGather(vgb_group* g, Pipeline* pipe, uint32_t idxBytes, int owner, void** pos, void** color, void** index, uint64_t info[4], float* ms,
+                std::string* err);
 void* hostAlloc(size_t bytes);
 void hostFree(void* p);
+int copyToHost(void* dst, const void* srcDev, size_t bytes);
 } // namespace vgb
 
 #endif
