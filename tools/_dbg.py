@@ -7,17 +7,20 @@ n = 1_000_000
 b = vgb.Batch(0)
 b.add_cubic_strokes(W.config3_cubics(n), width=4.0, cap=1, join=1)
 b.upload()
-mode = sys.argv[1] if len(sys.argv) > 1 else "sync"
+reps = int(sys.argv[1]) if len(sys.argv) > 1 else 200
 em = []
-for rep in range(3):
-    for i in range(40):
-        b.run()
-        if mode == "sync":
-            em.append(round(b.last_run_ms()["emit"], 3))
-    b.sync()
-    if mode != "sync":
-        em.append(round(b.last_run_ms()["emit"], 3))
-        for _ in range(4):
-            b.run(); em.append(round(b.last_run_ms()["emit"], 3))
-    time.sleep(0.2)
-print(mode, em)
+for i in range(reps):
+    b.run()
+    em.append(round(b.last_run_ms()["emit"], 2))
+# compress: print run-length of values rounded to 0.1
+out, prev, cnt = [], None, 0
+for v in em:
+    k = round(v, 1)
+    if k == prev:
+        cnt += 1
+    else:
+        if prev is not None:
+            out.append(f"{prev}x{cnt}")
+        prev, cnt = k, 1
+out.append(f"{prev}x{cnt}")
+print(os.environ.get("VGB_EMIT_PER_SM"), " ".join(out))

@@ -657,6 +657,7 @@ struct PieceArgs
 	const uint64_t* vertexBasePtr; /* merged run: this rank's base, computed on the device (nullptr otherwise) */
 	const uint32_t* meshBase; /* final layout: per-mesh index base (nullptr otherwise) */
 	uint32_t* ticket;         /* emit: dynamic group tickets (zeroed by k_mesh_off) */
+	uint32_t chunkShift;      /* emit: a ticket is worth 1 << chunkShift consecutive groups */
 	/* emit outputs */
 	float2* pos;
 	uint32_t* col;
@@ -1220,9 +1221,13 @@ __global__ void __launch_bounds__(128, (OPS == OPS_STROKE_AA && JT < 3) ? VGB_EM
 	 * The wait for the previous group's bulk copy (its reads of the staging image) sits right before
 	 * the image is written again, i.e. the copy-out of group t overlaps the classification of t + 1. */
 	const uint32_t lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-	const uint32_t W = gridDim.x * 4;
+	const uint32_t W = gridDim.x * 4; /* warps of the grid = statically assigned chunks */
 	const uint32_t numGroups = (a.numPieces + 31) >> 5;
-	uint32_t w = blockIdx.x * 4 + wib; /* the first group of every warp is static, the rest are tickets */
+	/* groups are handed out in CHUNKS of TC consecutive ones: the first chunk of every warp is static, the rest
+	 * are tickets (one same-address atomic per TC groups: at one per group the ~0.7 M atomics of a launch ran
+	 * into the L2's same-address atomic rate on some boards and doubled the kernel time) */
+	const uint32_t TC = 1u << a.chunkShift; /* 4 for large batches, 1 for small ones (all warps busy at once) */
+	uint32_t w = (blockIdx.x * 4 + wib) * TC;
 	if (w >= numGroups) {
 		return; /* whole warp out of range */
 	}
@@ -1232,13 +1237,18 @@ __global__ void __launch_bounds__(128, (OPS == OPS_STROKE_AA && JT < 3) ? VGB_EM
 	IDX* sIdx = reinterpret_cast<IDX*>(stage + POS_BYTES + COL_BYTES);
 	bool copyPending = false;
 	uint2 recA = make_uint2(0u, 0u), recB = make_uint2(0u, 0u);
-	uint32_t w1, w2;
+	uint32_t w1 = w + 1, w2 = w + 2; /* TC = 1: fixed up below */
+	uint32_t nextChunk = 0; /* lane 0: the prefetched ticket (valid in lane 0 only until it is consumed) */
 	{
-		uint32_t t = 0;
-		if (lane == 0) t = atomicAdd(a.ticket, 2u);
-		t = __shfl_sync(0xffffffffu, t, 0);
-		w1 = W + t;
-		w2 = W + t + 1;
+		if (TC == 1) {
+			/* every group is its own chunk: the next two groups are tickets already */
+			uint32_t t = 0;
+			if (lane == 0) t = atomicAdd(a.ticket, 2u);
+			t = __shfl_sync(0xffffffffu, t, 0);
+			w1 = W + t;
+			w2 = W + t + 1;
+		}
+		if (lane == 0) nextChunk = atomicAdd(a.ticket, 1u);
 		const uint32_t g0 = w * 32 + lane;
 		if (g0 < a.numPieces) recA = a.pieceRec[g0];
 		const uint32_t g1 = w1 * 32 + lane;
@@ -1250,10 +1260,8 @@ __global__ void __launch_bounds__(128, (OPS == OPS_STROKE_AA && JT < 3) ? VGB_EM
 	const uint2 rec = recA;
 	const uint32_t j = rec.x;
 	recA = recB;
-	uint32_t ticket = 0;
 	{
-		/* the ticket of the group three ahead, the records of the group two ahead, L2 prefetch for the group one ahead */
-		if (lane == 0) ticket = atomicAdd(a.ticket, 1u);
+		/* the records of the group two ahead, L2 prefetch for the group one ahead */
 		const uint32_t g2 = w2 * 32 + lane;
 		recB = make_uint2(0u, 0u);
 		if (w2 < numGroups && g2 < a.numPieces) recB = a.pieceRec[g2];
@@ -1369,7 +1377,13 @@ __global__ void __launch_bounds__(128, (OPS == OPS_STROKE_AA && JT < 3) ? VGB_EM
 	/* next group: tickets keep the groups in flight a contiguous window of the output whatever the warps' pace */
 	w = w1;
 	w1 = w2;
-	w2 = W + __shfl_sync(0xffffffffu, ticket, 0);
+	if (((w2 + 1) & (TC - 1)) != 0) {
+		++w2;
+	} else {
+		/* chunk boundary: consume the prefetched ticket (it was issued TC groups ago) and ask for the next */
+		w2 = (W + __shfl_sync(0xffffffffu, nextChunk, 0)) << a.chunkShift;
+		if (lane == 0) nextChunk = atomicAdd(a.ticket, 1u);
+	}
 	if (w >= numGroups) {
 		break;
 	}
@@ -1685,13 +1699,20 @@ public:
 			const char* e = getenv("VGB_EMIT_WAVES");
 			waves = e ? atoi(e) : 1;
 			if (waves < 1) waves = 1;
+			const char* f = getenv("VGB_EMIT_PER_SM"); /* tuning / diagnosis: resident blocks per SM the grid is sized for */
+			if (f && atoi(f) > 0) perSM = atoi(f);
 		}
 		if (numSMs == 0) {
 			if (cudaDeviceGetAttribute(&numSMs, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || numSMs < 1) numSMs = 148;
 		}
 		const uint32_t cap = (uint32_t)perSM * (uint32_t)numSMs * (uint32_t)waves;
 		if (getenv("VGB_DEBUG")) fprintf(stderr, "[vgb] emit grid: perSM %d numSMs %d waves %d blocks %u of %u\n", perSM, numSMs, waves, gridBlocks < cap ? gridBlocks : cap, gridBlocks);
-		k_group_emit<IDX, OPS, JT, CT, BIGI><<<gridBlocks < cap ? gridBlocks : cap, PPB, 0, st>>>(pa);
+		/* large batches: a ticket is a chunk of 4 consecutive groups (a quarter of the same-address atomics);
+		 * small ones keep one group per ticket so that every warp has work at once */
+		PieceArgs q = pa;
+		q.chunkShift = gridBlocks >= 8 * cap ? 2u : 0u;
+		const uint32_t need = (gridBlocks + (1u << q.chunkShift) - 1) >> q.chunkShift;
+		k_group_emit<IDX, OPS, JT, CT, BIGI><<<need < cap ? need : cap, PPB, 0, st>>>(q);
 	}
 
 	int run(uint32_t flags, uint64_t vertexBase, std::string* err, const MergeHook* merge = nullptr) override

@@ -96,8 +96,10 @@ def tiger_like(num_paths=240, seed=7):
     return r.tables()
 
 
-def instance_tables(t, num_instances, seed=11, fringe=1.0):
+def instance_tables(t, num_instances, seed=11, fringe=1.0, first=0, total=None):
     """config 5: the scene x num_instances, each with T(U[0,4096)^2) * R(U[0,2pi)) * S(U[0.5,2)).
+    first / total: this is the slice [first, first + num_instances) of a stream of `total` instances (ranks shard by
+    range and must draw the same transform for the same instance whatever the world size).
     Reference semantics (vg.cpp:2969-2981, 3416-3433): the path is flattened with scale = avgScale,
     stroke width = clamp(width * avgScale, 0, 200), thin stroke when that is <= fringe."""
     from .tables import BatchTables
@@ -112,9 +114,11 @@ def instance_tables(t, num_instances, seed=11, fringe=1.0):
     out.draw_begin = np.concatenate([(t.draw_begin[:-1][None, :] + k * ndraw).reshape(-1), [M * ndraw]]).astype(np.uint32)
     out.cmd = np.tile(t.cmd, M)
     out.data = np.tile(t.data, M)
-    s = rng.uniform(0.5, 2.0, M).astype(np.float32)
-    a = rng.uniform(0, 2 * np.pi, M)
-    tx, ty = rng.uniform(0, 4096, M), rng.uniform(0, 4096, M)
+    T = M + first if total is None else total
+    sl = slice(first, first + M)
+    s = rng.uniform(0.5, 2.0, T).astype(np.float32)[sl]
+    a = rng.uniform(0, 2 * np.pi, T)[sl]
+    tx, ty = rng.uniform(0, 4096, T)[sl], rng.uniform(0, 4096, T)[sl]
     m = np.stack([s * np.cos(a), s * np.sin(a), -s * np.sin(a), s * np.cos(a), tx, ty], 1).astype(np.float32)
     out.path_xform = np.repeat(m, P, axis=0).reshape(-1)
     out.path_scale = np.repeat(s, P)
