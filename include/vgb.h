@@ -13,7 +13,7 @@
  *   src/vg.cpp:3061-3179 ctxFillPathColor (convex)         vgb_batch_convex_fill
  *   src/vg.cpp:4957-4975 transformPath                     xform6 argument of begin_path
  *   src/vg.cpp:5207-5244 createDrawCommand_VertexColor     VGB_RUN_INDEX_U32 merged buffers /
- *                                                          vgb_batch_download_bgfx_streams
+ *                                                          vgb_batch_download_final
  *
  * Plain C types only: pointers, sizes, PODs.  No torch / CUDA types in any signature
  * (device pointers are returned as void*).  All functions return 0 on success, a negative
@@ -81,7 +81,12 @@ enum {
 /* vgb_batch_run flags */
 enum {
 	VGB_RUN_INDEX_U16 = 0, /* per-mesh local uint16 indices: exactly vg::Mesh::m_IndexBuffer */
-	VGB_RUN_INDEX_U32 = 1  /* merged uint32 indices: local + mesh first vertex + vertex_base  */
+	VGB_RUN_INDEX_U32 = 1, /* merged uint32 indices: local + mesh first vertex + vertex_base  */
+	/* strokerConvexFillAA index ORDER of the reference's stock x86 build (VG_CONFIG_ENABLE_SIMD=1, stroker.cpp:616-701):
+	 * Q0, F0,Q1, F1,Q2, ... F(N-3),Q(N-2), Q(N-1) instead of the scalar build's [all fan triangles][all fringe quads]
+	 * (stroker.cpp:768-796).  Same triangles, same vertices (values stay those of the scalar build: the SSE
+	 * build's approximate rsqrt/rcp are hardware dependent and not a parity target). */
+	VGB_RUN_FILL_ORDER_SSE = 2
 };
 
 /* Final layout: what vg.cpp's merge step createDrawCommand_VertexColor
@@ -209,7 +214,8 @@ VGB_API int vgb_batch_add_paths(vgb_batch* b, uint32_t num_paths, const uint32_t
 /* zero-copy variant for the host-buffer path: REPLACES everything recorded by the n paths of
  * vgb_batch_add_cubic_strokes, but p8 is only borrowed -- it is read (DMA, straight from the
  * caller's memory: make it pinned) by the next vgb_batch_upload / _run / _execute, where the command,
- * sub-path and job tables are generated on the device; keep it valid and unchanged until then.
+ * sub-path and job tables are generated on the device; keep it valid and unchanged until the next vgb_batch_sync (or any
+ * download) returns: vgb_batch_upload only ENQUEUES the copy on the batch's stream.
  * Non-finite coordinates are detected on the device: the run fails with VGB_ERR_NONFINITE. */
 VGB_API int vgb_batch_set_cubic_strokes(vgb_batch* b, const float* p8, uint32_t n, float scale, float tess_tol,
                                         uint32_t op, uint32_t color, float width, uint32_t cap, uint32_t join);
@@ -266,11 +272,16 @@ typedef struct vgb_cl_stats {
 	uint32_t commands;    /* records decoded                                         */
 	uint32_t paths;       /* BeginPath                                               */
 	uint32_t draws;       /* fills / strokes recorded into the batch                 */
-	uint32_t culled;      /* stroker commands skipped under a zero-sized scissor     */
+	uint32_t culled;      /* stroker commands skipped under a zero-sized scissor, or belonging to a
+	                       * path begun under a collapsed transform (average scale 0: invisible)   */
 	uint32_t zero_alpha;  /* draws dropped because their colour ends up transparent  */
 	uint32_t unsupported; /* commands outside this path (see above)                  */
 	uint32_t state_depth; /* states left pushed when the list ended                  */
 	uint32_t nested;      /* SubmitCommandList commands executed                     */
+	uint32_t scissor_changes; /* recorded draws whose (uint16) scissor rect differs from the previous draw's: vg.cpp starts a
+	                       * new DrawCommand there (m_ForceNewDrawCommand, vg.cpp:3946-4033, 5359-5405).  The batch does NOT
+	                       * carry scissor rects: with vgb_batch_set_final_layout the draw-command table is only valid for
+	                       * lists where this is 0 -- otherwise split the submission at the scissor changes */
 } vgb_cl_stats;
 
 VGB_API int vgb_batch_submit_command_list(vgb_batch* b, const void* commands, uint32_t size, vgb_cl_context* ctx, vgb_cl_stats* stats);

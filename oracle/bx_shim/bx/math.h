@@ -47,7 +47,7 @@ template<typename T> inline T min(const T& a, const T& b) { return a < b ? a : b
 template<typename T> inline T max(const T& a, const T& b) { return a > b ? a : b; }
 template<typename T> inline T min(const T& a, const T& b, const T& c) { return min(min(a, b), c); }
 template<typename T> inline T max(const T& a, const T& b, const T& c) { return max(max(a, b), c); }
-template<typename T> inline T clamp(const T& a, const T& lo, const T& hi) { return max(min(a, hi), lo); }
+template<typename T> inline T clamp(const T& a, const T& lo, const T& hi) { return min(max(a, lo), hi); } /* bx order */
 }
 
 #endif

@@ -223,3 +223,28 @@ def test_nested_lists(sincos):
     lim = vgb.Batch(-1)
     st3 = lim.submit_command_list(top.bytes(), vgb.make_cl_context(lists={k: (w.bytes(), fl) for k, (w, fl) in lists.items()}, max_depth=1))
     assert st3.draws == 1 and st3.nested == 4
+
+
+def test_collapsed_transform_does_not_abort_the_list():
+    """A path begun under TransformScale(0, 0) (average scale 0) is legal in the reference (tessTol = inf, zero-alpha
+    strokes, zero-area fills: nothing visible) and the list keeps executing.  The decoder must not reject it: the dead
+    path's commands and draws are skipped, everything after PopState is recorded as usual."""
+    w = (CL.Writer().push_state().scale(0, 0).begin_path().move_to(0, 0).cubic_to(10, 0, 20, 5, 30, 30).line_to(5, 40).close_path()
+         .fill(0xFF112233, CL.fill_flags()).stroke(0xFF445566, 3.0, CL.stroke_flags(1, 1, True)).pop_state()
+         .begin_path().rect(10, 10, 50, 40).fill(0xFF778899, CL.fill_flags()).set_scissor(0, 0, 100, 100)
+         .begin_path().circle(50, 50, 20).stroke(0xFF000000, 2.0, CL.stroke_flags(0, 0, True)))
+    got = vgb.Batch(-1)
+    ctx = vgb.make_cl_context()
+    st = got.submit_command_list(w.bytes(), ctx)
+    assert st.paths == 3 and st.draws == 2 and st.culled == 2 and st.state_depth == 0
+    assert st.scissor_changes == 1  # the second recorded draw runs under another scissor rect than the first
+    expect = vgb.Batch(-1)
+    expect.begin_path(1.0, 0.25, [1, 0, 0, 1, 0, 0])
+    expect.rect(10, 10, 50, 40)
+    expect.convex_fill(0xFF778899, True)
+    expect.begin_path(1.0, 0.25, [1, 0, 0, 1, 0, 0])
+    expect.circle(50, 50, 20)
+    expect.stroke(0, 0xFF000000, 2.0, 0, 0)
+    a, b = got.recorded_streams(), expect.recorded_streams()
+    for k in ("cmd", "data", "draw_op", "draw_color", "draw_width", "path_scale"):
+        np.testing.assert_array_equal(a[k], b[k], err_msg=k)

@@ -610,3 +610,158 @@ def test_dropin_linked_build_equals_reference(ref):
     for t in (mixed_recorder().tables(), BatchTables.cubic_strokes(W.config3_cubics(300, first=3), width=4.0, cap=1, join=1),
               BatchTables.rounded_rect_fills(W.config4_rrects(50, 32))):
         check_same(d.run_batch(t), ref.run_batch(t))
+
+
+@pytest.mark.parametrize("generic", [False, True])
+def test_sse_fill_index_order_flag(gpu_batch, ref, generic, monkeypatch):
+    """VGB_RUN_FILL_ORDER_SSE: strokerConvexFillAA's indices in the order the reference's stock x86 build (SIMD=1) emits
+    (stroker.cpp:616-701: Q0, F0,Q1, ... F(N-3),Q(N-2), Q(N-1)) -- bit-exact against libvgref_sse.so's index buffers;
+    vertex values stay those of the scalar build (golden).  Both the closed-form fill path and the general piece kernels."""
+    from oracle.pyref import RefLib, have_ref
+    if not have_ref("sse"):
+        pytest.skip("oracle/_ref/libvgref_sse.so not built")
+    sse = RefLib("sse")
+    if generic:
+        monkeypatch.setenv("VGB_GENERIC_FILL", "1")
+    cases = [BatchTables.rounded_rect_fills(np.concatenate([W.config4_rrects(40, r) for r in (2, 8, 32, 128)]))]
+    r = Recorder(fringe=1.0)  # fills of 3..9-gons (every remainder of the SIMD loop's unrolling) mixed with strokes
+    rng = np.random.default_rng(5)
+    for n in (3, 4, 5, 6, 7, 8, 9, 13, 40):
+        a = np.sort(rng.uniform(0, 2 * np.pi, n))
+        pts = np.stack([200 + 90 * np.cos(a), 200 + 70 * np.sin(a)], 1)
+        r.begin_path().move_to(*pts[0])
+        for p in pts[1:]:
+            r.line_to(*p)
+        r.close().convex_fill(0xFF336699, True)
+        if generic:
+            r.stroke(0, 0xFF000000, 3.0, 1, 1)
+    cases.append(r.tables())
+    for t in cases:
+        b = vgb.Batch(0)
+        b.add_tables(t)
+        b.run(fill_order_sse=True)
+        out = b.download()
+        exp_idx = sse.run_batch(t)
+        exp_val = ref.run_batch(t)
+        np.testing.assert_array_equal(out["mesh_idx_off"], exp_idx["mesh_idx_off"])
+        np.testing.assert_array_equal(out["index"], exp_idx["index"])      # the SIMD build's order
+        np.testing.assert_array_equal(out["pos"], exp_val["pos"])          # the scalar build's values
+        np.testing.assert_array_equal(out["color"], exp_val["color"])
+        b.run()  # and back: the default order again (sizes re-learnt)
+        check_same(b.download(), exp_val)
+
+
+def _ref_chunk(args):
+    first, count = args
+    from oracle.pyref import RefLib
+    t = BatchTables.cubic_strokes(W.config3_cubics(count, first=first), width=4.0, cap=1, join=1)
+    o = RefLib("scalar").run_batch(t)
+    return o["num_vertices"], o["num_indices"], o["num_points"], o["checksum"], o["pos"], o["color"], o["index"], o["mesh_vtx_off"], o["mesh_idx_off"]
+
+
+def test_full_size_1m_benchmark_workload_equals_reference(ref):
+    """The BENCHMARKED workload at full size (BASELINE configs[2]: 1 M cubics, AA stroke, round/round, uint16): every
+    vertex, colour, index and mesh offset of the 3.9 GB the GPU emits against the compiled reference, which works
+    through the same stream in 20 chunks on the host cores; plus the reference's own order-sensitive checksum
+    (oracle/ref_capi.cpp: totals[4]) recomputed from the GPU output chunk by chunk."""
+    import multiprocessing as mp
+    n, chunks = 1_000_000, 20
+    b = vgb.Batch(0)
+    b.add_cubic_strokes(W.config3_cubics(n), width=4.0, cap=1, join=1)
+    b.run()
+    out = b.download()
+    per = n // chunks
+    with mp.get_context("fork").Pool(min(chunks, max(1, (mp.cpu_count() or 2) // 2))) as pool:
+        res = pool.map(_ref_chunk, [(k * per, per) for k in range(chunks)], chunksize=1)
+    v0 = i0 = pts = 0
+    P = np.uint64(1099511628211)
+    for k, (nv, ni, npts, chk, pos, col, idx, mvo, mio) in enumerate(res):
+        m0, m1 = k * per, (k + 1) * per
+        np.testing.assert_array_equal(out["mesh_vtx_off"][m0:m1 + 1] - np.uint64(v0), mvo)
+        np.testing.assert_array_equal(out["mesh_idx_off"][m0:m1 + 1] - np.uint64(i0), mio)
+        np.testing.assert_array_equal(out["index"][i0:i0 + ni], idx)
+        np.testing.assert_array_equal(out["color"][v0:v0 + nv], col)
+        np.testing.assert_array_equal(out["pos"][v0:v0 + nv], pos)
+        # the reference's checksum over this chunk's meshes, from the GPU output
+        gv = (out["mesh_vtx_off"][m0 + 1:m1 + 1] - out["mesh_vtx_off"][m0:m1]).astype(np.uint64)
+        gi = out["mesh_idx_off"][m0 + 1:m1 + 1] - out["mesh_idx_off"][m0:m1]
+        keep = gi > 0
+        last = out["index"][(out["mesh_idx_off"][m0 + 1:m1 + 1] - np.uint64(1)).astype(np.int64)[keep]].astype(np.uint64)
+        term = last + gv[keep]
+        with np.errstate(over="ignore"):
+            pw = np.cumprod(np.concatenate([[np.uint64(1)], np.full(len(term) - 1, P, np.uint64)]))[::-1]
+            assert int(np.sum(term * pw, dtype=np.uint64)) == chk
+        v0, i0, pts = v0 + nv, i0 + ni, pts + npts
+    assert (v0, i0, pts) == (out["num_vertices"], out["num_indices"], out["num_points"])
+
+
+def _long_subpath_scene(seed):
+    """long sub-paths that exercise every branch of the command-parallel flatten (k_cmd_flatten): end points removed
+    by the epsilon-dedupe (a command whose end coincides with the previous end), repeated lineTo, a zero-length cubic
+    before CLOSE, sub-paths that are not eligible (RECT / ARC / polyline) mixed with eligible ones, path transforms."""
+    rng = np.random.default_rng(seed)
+    r = Recorder(fringe=1.0)
+    for p in range(40):
+        xf = None if p % 3 else [1.1, 0.2, -0.2, 0.9, 5.0, -3.0]
+        r.begin_path(1.0 if p % 2 else 1.7, 0.25, xf)
+        x, y = rng.uniform(50, 900, 2)
+        r.move_to(x, y)
+        for k in range(int(rng.integers(9, 30))):
+            kind = rng.integers(0, 7)
+            nx, ny = x + rng.uniform(-60, 60), y + rng.uniform(-60, 60)
+            if kind == 0:
+                r.line_to(nx, ny)
+            elif kind == 1:
+                r.line_to(x + 1e-3, y - 1e-3)      # within epsilon of the last kept vertex: dropped, cmdOk = 0 downstream
+                nx, ny = x, y
+            elif kind == 2:
+                r.line_to(nx, ny).line_to(nx, ny)  # exact repeat
+            elif kind == 3:
+                r.quadratic_to(x + rng.uniform(-40, 40), y + rng.uniform(-40, 40), nx, ny)
+            elif kind == 4:
+                r.cubic_to(x, y, x, y, x, y)       # zero-length cubic (count 0 after the dedupe)
+                nx, ny = x, y
+            else:
+                r.cubic_to(x + rng.uniform(-50, 50), y + rng.uniform(-50, 50), nx + rng.uniform(-50, 50), ny + rng.uniform(-50, 50), nx, ny)
+            x, y = nx, ny
+        if p % 4 == 0:
+            r.line_to(*r.paths[-1]["cmds"][0][1])  # end on the first point: pathClose drops the last vertex
+        if p % 2 == 0:
+            r.close()
+        if p % 5 == 0:
+            r.rect(10, 10, 30, 20)                 # a second, ineligible sub-path in the same path
+        if p % 7 == 0:
+            r.move_to(400, 400).arc(400, 300, 60, 0.2, 2.0, False)
+        r.convex_fill(0xFF102030, True) if p % 6 == 0 else None
+        r.stroke(0, 0xFF334455, float(rng.uniform(1.5, 6.0)), int(rng.integers(0, 3)), int(rng.integers(0, 3)))
+    return r.tables()
+
+
+@pytest.mark.parametrize("mode", ["0", "1"])
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_command_parallel_flatten_on_and_off(ref, monkeypatch, mode, seed):
+    """VGB_CMD_FLATTEN=0/1 A/B: thread-per-sub-path walk vs thread-per-command flatten (with its per-sub-path fallback)
+    on long sub-paths built to hit the fallback branches; both must equal the compiled reference bit for bit."""
+    monkeypatch.setenv("VGB_CMD_FLATTEN", mode)
+    t = _long_subpath_scene(seed)
+    b = vgb.Batch(0)
+    b.add_tables(t)
+    b.run()
+    exp = ref.run_batch(t)
+    check_same(b.download(), exp)
+    pts, subs = b.download_paths()
+    assert len(pts) == exp["num_points"] and len(subs) == exp["num_subpaths"]
+    b.run(index_u32=True)  # re-run of the same upload (sizes known)
+    assert b.download()["num_vertices"] == exp["num_vertices"]
+
+
+def test_per_object_api_survives_bad_input():
+    """The per-object (drop-in) API has no error channel: input-dependent failures (a NaN vertex, a non-finite width)
+    must give an EMPTY mesh and leave the reason in vgb_last_error -- not abort the host process."""
+    s = vgb.Stroker()
+    s.reset(1.0, 0.25, 1.0)
+    pos, col, idx = s.polyline_stroke_aa(np.array([[0, 0], [np.nan, 5], [10, 10]], np.float32), False, 0xFFFFFFFF, 3.0, 1, 1)
+    assert len(pos) == 0 and len(idx) == 0
+    assert b"non-finite" in vgb.load_library().vgb_last_error()
+    pos, col, idx = s.polyline_stroke_aa(np.array([[0, 0], [10, 5], [20, 0]], np.float32), False, 0xFFFFFFFF, 3.0, 1, 1)
+    assert len(pos) > 0 and len(idx) > 0  # and the object keeps working

@@ -18,6 +18,7 @@ JOIN_MITER, JOIN_ROUND, JOIN_BEVEL = 0, 1, 2
 WINDING_CCW, WINDING_CW = 0, 1
 OP_STROKE_AA, OP_CONVEX_FILL_AA, OP_STROKE, OP_STROKE_AA_THIN, OP_CONVEX_FILL = range(5)
 INDEX_U16, INDEX_U32 = 0, 1
+FILL_ORDER_SSE = 2
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 
@@ -79,7 +80,7 @@ class ClContext(C.Structure):
 
 class ClStats(C.Structure):
     """vgb_cl_stats"""
-    _fields_ = [(k, C.c_uint32) for k in ("commands", "paths", "draws", "culled", "zero_alpha", "unsupported", "state_depth", "nested")]
+    _fields_ = [(k, C.c_uint32) for k in ("commands", "paths", "draws", "culled", "zero_alpha", "unsupported", "state_depth", "nested", "scissor_changes")]
 
 
 def make_cl_context(xform=(1, 0, 0, 1, 0, 0), global_alpha=1.0, tess_tolerance=0.25, canvas=(1280.0, 720.0), scissor=None, flags=0,
@@ -374,9 +375,10 @@ class Batch:
     # ---- execution ----
     def upload(self): return self._chk(self.L.vgb_batch_upload(self.h))
 
-    def run(self, index_u32=False, vertex_base=0):
+    def run(self, index_u32=False, vertex_base=0, fill_order_sse=False):
+        """fill_order_sse: strokerConvexFillAA indices in the order of the reference's SIMD build (VGB_RUN_FILL_ORDER_SSE)"""
         self.index_u32 = bool(index_u32)
-        return self._chk(self.L.vgb_batch_run(self.h, INDEX_U32 if index_u32 else INDEX_U16, vertex_base))
+        return self._chk(self.L.vgb_batch_run(self.h, (INDEX_U32 if index_u32 else INDEX_U16) | (FILL_ORDER_SSE if fill_order_sse else 0), vertex_base))
 
     def run_merged(self, group):
         """run as one rank of `group`: merged uint32 indices, base from the in-library all-gather (asynchronous)"""

@@ -229,59 +229,70 @@ int vgb_batch_set_path_xform(vgb_batch* b, const float* xform6)
 
 int vgb_batch_move_to(vgb_batch* b, float x, float y)
 {
+	if (!b) return fail(VGB_ERR_INVALID, "null batch");
 	const float d[2] = {x, y};
 	return b->push(VGB_CMD_MOVE_TO, d, 2, true);
 }
 int vgb_batch_line_to(vgb_batch* b, float x, float y)
 {
+	if (!b) return fail(VGB_ERR_INVALID, "null batch");
 	const float d[2] = {x, y};
 	return b->push(VGB_CMD_LINE_TO, d, 2, false);
 }
 int vgb_batch_cubic_to(vgb_batch* b, float c1x, float c1y, float c2x, float c2y, float x, float y)
 {
+	if (!b) return fail(VGB_ERR_INVALID, "null batch");
 	const float d[6] = {c1x, c1y, c2x, c2y, x, y};
 	return b->push(VGB_CMD_CUBIC_TO, d, 6, false);
 }
 int vgb_batch_quadratic_to(vgb_batch* b, float cx, float cy, float x, float y)
 {
+	if (!b) return fail(VGB_ERR_INVALID, "null batch");
 	const float d[4] = {cx, cy, x, y};
 	return b->push(VGB_CMD_QUAD_TO, d, 4, false);
 }
 int vgb_batch_arc_to(vgb_batch* b, float x1, float y1, float x2, float y2, float r)
 {
+	if (!b) return fail(VGB_ERR_INVALID, "null batch");
 	const float d[5] = {x1, y1, x2, y2, r};
 	return b->push(VGB_CMD_ARC_TO, d, 5, false);
 }
 int vgb_batch_rect(vgb_batch* b, float x, float y, float w, float h)
 {
+	if (!b) return fail(VGB_ERR_INVALID, "null batch");
 	if (degenerateRect(w, h)) return 0; /* pathRect returns without touching the path */
 	const float d[4] = {x, y, w, h};
 	return b->push(VGB_CMD_RECT, d, 4, true);
 }
 int vgb_batch_rounded_rect(vgb_batch* b, float x, float y, float w, float h, float r)
 {
+	if (!b) return fail(VGB_ERR_INVALID, "null batch");
 	if (r < 0.1f && degenerateRect(w, h)) return 0; /* path.cpp:290-293 */
 	const float d[5] = {x, y, w, h, r};
 	return b->push(VGB_CMD_ROUNDED_RECT, d, 5, true);
 }
 int vgb_batch_rounded_rect_varying(vgb_batch* b, float x, float y, float w, float h, float rtl, float rtr, float rbr, float rbl)
 {
+	if (!b) return fail(VGB_ERR_INVALID, "null batch");
 	if (rtl < 0.1f && rbl < 0.1f && rbr < 0.1f && rtr < 0.1f && degenerateRect(w, h)) return 0; /* path.cpp:413-416 */
 	const float d[8] = {x, y, w, h, rtl, rtr, rbr, rbl};
 	return b->push(VGB_CMD_ROUNDED_RECT_VARYING, d, 8, true);
 }
 int vgb_batch_circle(vgb_batch* b, float x, float y, float r)
 {
+	if (!b) return fail(VGB_ERR_INVALID, "null batch");
 	const float d[3] = {x, y, r};
 	return b->push(VGB_CMD_CIRCLE, d, 3, true);
 }
 int vgb_batch_ellipse(vgb_batch* b, float x, float y, float rx, float ry)
 {
+	if (!b) return fail(VGB_ERR_INVALID, "null batch");
 	const float d[4] = {x, y, rx, ry};
 	return b->push(VGB_CMD_ELLIPSE, d, 4, true);
 }
 int vgb_batch_arc(vgb_batch* b, float x, float y, float r, float a0, float a1, uint32_t dir)
 {
+	if (!b) return fail(VGB_ERR_INVALID, "null batch");
 	/* pathArc normalises its angles with `while (a > 2pi) a -= 2pi` (path.cpp:635-645): beyond ~1e8 the
 	 * subtraction no longer changes a float and the reference never returns; a device thread would spin
 	 * the same way.  Angles that large are refused at record time like non-finite coordinates are. */
@@ -292,6 +303,7 @@ int vgb_batch_arc(vgb_batch* b, float x, float y, float r, float a0, float a1, u
 }
 int vgb_batch_polyline(vgb_batch* b, const float* coords, uint32_t n)
 {
+	if (!b) return fail(VGB_ERR_INVALID, "null batch");
 	if (!coords && n) return fail(VGB_ERR_INVALID, "null coords");
 	if (!finite_all(coords, 2 * (size_t)n)) return fail(VGB_ERR_NONFINITE, "non-finite coordinate");
 	float hdr;
@@ -309,6 +321,7 @@ int vgb_batch_polyline(vgb_batch* b, const float* coords, uint32_t n)
 }
 int vgb_batch_close(vgb_batch* b)
 {
+	if (!b) return fail(VGB_ERR_INVALID, "null batch");
 	return b->push(VGB_CMD_CLOSE, nullptr, 0, false);
 }
 
@@ -1089,8 +1102,13 @@ static void strokerRun(vgb_stroker* s, vgb_mesh* mesh, uint32_t op, const float*
 	int rc = vgb_batch_set_polylines(b, vtx, n, &first, &n, &cl, 1, s->scale, s->tol);
 	if (!rc) rc = vgb_batch_draw_polyline(b, 0, op, color, width, cap, join);
 	if (!rc) rc = vgb_batch_run(b, VGB_RUN_INDEX_U16, 0);
+	if (rc == VGB_ERR_INVALID || rc == VGB_ERR_NONFINITE) {
+		/* input-dependent (a NaN vertex out of the caller's transform, a non-finite width, scale <= 0): the reference
+		 * has no error channel and produces a degenerate mesh; here: an EMPTY mesh, the reason in vgb_last_error() */
+		return;
+	}
 	if (rc) {
-		fprintf(stderr, "libvgb200: %s\n", t_err.c_str());
+		fprintf(stderr, "libvgb200: %s\n", t_err.c_str()); /* device failure: there is no CPU path to fall back to */
 		abort();
 	}
 	vgb_sizes sz;

@@ -87,7 +87,18 @@ struct Run /* what one top-level submit shares with the lists it nests */
 	std::vector<State> stack;
 	float fringe;
 	bool inClip;
+	bool deadPath = false;   /* the current path was begun under a collapsed transform (avgScale <= 0) */
 	uint32_t depth, maxDepth;
+	/* scissor of the last recorded draw (uint16-truncated like DrawCommand::m_ScissorRect, vg.cpp:5392-5395) */
+	uint16_t lastScissor[4] = {0, 0, 0, 0};
+	bool anyDraw = false;
+	void noteDraw(const float* sc)
+	{
+		const uint16_t r[4] = {(uint16_t)sc[0], (uint16_t)sc[1], (uint16_t)sc[2], (uint16_t)sc[3]};
+		if (anyDraw && memcmp(r, lastScissor, sizeof(r)) != 0) ++st.scissor_changes;
+		memcpy(lastScissor, r, sizeof(r));
+		anyDraw = true;
+	}
 };
 
 int runList(Run& R, const void* buffer, uint32_t size, uint32_t listFlags)
@@ -127,11 +138,20 @@ int runList(Run& R, const void* buffer, uint32_t size, uint32_t listFlags)
 			cmd = next;
 			continue;
 		}
+		if (R.deadPath && (isStroker || (type >= CL_MoveTo && type <= CL_ClosePath))) {
+			if (isStroker) ++st.culled;
+			cmd = next;
+			continue;
+		}
 		auto need = [&](uint32_t bytes) { return dataSize >= bytes; };
 #define BAD fail(VGB_ERR_INVALID, "malformed command payload")
 		switch (type) {
 		case CL_BeginPath: /* ctxBeginPath, vg.cpp:2969-2981: flatten scale = the state's average scale NOW */
-			rc = vgb_batch_begin_path(b, s->avgScale, ctx->tess_tolerance, nullptr);
+			/* A collapsed transform (TransformScale(0, 0) ...: avgScale 0) is legal in the reference: tessTol becomes
+			 * inf, every stroke gets zero alpha, every fill a zero-area polygon -- nothing visible, and the list keeps
+			 * executing.  Here such a path is DEAD: its commands and draws are skipped (counted as culled). */
+			R.deadPath = !(s->avgScale > 0.0f) || !(s->avgScale < 3.0e38f);
+			if (!R.deadPath) rc = vgb_batch_begin_path(b, s->avgScale, ctx->tess_tolerance, nullptr);
 			++st.paths;
 			break;
 		case CL_ClosePath: rc = vgb_batch_close(b); break;
@@ -176,6 +196,7 @@ int runList(Run& R, const void* buffer, uint32_t size, uint32_t listFlags)
 			}
 			vgb_batch_set_path_xform(b, s->mtx); /* transformPath: the state transform at the path's FIRST draw, vg.cpp:4957-4975 */
 			rc = vgb_batch_convex_fill(b, col, (flags & 0x04u) != 0);
+			R.noteDraw(s->scissor);
 			++st.draws;
 		} break;
 		case CL_StrokePathColor: {
@@ -205,6 +226,7 @@ int runList(Run& R, const void* buffer, uint32_t size, uint32_t listFlags)
 			const uint32_t op = !aa ? VGB_OP_STROKE : (thin ? VGB_OP_STROKE_AA_THIN : VGB_OP_STROKE_AA);
 			vgb_batch_set_path_xform(b, s->mtx);
 			rc = vgb_batch_stroke(b, op, col, thin ? fringe : scaled, (flags >> 2) & 3u, flags & 3u);
+			R.noteDraw(s->scissor);
 			++st.draws;
 		} break;
 		case CL_FillPathGradient: case CL_FillPathImagePattern: case CL_StrokePathGradient: case CL_StrokePathImagePattern:

@@ -60,7 +60,7 @@ namespace vgb
 #define VGB_EMIT_MIN_BLOCKS_SPEC 8
 #endif
 #ifndef VGB_EMIT_MIN_BLOCKS
-#define VGB_EMIT_MIN_BLOCKS 9
+#define VGB_EMIT_MIN_BLOCKS 6
 #endif
 static constexpr uint32_t PPB = 128; /* threads per block of the piece kernels (4 warps = 4 groups) */
 
@@ -580,11 +580,11 @@ __global__ void k_draw_prep(const DrawRec* __restrict__ draws, uint32_t n, const
 }
 
 __global__ void k_job_pieces(const uint32_t* __restrict__ jobSub, const uint32_t* __restrict__ jobDraw, uint32_t numJobs,
-                             const uint32_t* __restrict__ subNum, const DrawRec* __restrict__ draws, uint32_t* __restrict__ jobPieces)
+                             const uint32_t* __restrict__ subNum, const DrawRec* __restrict__ draws, uint32_t* __restrict__ jobPieces, uint32_t sseFill)
 {
 	const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
 	if (j >= numJobs) return;
-	jobPieces[j] = pieceCount(draws[jobDraw[j]].ocj & 0xFF, subNum[jobSub[j]]);
+	jobPieces[j] = pieceCount(draws[jobDraw[j]].ocj & 0xFF, subNum[jobSub[j]], sseFill != 0);
 }
 
 /* per job: the 48-byte record the piece kernels read, and for each of its pieces the record
@@ -596,7 +596,7 @@ __global__ void __launch_bounds__(256) k_job_prep(const uint32_t* __restrict__ j
                                                   const uint32_t* __restrict__ subFirst, const uint32_t* __restrict__ subNum,
                                                   const uint8_t* __restrict__ subClosed, const DrawDerived* __restrict__ dd,
                                                   const uint32_t* __restrict__ pieceStart, JobRec* __restrict__ jobRec,
-                                                  uint2* __restrict__ pieceRec)
+                                                  uint2* __restrict__ pieceRec, uint32_t sseFill)
 {
 	const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
 	const uint32_t lane = threadIdx.x & 31;
@@ -608,12 +608,12 @@ __global__ void __launch_bounds__(256) k_job_prep(const uint32_t* __restrict__ j
 		r.first = subFirst[sp];
 		r.N = subNum[sp];
 		const uint32_t op = d.ocj & 0xFF, cap = (d.ocj >> 8) & 0xFF, join = (d.ocj >> 16) & 0xFF;
-		r.flags = (uint32_t)(subClosed[sp] & 1) | (((d.ocj >> 24) & 1u) << 1) | (op << 8) | (cap << 16) | (join << 24);
+		r.flags = (uint32_t)(subClosed[sp] & 1) | (((d.ocj >> 24) & 1u) << 1) | ((sseFill & 1u) << 2) | (op << 8) | (cap << 16) | (join << 24);
 		ps = pieceStart[j];
 		pe = pieceStart[j + 1];
 		first = r.first;
 		/* fills: N-2 fan-triangle pieces (no vertex of their own) precede the N vertex pieces */
-		fan = (op == VGB_OP_CONVEX_FILL_AA || op == VGB_OP_CONVEX_FILL) && r.N >= 2 ? r.N - 2 : 0u;
+		fan = ((op == VGB_OP_CONVEX_FILL_AA && !sseFill) || op == VGB_OP_CONVEX_FILL) && r.N >= 2 ? r.N - 2 : 0u;
 		r.pieceStart = ps;
 		r.hsw = d.hsw;
 		r.hsw_aa = d.hsw_aa;
@@ -673,6 +673,7 @@ __device__ __forceinline__ JobCtx loadJob(const PieceArgs& a, uint32_t j, uint32
 	J.N = r0.y;
 	J.closed = r0.z & 1u;
 	J.nfix = (r0.z >> 1) & 1u;
+	J.sse = (r0.z >> 2) & 1u;
 	J.op = (r0.z >> 8) & 0xFF;
 	J.cap = (r0.z >> 16) & 0xFF;
 	J.join = r0.z >> 24;
@@ -1200,9 +1201,9 @@ __global__ void __launch_bounds__(128, VGB_COUNT_MIN_BLOCKS) k_group_count(Piece
 
 /* BIGI: index image sized for ~40 indices per piece (uint32 output of fat pieces); otherwise half of
  * that for uint32, so that thin meshes keep 9 blocks per SM.  uint16 always uses the full count. */
-/* Resident blocks per SM: the (cap, join)-specialised AA-stroke kernels run best at 8 (64 registers, no
- * spills; measured equal at 6-8, 2 % slower at 9), the general mixed-op kernel at 9 (it is the one that
- * needs the extra warps to cover its longer dependent chains: tiger-like scene 1.29 vs 1.38 ms). */
+/* Resident blocks per SM: the (cap, join)-specialised AA-stroke kernels run best at 8 (64 registers), the general
+ * mixed-op kernel at 6 (80 registers, no spills; its uint32 image limits it to 6 blocks of shared memory anyway --
+ * tiger-like scene x 600, emit: 2.96 ms at 6, 3.29 at 7, 3.71 at 8, 3.34 at 9 with 72 bytes of spills). */
 template<class IDX, uint32_t OPS, int JT, int CT, bool BIGI>
 __global__ void __launch_bounds__(128, (OPS == OPS_STROKE_AA && JT < 3) ? VGB_EMIT_MIN_BLOCKS_SPEC : VGB_EMIT_MIN_BLOCKS) k_group_emit(PieceArgs a)
 {
@@ -1411,7 +1412,7 @@ __global__ void k_fill_job_sizes(const uint32_t* __restrict__ jobSub, uint32_t n
 	meshTotals[j] = ok ? make_uint2(2 * N, 9 * N - 6) : make_uint2(0u, 0u);
 }
 
-template<class IDX>
+template<class IDX, bool SSE>
 __global__ void __launch_bounds__(256) k_fill_emit(PieceArgs a)
 {
 	const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1436,13 +1437,15 @@ __global__ void __launch_bounds__(256) k_fill_emit(PieceArgs a)
 	const uint32_t base = sizeof(IDX) == 2 ? (a.meshBase != nullptr ? a.meshBase[j] : 0u) : (uint32_t)(mo.x + a.vertexBase + (a.vertexBasePtr ? __ldg(a.vertexBasePtr) : 0ull));
 	IDX* idx = reinterpret_cast<IDX*>(a.idx) + mo.y;
 	const uint32_t f = 2 * i;
+	/* scalar order (stroker.cpp:768-796): fan triangle i at 3i, quad i at 3(N-2) + 6i;
+	 * SIMD order (stroker.cpp:616-701): Q0 at 0, F(k) at 6 + 9k, Q(i) at 9i for 1 <= i <= N-2, Q(N-1) at 9N - 12 */
 	if (i + 2 < N) {
-		IDX* t = idx + 3 * i;
+		IDX* t = idx + (SSE ? 6 + 9 * i : 3 * i);
 		t[0] = (IDX)(base);
 		t[1] = (IDX)(base + f + 2);
 		t[2] = (IDX)(base + f + 4);
 	}
-	IDX* q = idx + 3 * (N - 2) + 6 * i;
+	IDX* q = idx + (SSE ? (i == 0 ? 0u : (i + 1 == N ? 9 * N - 12 : 9 * i)) : 3 * (N - 2) + 6 * i);
 	const uint32_t nA = (i + 1 < N) ? f + 3 : 1u, nB = (i + 1 < N) ? f + 2 : 0u; /* next vertex's (outer, inner), wrapping to (1, 0) */
 	q[0] = (IDX)(base + f);
 	q[1] = (IDX)(base + f + 1);
@@ -1493,6 +1496,7 @@ public:
 	DevBuf dBlockTotals, dBlockBase, dMeshTotals, dMeshOff, dScanTmp, dBlockTail;
 	DevBuf dSlotFirst, dCounters, dDenseFirst, dDensePts, dBulkErr, dMeshSplit, dTicket, dRankTotals, dRankBase;
 	bool mergedRan = false;
+	bool sseFill = false; /* VGB_RUN_FILL_ORDER_SSE of the current run */
 	bool bulkMode = false;
 	/* sizes of the uploaded batch, learnt by the first run (they are facts about the input, and the
 	 * kernels are deterministic): later runs of the SAME upload reuse them instead of draining the
@@ -1724,6 +1728,11 @@ public:
 		VGB_CUDA(cudaSetDevice(dev));
 		launches = 0;
 		idxBytes = (flags & VGB_RUN_INDEX_U32) ? 4 : 2;
+		{
+			const bool sse = (flags & VGB_RUN_FILL_ORDER_SSE) != 0;
+			if (sse != sseFill) sizesKnown = false; /* the piece decomposition of fills differs between the two orders */
+			sseFill = sse;
+		}
 		memset(&sz, 0, sizeof(sz));
 		sz.num_subpaths = numSub;
 		sz.num_meshes = numJobs;
@@ -1828,37 +1837,40 @@ public:
 				                                                         dJobPieces.as<uint32_t>(), dMeshTotals.as<uint2>());
 			} else {
 				k_job_pieces<<<(numJobs + 255) / 256, 256, 0, st>>>(dJobSub.as<uint32_t>(), dJobDraw.as<uint32_t>(), numJobs, dSubNum.as<uint32_t>(),
-				                                                     dDraws.as<DrawRec>(), dJobPieces.as<uint32_t>());
+				                                                     dDraws.as<DrawRec>(), dJobPieces.as<uint32_t>(), sseFill ? 1u : 0u);
 			}
 			launches += 2;
 			if (scan<ScanOps<uint32_t>>(dJobPieces.as<uint32_t>(), numJobs, dPieceStart.as<uint32_t>(), err)) return VGB_ERR_CUDA;
 			if (sizesKnown) {
 				numPieces = kNumPieces;
-			} else if (readback(&numPieces, dPieceStart.as<uint32_t>() + numJobs, 4, err)) {
-				return VGB_ERR_CUDA;
 			}
 		}
-		if (bulkMode && !sizesKnown) {
-			uint32_t e = 0;
-			if (readback(&e, dBulkErr.p, 4, err)) return VGB_ERR_CUDA;
-			if (e) {
+		if (!sizesKnown) {
+			/* first run of an upload: the piece count, the bulk input's error flag and the slot-flatten counters come
+			 * back in ONE read (three small copies, one stream drain) */
+			uint32_t* h = reinterpret_cast<uint32_t*>(hPinned);
+			memset(h, 0, 32);
+			if (numJobs) VGB_CUDA(cudaMemcpyAsync(h, dPieceStart.as<uint32_t>() + numJobs, 4, cudaMemcpyDeviceToHost, st));
+			if (bulkMode) VGB_CUDA(cudaMemcpyAsync(h + 1, dBulkErr.p, 4, cudaMemcpyDeviceToHost, st));
+			if (slotsUsed) VGB_CUDA(cudaMemcpyAsync(h + 4, dCounters.p, 16, cudaMemcpyDeviceToHost, st));
+			VGB_CUDA(cudaStreamSynchronize(st));
+			numPieces = h[0];
+			if (bulkMode && h[1]) {
 				if (err) *err = "non-finite coordinate in the bulk input";
 				return VGB_ERR_NONFINITE;
 			}
-		}
-		if (slotsUsed && sizesKnown) {
-			numPts = kNumPts;
-			sz.num_points = numPts;
-		} else if (slotsUsed) {
-			uint32_t c[4];
-			if (readback(c, dCounters.p, 16, err)) return VGB_ERR_CUDA;
-			if (c[1]) {
-				/* the overflow arena was too small: redo this run with the two-pass flatten */
-				slotMode = false;
-				const int rc = run(flags, vertexBase, err, merge);
-				return rc;
+			if (slotsUsed) {
+				if (h[5]) {
+					/* the overflow arena was too small: redo this run with the two-pass flatten */
+					slotMode = false;
+					const int rc = run(flags, vertexBase, err, merge);
+					return rc;
+				}
+				numPts = h[6];
+				sz.num_points = numPts;
 			}
-			numPts = c[2];
+		} else if (slotsUsed) {
+			numPts = kNumPts;
 			sz.num_points = numPts;
 		}
 		const uint32_t numBlocks = (numPieces + GRP - 1) / GRP;          /* offset groups (warps or blocks) */
@@ -1874,7 +1886,7 @@ public:
 				return VGB_ERR_CUDA;
 			k_job_prep<<<(numJobs + 255) / 256, 256, 0, st>>>(dJobSub.as<uint32_t>(), dJobDraw.as<uint32_t>(), numJobs, dSubFirst.as<uint32_t>(),
 			                                                   dSubNum.as<uint32_t>(), dSubClosed.as<uint8_t>(), dDD.as<DrawDerived>(),
-			                                                   dPieceStart.as<uint32_t>(), dJobRec.as<JobRec>(), dPieceJob.as<uint2>());
+			                                                   dPieceStart.as<uint32_t>(), dJobRec.as<JobRec>(), dPieceJob.as<uint2>(), sseFill ? 1u : 0u);
 			++launches;
 			pa.numPieces = numPieces;
 			pa.numJobs = numJobs;
@@ -1993,8 +2005,11 @@ public:
 		else VGB_EMIT_K(T, OPS_ALL, 3, 3);                                 \
 	} while (0)
 			if (fillOnly) {
-				if (idxBytes == 2) k_fill_emit<uint16_t><<<(numPieces + 255) / 256, 256, 0, st>>>(pa);
-				else k_fill_emit<uint32_t><<<(numPieces + 255) / 256, 256, 0, st>>>(pa);
+				const uint32_t fb = (numPieces + 255) / 256;
+				if (idxBytes == 2 && sseFill) k_fill_emit<uint16_t, true><<<fb, 256, 0, st>>>(pa);
+				else if (idxBytes == 2) k_fill_emit<uint16_t, false><<<fb, 256, 0, st>>>(pa);
+				else if (sseFill) k_fill_emit<uint32_t, true><<<fb, 256, 0, st>>>(pa);
+				else k_fill_emit<uint32_t, false><<<fb, 256, 0, st>>>(pa);
 			} else if (idxBytes == 2) {
 				VGB_LAUNCH_EMIT(uint16_t);
 			} else {

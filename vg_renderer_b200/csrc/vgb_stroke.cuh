@@ -32,6 +32,7 @@ struct JobCtx
 {
 	uint32_t first, N, closed;
 	uint32_t nfix; /* round joins of this job always have n == 2 when the turn is unambiguous (3*da > pi) */
+	uint32_t sse;  /* convex AA fills in the SIMD build's index order (VGB_RUN_FILL_ORDER_SSE) */
 	uint32_t op, cap, join;
 	float hsw, hsw_aa, da, fringe;
 	uint32_t nHC, color, c0;
@@ -69,13 +70,13 @@ __device__ __forceinline__ float2 extrusion(float2 d01, float2 d12)
 }
 
 /* number of pieces of a job (0 = the caller skips this sub-path: vg.cpp:3101, 3450) */
-__host__ __device__ __forceinline__ uint32_t pieceCount(uint32_t op, uint32_t N)
+__host__ __device__ __forceinline__ uint32_t pieceCount(uint32_t op, uint32_t N, bool sseFill = false)
 {
 	switch (op) {
 	case VGB_OP_STROKE_AA:
 	case VGB_OP_STROKE:
 	case VGB_OP_STROKE_AA_THIN: return N >= 2 ? N : 0;
-	case VGB_OP_CONVEX_FILL_AA:
+	case VGB_OP_CONVEX_FILL_AA: return N >= 3 ? (sseFill ? N : 2 * N - 2) : 0; /* SIMD order: vertex i carries F(i-1) and Q(i) */
 	case VGB_OP_CONVEX_FILL: return N >= 3 ? 2 * N - 2 : 0;
 	default: return 0;
 	}
@@ -364,15 +365,15 @@ __device__ __forceinline__ Piece classify(const JobCtx& J, uint32_t q, const flo
 	P.p = P.d01 = P.d12 = P.v = f2(0.0f, 0.0f);
 	if (false) {
 	} else if ((OPS & OPS_FILL_AA) && (!(OPS & ~OPS_FILL_AA) || J.op == VGB_OP_CONVEX_FILL_AA)) {
-		if (q < N - 2) {
+		if (!J.sse && q < N - 2) {
 			P.kind = PK_FILL_FAN;
 			P.icount = 3;
 		} else {
-			const uint32_t i = q - (N - 2);
+			const uint32_t i = J.sse ? q : q - (N - 2);
 			P.kind = PK_FILL_VTX;
 			P.li = i;
 			P.vcount = 2;
-			P.icount = 6;
+			P.icount = (J.sse && i > 0 && i + 1 < N) ? 9u : 6u;
 			const float2 pm = v[i == 0 ? N - 1 : i - 1];
 			const float2 pn = v[i == N - 1 ? 0 : i + 1];
 			P.p = v[i];
@@ -1016,6 +1017,12 @@ __device__ __forceinline__ void emitFillVtx(const JobCtx& J, const Piece& P, con
 	const float ex = e.x * aa, ey = e.y * aa;
 	S.VP(0, P.p.x + ex, P.p.y + ey, J.color, P.p.x - ex, P.p.y - ey, J.c0);
 	const uint32_t f = 2 * P.li;
+	if (J.sse && P.li > 0 && P.li + 1 < J.N) {
+		/* SIMD order (stroker.cpp:640-690): fan triangle F(i-1) = (0, 2i, 2i+2) right before this vertex's quad */
+		S.tri(0, 0, f, f + 2);
+		S.tri2(3, f, f + 1, f + 3, f, f + 3, f + 2);
+		return;
+	}
 	if (P.li + 1 < J.N) {
 		S.tri2(0, f, f + 1, f + 3, f, f + 3, f + 2);
 	} else {
