@@ -1,2 +1,2 @@
-python -m pytest tests -m gpu -x -q --durations=5 2>&1 | tail -15
-python tools/perf_probe_tiger.py 600 2>&1 | tail -2
+ncu --set full --clock-control none --import-source on -k regex:"k_group_emit|k_group_count|k_flatten_slots|k_job_prep" -s 8 -c 4 -o gpurun_out/r02_final python tools/perf_probe.py 1000000 1 > gpurun_out/ncu_r02_final.log 2>&1
+tail -3 gpurun_out/ncu_r02_final.log
