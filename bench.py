@@ -361,6 +361,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--ref-curves", type=int, default=0, help="reference arm: total cubics per step (0 = 50k per core)")
     ap.add_argument("--merged", action="store_true", help="single merged uint32 index space: in-library all-gather of per-rank (V,I) totals")
+    ap.add_argument("--no-merged-leg", action="store_true", help="N>1: skip the extra merged-space measurement of a plain run")
     ap.add_argument("--gather", action="store_true", help="merged space, N>1: also gather the payload into rank 0's buffer over NVLink (once, reported separately)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "vgb" else args.warmup
@@ -529,6 +530,38 @@ def main():
     if not args.no_e2e:
         e2e, e2e_dev = run_e2e(args, wl, vgb, pinned_empty, V, I, idx_bytes, merged, barrier, allmax, total_verts)
 
+    # ---- N > 1, plain run: also measure the ONE exchange step of the path -----------------------------------
+    # (so that a default multi-GPU run carries the data-path collective: merged uint32 space through the library group)
+    merged_space = None
+    if world > 1 and wl.group is None and args.workload == "cubics" and not args.no_merged_leg:
+        import torch  # noqa: F401
+        ids = [vgb.Group.unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0)
+        grp = vgb.Group(local, rank, world, ids[0])
+        for _ in range(3):
+            b0.run_merged(grp)
+        b0.sync()
+        barrier()
+        k = 20
+        b0.mark(2)
+        for _ in range(k):
+            b0.run_merged(grp)
+        b0.mark(3)
+        mms = allmax(b0.elapsed_ms(2, 3)) / k
+        mi = b0.merged_info()
+        barrier()
+        grp.gather(b0, owner=0)
+        barrier()
+        g = grp.gather(b0, owner=0)
+        gms = allmax(g["ms"])
+        moved = allmax(float((g["total_vertices"] - V[0]) * 12 + (g["total_indices"] - I[0]) * 4 if rank == 0 else 0))
+        merged_space = {"what": "the same batches as ONE merged uint32 vertex/index space: vgb_batch_run_merged = count stage -> ncclAllGather of 16 B/rank "
+                                "(V,I totals) on the batch stream -> device-side base -> emit", "value": total_verts / (mms * 1e-3) / 1e6, "unit": UNIT,
+                        "ms_per_step": mms, "steps": k, "nranks": world, "total_vertices": mi["total_vertices"], "total_indices": mi["total_indices"],
+                        "gather_into_rank0": {"what": "vgb_group_gather (ncclSend/ncclRecv over NVLink)", "ms": gms, "bytes": moved,
+                                              "gbs": moved / (gms * 1e-3) / 1e9, "frac_of_measured_peer_copy_770": moved / (gms * 1e-3) / 1e9 / 770.0}}
+        grp.close()
+
     cpu = None
     if rank == 0 and args.gpus == 1 and not args.no_cpu:
         kind = ref_kind()
@@ -557,11 +590,12 @@ def main():
                        "l2": ("a 280 MB mesh is written between steps (L2 flush)" if flush is not None else
                               "each step writes ~%.2f GB per GPU (>> 126 MB L2): no explicit flush" % (sum(alg) / 1e9)),
                        "parallelism": (f"{world} x sharded instance ranges" if args.workload == "tiger_x10000" else f"{world} x independent path ranges")
-                                      + (coll if coll else ", no data-path collective"),
+                                      + (coll if coll else ", no data-path collective" + ("; the one exchange step (merged uint32 space: ncclAllGather of the "
+                                         "(V,I) totals inside vgb_batch_run_merged, payload gather over NVLink) is measured in merged_space" if merged_space else "")),
                        "merged": minfo, "host_placement": numa},
             "clocks": clocks, "e2e": e2e, "e2e_device_consumer": e2e_dev, "gpu_launches": launches * args.steps,
             "launches_per_step": launches, "wall_ms_per_step": wall_ms_per_step,
-            "roofline": roofline, "nvlink": nvlink, "cpu_baseline": cpu,
+            "roofline": roofline, "nvlink": nvlink, "merged_space": merged_space, "cpu_baseline": cpu,
         }
         print(json.dumps(line))
     if dist is not None:
