@@ -797,8 +797,10 @@ __device__ __forceinline__ void emitAny(const float2* __restrict__ pts, const Jo
 	}
 }
 
-/* the same through the plain-pointer sink, out of line: it only runs for warps whose pieces do not fit
- * the staging image, and must not cost the common path registers or instruction-cache footprint */
+/* the same through the plain-pointer sink: it only runs for warps whose pieces do not fit the staging image.
+ * Inlined on purpose: as a __noinline__ call its JobCtx / Piece arguments had to live in local memory, which put
+ * STL/LDL on the COMMON path (the structs' addresses escape); inlined, the overflow code is a cold block behind a
+ * warp-uniform branch and only costs instruction-cache footprint. */
 template<uint32_t OPS, int JT, int CT, class SINK>
 __device__ __forceinline__ void emitAnyCold(const float2* __restrict__ pts, const JobCtx& J, const Piece& P, uint32_t F, uint4 prev, const SINK& S)
 {
