@@ -48,6 +48,22 @@ inline void* alignedRealloc(AllocatorI* a, void* ptr, size_t size, size_t align)
 	return (void*)p;
 }
 
+/* placement-new helpers vg.cpp uses for its Context (vg.cpp:735, 1015) */
+struct PlacementNewTag {};
+}
+inline void* operator new(size_t, bx::PlacementNewTag, void* p) { return p; }
+inline void operator delete(void*, bx::PlacementNewTag, void*) throw() {}
+#define BX_NEW(_allocator, _type) ::new (bx::PlacementNewTag(), bx::alloc(_allocator, sizeof(_type))) _type
+namespace bx
+{
+template<typename T> inline void deleteObject(AllocatorI* a, T* obj, size_t align = 0)
+{
+	if (obj) {
+		obj->~T();
+		free(a, obj, align);
+	}
+}
+
 /* malloc-backed default, used by the oracle's C wrapper */
 struct DefaultAllocator : AllocatorI
 {

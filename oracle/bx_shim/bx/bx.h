@@ -32,6 +32,15 @@ inline void memSet(void* dst, uint8_t v, size_t n) { ::memset(dst, v, n); }
 inline void memMove(void* dst, const void* src, size_t n) { ::memmove(dst, src, n); }
 inline uint32_t uint32_max(uint32_t a, uint32_t b) { return a > b ? a : b; }
 inline uint32_t uint32_min(uint32_t a, uint32_t b) { return a < b ? a : b; }
+inline int32_t memCmp(const void* a, const void* b, size_t n) { return ::memcmp(a, b, n); }
+template<typename T> inline bool isPowerOf2(T a) { return a && !(a & (a - 1)); }
+/* strided copy (vg.cpp: text atlas upload) */
+inline void gather(void* dst, const void* src, uint32_t srcStride, uint32_t stride, uint32_t num)
+{
+	uint8_t* d = (uint8_t*)dst;
+	const uint8_t* s = (const uint8_t*)src;
+	for (uint32_t i = 0; i < num; ++i, d += stride, s += srcStride) ::memcpy(d, s, stride);
+}
 }
 
 #define BX_UNUSED(...) ::bx::unusedArgs(__VA_ARGS__)

@@ -43,6 +43,27 @@ inline float acos(float a) { return vgb_acos(a); }
 inline float atan2(float y, float x) { return vgb_atan2(y, x); }
 #endif
 
+inline float exp(float a) { return ::expf(a); }
+inline float pow(float a, float b) { return ::powf(a, b); }
+inline float log(float a) { return ::logf(a); }
+inline float round(float a) { return ::roundf(a); }
+inline float trunc(float a) { return ::truncf(a); }
+inline float fract(float a) { return a - ::truncf(a); }
+inline float toRad(float d) { return d * kPi / 180.0f; }
+/* column-major 4x4, as bgfx expects (only used for the view/projection of vg::end, which the stub ignores) */
+inline void mtxIdentity(float* m)
+{
+	memset(m, 0, sizeof(float) * 16);
+	m[0] = m[5] = m[10] = m[15] = 1.0f;
+}
+inline void mtxOrtho(float* m, float l, float r, float b, float t, float n, float f, float offset, bool homogeneousNdc)
+{
+	const float aa = 2.0f / (r - l), bb = 2.0f / (t - b), cc = (homogeneousNdc ? 2.0f : 1.0f) / (f - n);
+	const float dd = (l + r) / (l - r), ee = (t + b) / (b - t), ff = homogeneousNdc ? (n + f) / (n - f) : n / (n - f);
+	memset(m, 0, sizeof(float) * 16);
+	m[0] = aa; m[5] = bb; m[10] = cc; m[12] = dd + offset; m[13] = ee; m[14] = ff; m[15] = 1.0f;
+}
+
 template<typename T> inline T min(const T& a, const T& b) { return a < b ? a : b; }
 template<typename T> inline T max(const T& a, const T& b) { return a > b ? a : b; }
 template<typename T> inline T min(const T& a, const T& b, const T& c) { return min(min(a, b), c); }

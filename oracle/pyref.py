@@ -183,3 +183,46 @@ class OracleLib(_Lib):
 
 def have_ref(kind="scalar"):
     return os.path.exists(os.path.join(HERE, "_ref", _REF_NAMES[kind]))
+
+
+CTX_DRAW_DTYPE = np.dtype([("vb_id", "<u4"), ("first_vertex", "<u4"), ("num_vertices", "<u4"), ("first_index", "<u4"), ("num_indices", "<u4"),
+                           ("program", "<u4"), ("scissor", "<u2", 4)])
+
+
+def have_ctx():
+    return os.path.exists(os.path.join(HERE, "_ref", "libvgctx.so"))
+
+
+class CtxLib:
+    """The reference's WHOLE context -- src/vg.cpp itself, compiled against a record-only bgfx stand-in
+    (oracle/vgctx_capi.cpp, oracle/bgfx_stub): records a command list through vg::clXXX, submits it between
+    vg::begin / vg::end and returns what bgfx was handed."""
+
+    def __init__(self):
+        p = os.path.join(HERE, "_ref", "libvgctx.so")
+        if not os.path.exists(p):
+            raise FileNotFoundError(f"{p} missing: run `make -C oracle ref` (needs /root/reference)")
+        self.lib = C.CDLL(p)
+        self.lib.vgctx_run.restype = C.c_int
+
+    def run(self, script, list_flags=0, canvas=(1280, 720), max_vb_vertices=65536, vcap=1 << 22, icap=1 << 24):
+        script = np.frombuffer(bytes(script), np.uint8)
+        cl = np.zeros(len(script) + 4096, np.uint8)
+        cl_size, ndraws, nvbs, nidx = C.c_uint32(), C.c_uint32(), C.c_uint32(), C.c_uint64()
+        draws = np.zeros(1 << 16, CTX_DRAW_DTYPE)
+        pos = np.zeros((vcap, 2), np.float32)
+        uv = np.zeros((vcap, 2), np.int16)
+        col = np.zeros(vcap, np.uint32)
+        vbc = np.zeros(4096, np.uint32)
+        idx = np.zeros(icap, np.uint16)
+        rc = self.lib.vgctx_run(_p(script, C.c_uint8), C.c_uint32(len(script)), C.c_uint32(list_flags), C.c_uint32(canvas[0]), C.c_uint32(canvas[1]),
+                                C.c_uint32(max_vb_vertices), _p(cl, C.c_uint8), C.c_uint32(len(cl)), C.byref(cl_size),
+                                draws.ctypes.data_as(C.c_void_p), C.c_uint32(len(draws)), C.byref(ndraws),
+                                _p(pos, C.c_float), _p(uv, C.c_int16), _p(col, C.c_uint32), C.c_uint64(vcap), _p(vbc, C.c_uint32), C.c_uint32(len(vbc)),
+                                C.byref(nvbs), _p(idx, C.c_uint16), C.c_uint64(icap), C.byref(nidx))
+        if rc != 0:
+            raise RuntimeError(f"vgctx_run rc={rc}")
+        counts = vbc[: nvbs.value].copy()
+        nv = int(counts.sum())
+        return dict(cl_bytes=cl[: cl_size.value].tobytes(), draws=draws[: ndraws.value].copy(), vb_counts=counts, pos=pos[:nv].copy(),
+                    uv=uv[:nv].copy(), color=col[:nv].copy(), index=idx[: nidx.value].copy())

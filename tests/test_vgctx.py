@@ -1,0 +1,183 @@
+"""The reference's WHOLE context as the oracle for the rows either side of the hot path: src/vg.cpp
+itself -- command-list recorder and executor (vg.cpp:2323-2966, 4273-4637), ctxFillPathColor / ctxStrokePathColor
+(3061-3492), the merge step (5207-5405) and vg::end (1076-1288) -- compiled where it lies against a record-only bgfx
+stand-in (oracle/vgctx_capi.cpp, oracle/bgfx_stub).  Checked here, on the CPU:
+  * tests/cmdlist.py's writer produces the bytes vg::clXXX really records,
+  * the product's command-list decoder records the draws ctxSubmitCommandList really issues: the compiled hot path
+    (oracle/_ref/libvgref.so) run on the decoder's recording gives vg.cpp's vertex streams,
+  * the restated merge step (ref_capi.cpp: vgref_final_layout) gives vg.cpp's index buffer and draw-command table.
+The -m gpu test compares the GPU's final layout with vg.cpp's output directly."""
+import numpy as np
+import pytest
+
+import vg_renderer_b200 as vgb
+from oracle.pyref import CtxLib, RefLib, have_ctx, have_ref
+from vg_renderer_b200.tables import tables_from_recorded
+
+import cmdlist as CL
+
+pytestmark = pytest.mark.skipif(not (have_ctx() and have_ref("scalar")), reason="oracle/_ref/libvgctx.so not built (needs /root/reference)")
+
+
+def scene(seed=3, shapes=60):
+    """transforms, state stack, global alpha, scaled / fixed-width / thin / non-AA strokes, AA and plain fills of every path
+    builder -- one scissor throughout (the batch does not carry scissor rects) -- and enough vertices to roll vertex buffers"""
+    rng = np.random.default_rng(seed)
+    w = CL.Writer()
+    w.translate(20, 10).scale(1.5, 1.5)
+    for k in range(shapes):
+        if k % 7 == 0:
+            w.push_state().rotate(float(np.float32(rng.uniform(-0.6, 0.6)))).translate(float(np.float32(rng.uniform(-30, 30))), 5.0)
+        if k % 11 == 0:
+            w.global_alpha(float(np.float32(rng.uniform(0.3, 1.0))))
+        x, y = [float(np.float32(v)) for v in rng.uniform(20, 500, 2)]
+        w.begin_path()
+        kind = k % 8
+        if kind == 0:
+            w.rounded_rect(x, y, 120, 60, float(np.float32(rng.uniform(2, 25))))
+        elif kind == 1:
+            w.circle(x, y, float(np.float32(rng.uniform(5, 60))))
+        elif kind == 2:
+            w.ellipse(x, y, 50, 20)
+        elif kind == 3:
+            w.move_to(x, y).cubic_to(x + 50, y - 80, x + 120, y + 90, x + 180, y).quadratic_to(x + 200, y + 60, x + 90, y + 70).close_path()
+        elif kind == 4:
+            w.rect(x, y, 70, 30)
+        elif kind == 5:
+            w.move_to(x, y).arc_to(x + 60, y, x + 60, y + 60, 20).line_to(x + 10, y + 80)
+        elif kind == 6:
+            w.move_to(x + 40, y).arc(x, y, 40, 0.0, 4.0, bool(k & 8)).line_to(x, y)
+        else:
+            w.move_to(x, y).polyline(rng.uniform(0, 200, 10).astype(np.float32) + np.float32(x))
+        if kind in (0, 1, 2, 3, 4):
+            w.fill(0xFF000000 | int(rng.integers(0, 1 << 24)), CL.fill_flags(aa=bool(k % 3)))
+        if kind != 4:
+            width = float(np.float32(rng.uniform(0.3, 9.0)))
+            w.stroke(0xC0000000 | int(rng.integers(0, 1 << 24)), width, CL.stroke_flags(int(rng.integers(0, 3)), int(rng.integers(0, 3)), bool((k + 1) % 5), fixed=bool(k % 6 == 0)))
+        if k % 7 == 3:
+            w.pop_state()
+    return w
+
+
+# meaningful payload bytes per command type (what the cl* functions CMD_WRITE, vg.cpp:2402-2960); the rest of a record --
+# the header's 8 padding bytes and the payload's tail up to the next multiple of 16 -- is whatever the allocator left there
+_PAYLOAD = {CL.BEGIN_PATH: 0, CL.MOVE_TO: 8, CL.LINE_TO: 8, CL.CUBIC_TO: 24, CL.QUAD_TO: 16, CL.ARC_TO: 20, CL.ARC: 24, CL.RECT: 16, CL.ROUNDED_RECT: 20,
+            CL.ROUNDED_RECT_VARYING: 32, CL.CIRCLE: 12, CL.ELLIPSE: 16, CL.CLOSE_PATH: 0, CL.FILL_COLOR: 8, CL.STROKE_COLOR: 12, CL.PUSH_STATE: 0,
+            CL.POP_STATE: 0, CL.RESET_SCISSOR: 0, CL.SET_SCISSOR: 16, CL.INTERSECT_SCISSOR: 16, CL.T_IDENTITY: 0, CL.T_SCALE: 8, CL.T_TRANSLATE: 8,
+            CL.T_ROTATE: 4, CL.T_MULT: 28, CL.SET_VIEW_BOX: 16, CL.SET_GLOBAL_ALPHA: 4}
+
+
+def records(buf):
+    """[(type, size, meaningful payload bytes)] of a command-list byte stream"""
+    out, i = [], 0
+    while i < len(buf):
+        t, n = np.frombuffer(buf[i:i + 8], np.uint32)
+        p = buf[i + 16:i + 16 + int(n)]
+        m = 4 + 8 * int(np.frombuffer(p[:4], np.uint32)[0]) if t == CL.POLYLINE else _PAYLOAD[int(t)]
+        out.append((int(t), int(n), bytes(p[:m])))
+        i += 16 + int(n)
+    assert i == len(buf)
+    return out
+
+
+def decoded_tables(w, canvas):
+    got = vgb.Batch(-1)
+    ctx = vgb.make_cl_context(canvas=(float(canvas[0]), float(canvas[1])))
+    st = got.submit_command_list(w.bytes(), ctx)
+    assert st.unsupported == 0 and st.scissor_changes == 0
+    return tables_from_recorded(got.recorded_streams()), st
+
+
+@pytest.mark.parametrize("max_vb", [65536, 5000])
+def test_decoder_and_merge_step_against_the_real_context(max_vb):
+    canvas = (1280, 720)
+    w = scene()
+    real = CtxLib().run(w.bytes(), canvas=canvas, max_vb_vertices=max_vb)
+    # (1) the byte format: what vg::clXXX recorded is what the writer produced
+    assert len(real["cl_bytes"]) == len(w.bytes()) and records(real["cl_bytes"]) == records(w.bytes())
+    # (2) the executor: the hot path run on the DECODER's recording gives the real context's vertex streams
+    t, st = decoded_tables(w, canvas)
+    ref = RefLib("scalar")
+    exp = ref.run_batch(t)
+    assert exp["num_vertices"] == len(real["pos"])
+    np.testing.assert_array_equal(real["pos"], exp["pos"])
+    np.testing.assert_array_equal(real["color"], exp["color"])
+    assert len(np.unique(real["uv"], axis=0)) == 1  # every path vertex samples the white pixel
+    # (3) the merge step: restated book-keeping (ref_capi.cpp) against the real createDrawCommand_VertexColor / vg::end
+    cfg = vgb.make_final_cfg(max_vb, uv=(int(real["uv"][0, 0]), int(real["uv"][0, 1])))
+    idx, uv, cmds = ref.final_layout(exp["mesh_vtx_off"], exp["mesh_idx_off"], exp["index"], cfg)
+    np.testing.assert_array_equal(real["index"], idx)
+    np.testing.assert_array_equal(real["uv"], uv)
+    d = real["draws"]
+    assert len(d) == len(cmds) and (max_vb == 65536 or len(d) > 1)
+    for k in ("vb_id", "first_vertex", "first_index", "num_vertices", "num_indices"):
+        np.testing.assert_array_equal(d[k], cmds[k], err_msg=k)
+    np.testing.assert_array_equal(real["vb_counts"], np.bincount(cmds["vb_id"], weights=cmds["num_vertices"]).astype(np.uint32)[cmds["vb_id"].min():])
+
+
+def test_scissor_changes_are_the_real_contexts_extra_draw_commands():
+    """the decoder's scissor_changes stat = the draw commands vg.cpp adds because the scissor rect changed"""
+    w = CL.Writer()
+    for k in range(6):
+        if k in (2, 4):
+            w.set_scissor(10.0 * k, 5.0, 300.0, 200.0)
+        w.begin_path().circle(100 + 20 * k, 100, 30).fill(0xFF336699, CL.fill_flags())
+    real = CtxLib().run(w.bytes())
+    got = vgb.Batch(-1)
+    st = got.submit_command_list(w.bytes(), vgb.make_cl_context())
+    assert st.scissor_changes == 2 and len(real["draws"]) == 1 + st.scissor_changes
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("max_vb", [65536, 5000])
+def test_gpu_final_layout_equals_the_real_context(max_vb):
+    """command-list bytes -> decoder -> GPU pipeline with the final layout == what the reference's own vg.cpp hands to
+    bgfx for the same list: vertex streams, uv stream, rebased uint16 indices, draw-command table"""
+    canvas = (1280, 720)
+    w = scene(seed=9, shapes=90)
+    real = CtxLib().run(w.bytes(), canvas=canvas, max_vb_vertices=max_vb)
+    b = vgb.Batch(0)
+    st = b.submit_command_list(w.bytes(), vgb.make_cl_context(canvas=(float(canvas[0]), float(canvas[1]))))
+    assert st.scissor_changes == 0
+    b.set_final_layout(vgb.make_final_cfg(max_vb, uv=(int(real["uv"][0, 0]), int(real["uv"][0, 1]))))
+    b.run()
+    out = b.download()
+    uv, cmds = b.download_final()
+    np.testing.assert_array_equal(out["pos"], real["pos"])
+    np.testing.assert_array_equal(out["color"], real["color"])
+    np.testing.assert_array_equal(uv, real["uv"])
+    np.testing.assert_array_equal(out["index"], real["index"])
+    d = real["draws"]
+    assert len(d) == len(cmds)
+    for k in ("vb_id", "first_vertex", "first_index", "num_vertices", "num_indices"):
+        np.testing.assert_array_equal(d[k], cmds[k], err_msg=k)
+
+
+@pytest.mark.parametrize("cull", [0, 2])
+def test_culling_scissor_and_matrix_commands_against_the_real_context(cull):
+    """AllowCommandCulling (vg.cpp:4307, 4338-4341) with zero-sized / restored scissors, IntersectScissor, SetViewBox,
+    TransformMult (both orders), TransformIdentity: the decoder's recording run through the compiled hot path must give
+    the vertices the real executor produced (draw-command boundaries differ: several scissor rects)."""
+    w = CL.Writer()
+    w.set_view_box(0.0, 0.0, 640.0, 360.0)
+    w.begin_path().circle(100, 100, 40).fill(0xFF102030, CL.fill_flags())
+    w.push_state().set_scissor(50.0, 50.0, 0.5, 300.0)                       # narrower than a pixel: strokers are culled when allowed
+    w.begin_path().rect(10, 10, 80, 40).fill(0xFF405060, CL.fill_flags()).stroke(0xFF000000, 2.0, CL.stroke_flags(1, 1, True))
+    w.intersect_scissor(0.0, 0.0, 10.0, 10.0)
+    w.begin_path().ellipse(200, 100, 60, 20).stroke(0xFF778899, 3.0, CL.stroke_flags(0, 2, True))
+    w.pop_state()
+    w.mult([1.0, 0.25, -0.25, 1.0, 12.0, -7.0], False).mult([0.9, 0.0, 0.0, 1.1, 3.0, 4.0], True)
+    w.begin_path().move_to(20, 200).cubic_to(80, 120, 160, 280, 240, 200).stroke(0xFFAA5500, 6.0, CL.stroke_flags(2, 0, True))
+    w.set_scissor(100.0, 50.0, 200.0, 150.0).intersect_scissor(150.0, 60.0, 400.0, 30.0)
+    w.begin_path().rounded_rect(120, 60, 150, 90, 12).fill(0xFF00FF00, CL.fill_flags(aa=False)).stroke(0x80FFFFFF, 0.4, CL.stroke_flags(0, 0, True))
+    w.reset_scissor().identity().global_alpha(0.5)
+    w.begin_path().circle(300, 300, 25).fill(0xFFFF00FF, CL.fill_flags())
+    real = CtxLib().run(w.bytes(), list_flags=cull, canvas=(1280, 720))
+    assert records(real["cl_bytes"]) == records(w.bytes())
+    got = vgb.Batch(-1)
+    st = got.submit_command_list(w.bytes(), vgb.make_cl_context(canvas=(1280.0, 720.0), flags=cull))
+    assert (st.culled > 0) == (cull == 2)
+    exp = RefLib("scalar").run_batch(tables_from_recorded(got.recorded_streams()))
+    np.testing.assert_array_equal(real["pos"], exp["pos"])
+    np.testing.assert_array_equal(real["color"], exp["color"])
+    assert int(real["draws"]["num_indices"].sum()) == exp["num_indices"]

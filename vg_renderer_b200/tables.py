@@ -72,6 +72,39 @@ class BatchTables:
         return t
 
 
+def tables_from_recorded(r, fringe=1.0):
+    """BatchTables out of what a (record-only) vg_renderer_b200.api.Batch recorded: Batch.recorded_streams().
+    Lets the compiled reference run exactly what the product's recorder / command-list decoder produced."""
+    t = BatchTables(fringe)
+    P = int(r["num_paths"])
+    t.num_paths = P
+    ncmd, ndata = len(r["cmd"]), len(r["data"])
+    coff = np.full(P + 1, ncmd, np.int64)
+    doff = np.full(P + 1, ndata, np.int64)
+    for s in range(int(r["num_subpaths"]) - 1, -1, -1):  # the first sub-path of a path gives the path's start
+        p = int(r["path_id"][s])
+        coff[p] = int(r["cmd_begin"][s])
+        doff[p] = int(r["data_begin"][s])
+    for p in range(P - 1, -1, -1):  # a path without commands starts where the next one does
+        if coff[p] > coff[p + 1]:
+            coff[p], doff[p] = coff[p + 1], doff[p + 1]
+    t.path_cmd_off = coff.astype(np.uint32)
+    t.path_data_off = doff.astype(np.uint32)
+    t.cmd = np.asarray(r["cmd"], np.uint8)
+    t.data = np.asarray(r["data"], np.float32)
+    t.path_scale = np.asarray(r["path_scale"], np.float32)
+    t.path_tol = np.asarray(r["path_tol"], np.float32)
+    t.path_xform = np.asarray(r["path_xform"], np.float32).reshape(-1)
+    dp = np.asarray(r["draw_path"], np.uint32)
+    t.draw_begin = np.searchsorted(dp, np.arange(P + 1), side="left").astype(np.uint32)
+    t.draw_op = np.asarray(r["draw_op"], np.uint32)
+    t.draw_color = np.asarray(r["draw_color"], np.uint32)
+    t.draw_width = np.asarray(r["draw_width"], np.float32)
+    t.draw_cap = np.asarray(r["draw_cap"], np.uint8)
+    t.draw_join = np.asarray(r["draw_join"], np.uint8)
+    return t
+
+
 class Recorder:
     """Immediate-mode style recorder producing BatchTables (and replayable into a Batch)."""
 
