@@ -119,7 +119,8 @@ typedef struct vgb_draw_cmd {
 	uint32_t num_indices;
 	uint32_t first_mesh;   /* meshes [first_mesh, first_mesh + num_meshes) of the batch       */
 	uint32_t num_meshes;
-	uint32_t reserved;
+	uint32_t scissor_id;   /* m_ScissorRect: index into the batch's scissor table (vgb_batch_scissor_rects); 0 when no
+	                        * scissor was ever set */
 	uint64_t stream_vertex; /* offset of the command's first vertex in the pos/uv/color streams */
 	uint64_t stream_index;  /* offset of its first index in the index stream                  */
 } vgb_draw_cmd;
@@ -190,6 +191,18 @@ VGB_API int vgb_batch_close(vgb_batch* b);
 /* draw the current path: one mesh per sub-path, in sub-path order (vg.cpp:3448-3485, 3099-3132).
  * stroke: op in {VGB_OP_STROKE_AA, VGB_OP_STROKE, VGB_OP_STROKE_AA_THIN}; width is the final
  * (already scaled/clamped) strokerXXX width.  fill: aa != 0 -> strokerConvexFillAA. */
+/* Scissor state for the draws recorded from now on (vg.cpp keeps it per State and stamps it on every DrawCommand,
+ * uint16-truncated: vg.cpp:5392-5395).  rect = {x, y, w, h} as State::m_ScissorRect holds it; force_new_command != 0
+ * reproduces m_ForceNewDrawCommand (vg.cpp sets it on every Set/Intersect/ResetScissor, and on PopState when the
+ * restored rect differs from the last draw command's): the next non-empty mesh opens a new draw command in the final
+ * layout (vgb_batch_set_final_layout) and vgb_draw_cmd::scissor_id names its rect.  Batches that never call this
+ * have one scissor (id 0 = {0,0,0,0}, "whatever the context has") and behave as before. */
+VGB_API int vgb_batch_set_scissor(vgb_batch* b, const float rect[4], int force_new_command);
+/* the batch's scissor table: n rects of 4 uint16 {x, y, w, h}; id 0 is the default entry */
+VGB_API int vgb_batch_scissor_rects(vgb_batch* b, uint16_t* rects4, uint32_t cap, uint32_t* n);
+/* per recorded draw: scissor id | force-new-command flag << 31 (sizes from vgb_batch_recorded_counts) */
+VGB_API int vgb_batch_recorded_draw_scissor(vgb_batch* b, uint32_t* out);
+
 VGB_API int vgb_batch_stroke(vgb_batch* b, uint32_t op, uint32_t color, float width, uint32_t cap, uint32_t join);
 VGB_API int vgb_batch_convex_fill(vgb_batch* b, uint32_t color, int aa);
 
@@ -278,10 +291,10 @@ typedef struct vgb_cl_stats {
 	uint32_t unsupported; /* commands outside this path (see above)                  */
 	uint32_t state_depth; /* states left pushed when the list ended                  */
 	uint32_t nested;      /* SubmitCommandList commands executed                     */
-	uint32_t scissor_changes; /* recorded draws whose (uint16) scissor rect differs from the previous draw's: vg.cpp starts a
-	                       * new DrawCommand there (m_ForceNewDrawCommand, vg.cpp:3946-4033, 5359-5405).  The batch does NOT
-	                       * carry scissor rects: with vgb_batch_set_final_layout the draw-command table is only valid for
-	                       * lists where this is 0 -- otherwise split the submission at the scissor changes */
+	uint32_t scissor_changes; /* recorded draws before which vg.cpp forces a new DrawCommand because of the scissor
+	                       * (m_ForceNewDrawCommand: every Set/Intersect/ResetScissor, and PopState when the restored rect
+	                       * differs from the last draw's; vg.cpp:3946-4033, 5359-5405).  The batch carries them
+	                       * (vgb_batch_set_scissor): the final layout starts a new draw command there */
 } vgb_cl_stats;
 
 VGB_API int vgb_batch_submit_command_list(vgb_batch* b, const void* commands, uint32_t size, vgb_cl_context* ctx, vgb_cl_stats* stats);

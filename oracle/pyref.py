@@ -117,11 +117,12 @@ class _Lib:
         return out
 
 
-    def final_layout(self, mesh_vtx_off, mesh_idx_off, index_local, cfg):
+    def final_layout(self, mesh_vtx_off, mesh_idx_off, index_local, cfg, mesh_scissor=None):
         """vg.cpp's merge step over stored meshes.  cfg: vg_renderer_b200.api.FinalCfg.
+        mesh_scissor: per mesh, scissor id | 1 << 31 on the first mesh of a draw that follows a scissor command.
         -> (index[I] u16 rebased, uv[V,2] i16, cmds structured array) or raises on an oversize mesh."""
         from vg_renderer_b200.api import DRAW_CMD_DTYPE
-        f = getattr(self.lib, self.prefix + "_final_layout")
+        f = getattr(self.lib, self.prefix + "_final_layout_sc")
         f.restype = C.c_int
         mvo = np.ascontiguousarray(mesh_vtx_off, np.uint64)
         mio = np.ascontiguousarray(mesh_idx_off, np.uint64)
@@ -132,8 +133,10 @@ class _Lib:
         uv = np.zeros((max(nv, 1), 2), np.int16)
         cmds = np.zeros(nm + 1, DRAW_CMD_DTYPE)
         n = C.c_uint32()
+        ms = None if mesh_scissor is None else np.ascontiguousarray(mesh_scissor, np.uint32)
+        assert ms is None or len(ms) == nm
         rc = f(_p(mvo, C.c_uint64), _p(mio, C.c_uint64), C.c_uint32(nm), _p(il, C.c_uint16), C.byref(cfg),
-               _p(idx, C.c_uint16), _p(uv, C.c_int16), cmds.ctypes.data_as(C.c_void_p), C.c_uint32(nm + 1), C.byref(n))
+               None if ms is None else _p(ms, C.c_uint32), _p(idx, C.c_uint16), _p(uv, C.c_int16), cmds.ctypes.data_as(C.c_void_p), C.c_uint32(nm + 1), C.byref(n))
         if rc != 0:
             raise RuntimeError(f"final_layout rc={rc}")
         return idx[:ni], uv[:nv], cmds[: n.value]

@@ -284,8 +284,12 @@ int vgref_run_batch(uint32_t pathBegin, uint32_t pathEnd,
  * Input: the meshes of a batch in submission order (local uint16 indices), as vgref_run_batch
  * stores them.  Empty meshes are skipped like vg.cpp:3101 / 3450 skip them.  One record per draw
  * command the batch touches; a record describes the batch's share of that command. */
-int vgref_final_layout(const uint64_t* meshVtxOff, const uint64_t* meshIdxOff, uint32_t numMeshes, const uint16_t* idxLocal,
-                       const vgb_final_cfg* cfg, uint16_t* idxOut, int16_t* uvOut, vgb_draw_cmd* cmds, uint32_t cmdCap, uint32_t* numCmds)
+/* meshScissor (may be null): per mesh, scissor id | 1u << 31 on the first mesh of a draw recorded after a scissor
+ * command (ctxSetScissor / ctxIntersectScissor / ctxResetScissor / ctxPopState raise m_ForceNewDrawCommand,
+ * vg.cpp:3946-4033; pinned against the real context in tests/test_vgctx.py) */
+int vgref_final_layout_sc(const uint64_t* meshVtxOff, const uint64_t* meshIdxOff, uint32_t numMeshes, const uint16_t* idxLocal,
+                          const vgb_final_cfg* cfg, const uint32_t* meshScissor, uint16_t* idxOut, int16_t* uvOut, vgb_draw_cmd* cmds,
+                          uint32_t cmdCap, uint32_t* numCmds)
 {
 	uint32_t vbID = cfg->vb_id, vbCount = cfg->vb_count, ibCount = cfg->ib_count; /* Context state on entry */
 	bool forceNew = cfg->cmd_vertices == 0;      /* m_ForceNewDrawCommand: no open command to continue  */
@@ -295,6 +299,7 @@ int vgref_final_layout(const uint64_t* meshVtxOff, const uint64_t* meshIdxOff, u
 	for (uint32_t m = 0; m < numMeshes; ++m) {
 		const uint64_t vo = meshVtxOff[m] - meshVtxOff[0], io = meshIdxOff[m] - meshIdxOff[0];
 		const uint32_t nv = (uint32_t)(meshVtxOff[m + 1] - meshVtxOff[m]), ni = (uint32_t)(meshIdxOff[m + 1] - meshIdxOff[m]);
+		if (meshScissor && (meshScissor[m] >> 31)) forceNew = true; /* stays up until allocDrawCommand runs, vg.cpp:5402 */
 		if (nv == 0) continue;
 		if (nv >= cfg->max_vb_vertices) return -5;  /* VG_CHECK, vg.cpp:5323 */
 		if (vbCount + nv > cfg->max_vb_vertices) {  /* allocVertices: the buffer cannot hold it, vg.cpp:5327-5335 */
@@ -314,6 +319,7 @@ int vgref_final_layout(const uint64_t* meshVtxOff, const uint64_t* meshIdxOff, u
 			cur->first_vertex = firstVertexID;
 			cur->first_index = firstIndexID;
 			cur->first_mesh = m;
+			cur->scissor_id = meshScissor ? (meshScissor[m] & 0x7fffffffu) : 0u; /* m_ScissorRect, vg.cpp:5392-5395 */
 			cur->stream_vertex = vo;
 			cur->stream_index = io;
 			if (forceNew) cmdNumVertices = 0;       /* vg.cpp:5391 */
@@ -329,6 +335,12 @@ int vgref_final_layout(const uint64_t* meshVtxOff, const uint64_t* meshIdxOff, u
 	}
 	*numCmds = n;
 	return 0;
+}
+
+int vgref_final_layout(const uint64_t* meshVtxOff, const uint64_t* meshIdxOff, uint32_t numMeshes, const uint16_t* idxLocal,
+                       const vgb_final_cfg* cfg, uint16_t* idxOut, int16_t* uvOut, vgb_draw_cmd* cmds, uint32_t cmdCap, uint32_t* numCmds)
+{
+	return vgref_final_layout_sc(meshVtxOff, meshIdxOff, numMeshes, idxLocal, cfg, nullptr, idxOut, uvOut, cmds, cmdCap, numCmds);
 }
 
 /* vgutil::batchTransformPositions (vg_util.cpp:136-227; this build: the scalar branch), the

@@ -1062,15 +1062,23 @@ void vgo_math_eval(uint32_t op, const float* x, const float* y, float* out, uint
  * Restatement of the merge step for colour meshes: first-fit packing of the meshes into vertex
  * buffers of max_vb_vertices, one draw command per buffer the batch touches, uint16 indices
  * rebased by the vertices that precede the mesh in its command, white-pixel uv for every vertex. */
-int vgo_final_layout(const uint64_t* meshVtxOff, const uint64_t* meshIdxOff, uint32_t numMeshes, const uint16_t* idxLocal,
-                     const vgb_final_cfg* cfg, uint16_t* idxOut, int16_t* uvOut, vgb_draw_cmd* cmds, uint32_t cmdCap, uint32_t* numCmds)
+/* meshScissor (may be NULL): per mesh, scissor id | 1u << 31 when a scissor command ran between the previous draw
+ * and the one this mesh opens (m_ForceNewDrawCommand, vg.cpp:3946-4033): the flag stays up until a mesh with
+ * vertices reaches allocDrawCommand (vg.cpp:5368, cleared at 5402), which then opens a command in the same buffer */
+int vgo_final_layout_sc(const uint64_t* meshVtxOff, const uint64_t* meshIdxOff, uint32_t numMeshes, const uint16_t* idxLocal,
+                        const vgb_final_cfg* cfg, const uint32_t* meshScissor, uint16_t* idxOut, int16_t* uvOut, vgb_draw_cmd* cmds,
+                        uint32_t cmdCap, uint32_t* numCmds)
 {
 	uint32_t vb = cfg->vb_id, inVb = cfg->vb_count, inIb = cfg->ib_count, inCmd = cfg->cmd_vertices;
 	int open = 0; /* a record for the current command exists */
+	int force = 0;
 	uint32_t n = 0;
 	for (uint32_t m = 0; m < numMeshes; ++m) {
 		const uint64_t vo = meshVtxOff[m] - meshVtxOff[0], io = meshIdxOff[m] - meshIdxOff[0];
 		const uint32_t nv = (uint32_t)(meshVtxOff[m + 1] - meshVtxOff[m]), ni = (uint32_t)(meshIdxOff[m + 1] - meshIdxOff[m]);
+		if (meshScissor != NULL && (meshScissor[m] >> 31) != 0) {
+			force = 1;
+		}
 		if (nv == 0) {
 			continue; /* never submitted: vg.cpp:3101, 3450 */
 		}
@@ -1083,6 +1091,11 @@ int vgo_final_layout(const uint64_t* meshVtxOff, const uint64_t* meshIdxOff, uin
 			inCmd = 0;
 			open = 0;
 		}
+		if (force) { /* vg.cpp:5368: no merging with the previous command */
+			inCmd = 0;
+			open = 0;
+			force = 0;
+		}
 		if (!open) {
 			if (n == cmdCap) {
 				return -5;
@@ -1093,6 +1106,7 @@ int vgo_final_layout(const uint64_t* meshVtxOff, const uint64_t* meshIdxOff, uin
 			c->first_vertex = inVb;
 			c->first_index = inIb;
 			c->first_mesh = m;
+			c->scissor_id = meshScissor != NULL ? (meshScissor[m] & 0x7fffffffu) : 0u; /* vg.cpp:5392-5395 */
 			c->stream_vertex = vo;
 			c->stream_index = io;
 			open = 1;
@@ -1113,6 +1127,12 @@ int vgo_final_layout(const uint64_t* meshVtxOff, const uint64_t* meshIdxOff, uin
 	}
 	*numCmds = n;
 	return 0;
+}
+
+int vgo_final_layout(const uint64_t* meshVtxOff, const uint64_t* meshIdxOff, uint32_t numMeshes, const uint16_t* idxLocal,
+                     const vgb_final_cfg* cfg, uint16_t* idxOut, int16_t* uvOut, vgb_draw_cmd* cmds, uint32_t cmdCap, uint32_t* numCmds)
+{
+	return vgo_final_layout_sc(meshVtxOff, meshIdxOff, numMeshes, idxLocal, cfg, NULL, idxOut, uvOut, cmds, cmdCap, numCmds);
 }
 
 /* vgutil::transformPos2D per vertex (vg_util.h:24-28, scalar association; -ffp-contract=off) */

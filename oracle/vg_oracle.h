@@ -35,6 +35,10 @@ int vgo_run_batch(uint32_t pathBegin, uint32_t pathEnd,
 int vgo_final_layout(const uint64_t* meshVtxOff, const uint64_t* meshIdxOff, uint32_t numMeshes, const uint16_t* idxLocal,
                      const vgb_final_cfg* cfg, uint16_t* idxOut, int16_t* uvOut, vgb_draw_cmd* cmds, uint32_t cmdCap, uint32_t* numCmds);
 
+int vgo_final_layout_sc(const uint64_t* meshVtxOff, const uint64_t* meshIdxOff, uint32_t numMeshes, const uint16_t* idxLocal,
+                        const vgb_final_cfg* cfg, const uint32_t* meshScissor, uint16_t* idxOut, int16_t* uvOut, vgb_draw_cmd* cmds,
+                        uint32_t cmdCap, uint32_t* numCmds);
+
 void vgo_transform_positions(const float* pos, uint32_t n, const float* mtx, float* out);
 
 #ifdef __cplusplus

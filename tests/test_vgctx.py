@@ -11,7 +11,7 @@ import numpy as np
 import pytest
 
 import vg_renderer_b200 as vgb
-from oracle.pyref import CtxLib, RefLib, have_ctx, have_ref
+from oracle.pyref import CtxLib, OracleLib, RefLib, have_ctx, have_ref
 from vg_renderer_b200.tables import tables_from_recorded
 
 import cmdlist as CL
@@ -88,6 +88,83 @@ def decoded_tables(w, canvas):
     return tables_from_recorded(got.recorded_streams()), st
 
 
+def scissor_scene(seed=5, shapes=80):
+    """scene() with the scissor moving underneath it: Set / Intersect / Reset between draws, PopState restoring a different
+    and the same rect, a scissor command followed by a draw that has no vertices (the force flag must wait for the next
+    mesh that has some, vg.cpp:5368-5402), a change between the fill and the stroke of one path, repeated rects"""
+    rng = np.random.default_rng(seed)
+    w = CL.Writer()
+    w.translate(10, 10)
+    for k in range(shapes):
+        x, y = [float(np.float32(v)) for v in rng.uniform(20, 500, 2)]
+        r = k % 13
+        if r == 1:
+            w.set_scissor(30.0 + k, 20.0, 600.0, 400.0)
+        elif r == 3:
+            w.push_state().intersect_scissor(100.0, 80.0, 500.0 - k, 300.0)
+        elif r == 5:
+            w.pop_state()                                              # back to the rect of r == 1: differs from the last draw's
+        elif r == 6:
+            w.push_state().translate(3.0, 4.0)
+        elif r == 7:
+            w.pop_state()                                              # same rect as the last draw's: no new command
+        elif r == 8:
+            w.reset_scissor()
+            w.begin_path().move_to(x, y).stroke(0xFF000000, 2.0, CL.stroke_flags(0, 0, True))   # one point: no vertices
+        elif r == 10:
+            w.set_scissor(30.0, 20.0, 600.0, 400.0)                    # a rect seen before
+        w.begin_path()
+        if k % 3 == 0:
+            w.rounded_rect(x, y, 90, 50, 9.0)
+        elif k % 3 == 1:
+            w.circle(x, y, float(np.float32(rng.uniform(5, 50))))
+        else:
+            w.move_to(x, y).cubic_to(x + 40, y - 60, x + 90, y + 70, x + 150, y).line_to(x + 100, y + 90)
+        if k % 3 != 2:
+            w.fill(0xFF000000 | int(rng.integers(0, 1 << 24)), CL.fill_flags(aa=bool(k % 2)))
+        if r == 11:
+            w.intersect_scissor(0.0, 0.0, 900.0, 500.0)                # between the fill and the stroke of the same path
+        w.stroke(0xD0000000 | int(rng.integers(0, 1 << 24)), float(np.float32(rng.uniform(0.5, 6.0))), CL.stroke_flags(int(rng.integers(0, 3)), int(rng.integers(0, 3)), True))
+    return w
+
+
+def assert_cmds_equal_real(real, cmds, rects, canvas=(1280, 720)):
+    d = real["draws"]
+    assert len(d) == len(cmds)
+    for k in ("vb_id", "first_vertex", "first_index", "num_vertices", "num_indices"):
+        np.testing.assert_array_equal(d[k], cmds[k], err_msg=k)
+    # vg::end (vg.cpp:1156-1186) starts from "previous rect = the whole canvas, cached bgfx scissor = none": commands with
+    # the canvas rect that come before any other rect reach bgfx with no scissor at all, which the stand-in records as zeros
+    sc = d["scissor"].copy()
+    sc[(sc == 0).all(axis=1)] = (0, 0, canvas[0], canvas[1])
+    np.testing.assert_array_equal(sc, rects[cmds["scissor_id"]])
+
+
+@pytest.mark.parametrize("max_vb", [65536, 3000])
+def test_scissor_changes_open_draw_commands_like_the_real_context(max_vb):
+    """the batch carries the scissor (vgb_batch_set_scissor, driven by the decoder): the restated merge step with the
+    per-mesh marks gives the real context's draw-command table, rects included, and its rebased indices"""
+    canvas = (1280, 720)
+    w = scissor_scene()
+    real = CtxLib().run(w.bytes(), canvas=canvas, max_vb_vertices=max_vb)
+    got = vgb.Batch(-1)
+    st = got.submit_command_list(w.bytes(), vgb.make_cl_context(canvas=(1280.0, 720.0)))
+    assert st.unsupported == 0 and st.scissor_changes > 20
+    ref = RefLib("scalar")
+    exp = ref.run_batch(tables_from_recorded(got.recorded_streams()))
+    np.testing.assert_array_equal(real["pos"], exp["pos"])
+    ms = got.recorded_mesh_scissor()
+    assert int((ms >> 31).sum()) == st.scissor_changes and (exp["mesh_vtx_off"][1:] == exp["mesh_vtx_off"][:-1]).any()
+    cfg = vgb.make_final_cfg(max_vb, uv=(int(real["uv"][0, 0]), int(real["uv"][0, 1])))
+    rects = got.scissor_rects()
+    for lib in (ref, OracleLib()):
+        idx, uv, cmds = lib.final_layout(exp["mesh_vtx_off"], exp["mesh_idx_off"], exp["index"], cfg, mesh_scissor=ms)
+        np.testing.assert_array_equal(real["index"], idx)
+        assert_cmds_equal_real(real, cmds, rects)
+    assert len(np.unique(real["draws"]["vb_id"])) > 1 or max_vb == 65536
+    assert len(real["draws"]) > len(np.unique(real["draws"]["vb_id"])) + 15
+
+
 @pytest.mark.parametrize("max_vb", [65536, 5000])
 def test_decoder_and_merge_step_against_the_real_context(max_vb):
     canvas = (1280, 720)
@@ -126,6 +203,28 @@ def test_scissor_changes_are_the_real_contexts_extra_draw_commands():
     got = vgb.Batch(-1)
     st = got.submit_command_list(w.bytes(), vgb.make_cl_context())
     assert st.scissor_changes == 2 and len(real["draws"]) == 1 + st.scissor_changes
+    np.testing.assert_array_equal(got.recorded_draw_scissor() >> 31, [0, 0, 1, 0, 1, 0])
+    np.testing.assert_array_equal(got.scissor_rects()[got.recorded_draw_scissor() & 0x7FFFFFFF][2:], real["draws"]["scissor"][[1, 1, 2, 2]])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("max_vb", [65536, 3000])
+def test_gpu_final_layout_with_scissor_changes_equals_the_real_context(max_vb):
+    """scissor changes inside the list: the GPU's draw-command table splits where vg.cpp's does and names the same rects"""
+    w = scissor_scene(seed=12, shapes=120)
+    real = CtxLib().run(w.bytes(), canvas=(1280, 720), max_vb_vertices=max_vb)
+    b = vgb.Batch(0)
+    st = b.submit_command_list(w.bytes(), vgb.make_cl_context(canvas=(1280.0, 720.0)))
+    assert st.scissor_changes > 20
+    b.set_final_layout(vgb.make_final_cfg(max_vb, uv=(int(real["uv"][0, 0]), int(real["uv"][0, 1]))))
+    b.run()
+    out = b.download()
+    uv, cmds = b.download_final()
+    np.testing.assert_array_equal(out["pos"], real["pos"])
+    np.testing.assert_array_equal(out["color"], real["color"])
+    np.testing.assert_array_equal(uv, real["uv"])
+    np.testing.assert_array_equal(out["index"], real["index"])
+    assert_cmds_equal_real(real, cmds, b.scissor_rects())
 
 
 @pytest.mark.gpu

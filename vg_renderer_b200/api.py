@@ -50,12 +50,12 @@ class DrawCmd(C.Structure):
     """vgb_draw_cmd"""
     _fields_ = [("vb_id", C.c_uint32), ("first_vertex", C.c_uint32), ("first_index", C.c_uint32),
                 ("num_vertices", C.c_uint32), ("num_indices", C.c_uint32), ("first_mesh", C.c_uint32),
-                ("num_meshes", C.c_uint32), ("reserved", C.c_uint32), ("stream_vertex", C.c_uint64),
+                ("num_meshes", C.c_uint32), ("scissor_id", C.c_uint32), ("stream_vertex", C.c_uint64),
                 ("stream_index", C.c_uint64)]
 
 
 DRAW_CMD_DTYPE = np.dtype([("vb_id", "<u4"), ("first_vertex", "<u4"), ("first_index", "<u4"), ("num_vertices", "<u4"),
-                           ("num_indices", "<u4"), ("first_mesh", "<u4"), ("num_meshes", "<u4"), ("reserved", "<u4"),
+                           ("num_indices", "<u4"), ("first_mesh", "<u4"), ("num_meshes", "<u4"), ("scissor_id", "<u4"),
                            ("stream_vertex", "<u8"), ("stream_index", "<u8")])
 
 
@@ -169,6 +169,9 @@ def load_library():
     L.vgb_batch_recorded_jobs.argtypes = [vp, vp, vp]
     L.vgb_batch_recorded_streams.argtypes = [vp] + [vp] * 11
     L.vgb_batch_set_path_xform.argtypes = [vp, vp]
+    L.vgb_batch_set_scissor.argtypes = [vp, vp, C.c_int]
+    L.vgb_batch_scissor_rects.argtypes = [vp, vp, u32, vp]
+    L.vgb_batch_recorded_draw_scissor.argtypes = [vp, vp]
     L.vgb_batch_fringe.restype = f
     L.vgb_batch_fringe.argtypes = [vp]
     L.vgb_batch_submit_command_list.argtypes = [vp, vp, u32, C.POINTER(ClContext), C.POINTER(ClStats)]
@@ -360,6 +363,39 @@ class Batch:
             "cmd", "data", "path_scale", "path_tol", "path_xform", "draw_op", "draw_color", "draw_width", "draw_cap", "draw_join", "draw_path")]))
         n = dict(cmd=r["num_cmds"], data=r["num_data"], path_scale=P, path_tol=P, path_xform=P)
         return {k: v[: n.get(k, D)] for k, v in out.items()} | r
+
+    def set_scissor(self, rect, force_new_command=True):
+        """scissor {x, y, w, h} of the draws recorded from now on (vg.cpp State::m_ScissorRect); force_new_command
+        mirrors m_ForceNewDrawCommand: the next non-empty mesh opens a draw command in the final layout"""
+        r = np.ascontiguousarray(rect, np.float32).reshape(4)
+        self._chk(self.L.vgb_batch_set_scissor(self.h, _ptr(r), 1 if force_new_command else 0))
+
+    def scissor_rects(self):
+        """the scissor table vgb_draw_cmd::scissor_id indexes: [n,4] uint16 {x, y, w, h}; row 0 = no scissor set"""
+        n = C.c_uint32()
+        self._chk(self.L.vgb_batch_scissor_rects(self.h, None, 0, C.byref(n)))
+        out = np.zeros((n.value, 4), np.uint16)
+        self._chk(self.L.vgb_batch_scissor_rects(self.h, _ptr(out), n.value, C.byref(n)))
+        return out
+
+    def recorded_draw_scissor(self):
+        """per recorded draw: scissor id | 1 << 31 when the draw opens a new draw command"""
+        d = self.recorded()["num_draws"]
+        out = np.zeros(max(d, 1), np.uint32)
+        self._chk(self.L.vgb_batch_recorded_draw_scissor(self.h, _ptr(out)))
+        return out[:d]
+
+    def recorded_mesh_scissor(self):
+        """the same per mesh (= job), the mark on the first mesh of its draw: what oracle final_layout(mesh_scissor=) takes"""
+        jd = self.recorded()["job_draw"]
+        ds = self.recorded_draw_scissor()
+        if len(jd) == 0:
+            return np.zeros(0, np.uint32)
+        ms = ds[jd].copy()
+        first = np.ones(len(jd), bool)
+        first[1:] = jd[1:] != jd[:-1]
+        ms[~first] &= np.uint32(0x7FFFFFFF)
+        return ms
 
     def set_path_xform(self, xform6):
         m = np.ascontiguousarray(xform6, np.float32).reshape(6)

@@ -60,6 +60,11 @@ struct vgb_batch
 	bool anyXform = false;
 	std::vector<DrawRec> draws;
 	std::vector<uint32_t> jobSub, jobDraw;
+	/* scissor state (vgb_batch_set_scissor): table of distinct uint16 rects, id of the current one, pending force flag */
+	std::vector<uint16_t> scissors = std::vector<uint16_t>(4, 0);
+	std::vector<uint32_t> drawScissor;
+	uint32_t curScissor = 0, scissorBreaks = 0;
+	bool forceNewCmd = false, anyScissor = false;
 	/* current path */
 	bool inPath = false;
 	bool subOpen = false; /* the current path has a current sub-path */
@@ -85,6 +90,8 @@ struct vgb_batch
 		pathScale.clear(); pathTol.clear(); pathXform.clear();
 		anyXform = false;
 		draws.clear(); jobSub.clear(); jobDraw.clear();
+		scissors.assign(4, 0); drawScissor.clear();
+		curScissor = 0; scissorBreaks = 0; forceNewCmd = false; anyScissor = false;
 		inPath = subOpen = drawn = false;
 		rawMode = false;
 		rawPts.clear(); rawFirst.clear(); rawNum.clear(); rawClosed.clear();
@@ -338,6 +345,12 @@ static int addDraw(vgb_batch* b, uint32_t op, uint32_t color, float width, uint3
 	const uint32_t d = (uint32_t)b->draws.size();
 	b->draws.push_back(r);
 	const size_t j0 = b->jobSub.size(), nj = sub1 > sub0 ? sub1 - sub0 : 0;
+	/* the force flag waits for a draw that has meshes (allocDrawCommand is what clears it, vg.cpp:5402); before the
+	 * first draw it says nothing new: describe that case with vgb_final_cfg::cmd_vertices = 0 */
+	const bool brk = b->forceNewCmd && d > 0 && nj > 0;
+	b->drawScissor.push_back(b->curScissor | (brk ? 0x80000000u : 0u));
+	if (brk) ++b->scissorBreaks;
+	if (nj > 0) b->forceNewCmd = false;
 	b->jobSub.resize(j0 + nj);
 	b->jobDraw.resize(j0 + nj);
 	for (size_t k = 0; k < nj; ++k) {
@@ -345,6 +358,46 @@ static int addDraw(vgb_batch* b, uint32_t op, uint32_t color, float width, uint3
 		b->jobDraw[j0 + k] = d;
 	}
 	b->dirty = true;
+	return 0;
+}
+
+int vgb_batch_set_scissor(vgb_batch* b, const float rect[4], int forceNewCommand)
+{
+	if (!b || !rect) return fail(VGB_ERR_INVALID, "null argument");
+	if (!finite_all(rect, 4)) return fail(VGB_ERR_NONFINITE, "non-finite scissor rect");
+	const uint16_t r[4] = {(uint16_t)rect[0], (uint16_t)rect[1], (uint16_t)rect[2], (uint16_t)rect[3]}; /* vg.cpp:5392-5395 */
+	uint32_t id = 0;
+	const uint32_t n = (uint32_t)(b->scissors.size() / 4);
+	for (id = 1; id < n; ++id) { /* id 0 is the "no scissor set" entry: never matched */
+		if (memcmp(&b->scissors[4 * (size_t)id], r, sizeof(r)) == 0) break;
+	}
+	if (id >= n) {
+		id = n;
+		b->scissors.insert(b->scissors.end(), r, r + 4);
+	}
+	b->curScissor = id;
+	b->forceNewCmd = b->forceNewCmd || forceNewCommand != 0;
+	b->anyScissor = true;
+	b->dirty = true;
+	return 0;
+}
+
+int vgb_batch_scissor_rects(vgb_batch* b, uint16_t* rects4, uint32_t cap, uint32_t* n)
+{
+	if (!b) return fail(VGB_ERR_INVALID, "null batch");
+	const uint32_t cnt = (uint32_t)(b->scissors.size() / 4);
+	if (n) *n = cnt;
+	if (rects4) {
+		if (cap < cnt) return fail(VGB_ERR_CAPACITY, "scissor table capacity too small");
+		memcpy(rects4, b->scissors.data(), b->scissors.size() * sizeof(uint16_t));
+	}
+	return 0;
+}
+
+int vgb_batch_recorded_draw_scissor(vgb_batch* b, uint32_t* out)
+{
+	if (!b || !out) return fail(VGB_ERR_INVALID, "null argument");
+	if (!b->drawScissor.empty()) memcpy(out, b->drawScissor.data(), b->drawScissor.size() * sizeof(uint32_t));
 	return 0;
 }
 
@@ -664,6 +717,10 @@ int vgb_batch_upload(vgb_batch* b)
 	}
 	t.draws = b->draws.data();
 	t.numDraws = (uint32_t)b->draws.size();
+	if (b->anyScissor && b->drawScissor.size() == b->draws.size()) {
+		t.drawScissor = b->drawScissor.data();
+		t.numScissorBreaks = b->scissorBreaks;
+	}
 	if (!b->bulkP8) {
 		t.jobSub = b->jobSub.data();
 		t.jobDraw = b->jobDraw.data();

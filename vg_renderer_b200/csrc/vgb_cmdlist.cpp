@@ -92,12 +92,22 @@ struct Run /* what one top-level submit shares with the lists it nests */
 	/* scissor of the last recorded draw (uint16-truncated like DrawCommand::m_ScissorRect, vg.cpp:5392-5395) */
 	uint16_t lastScissor[4] = {0, 0, 0, 0};
 	bool anyDraw = false;
+	bool force = false; /* m_ForceNewDrawCommand: a scissor command ran since the last recorded draw */
+	/* before a draw is recorded: hand the state's scissor to the batch (vg.cpp stamps it on the DrawCommand) */
 	void noteDraw(const float* sc)
 	{
 		const uint16_t r[4] = {(uint16_t)sc[0], (uint16_t)sc[1], (uint16_t)sc[2], (uint16_t)sc[3]};
-		if (anyDraw && memcmp(r, lastScissor, sizeof(r)) != 0) ++st.scissor_changes;
+		if (anyDraw && force) ++st.scissor_changes;
+		vgb_batch_set_scissor(b, sc, force ? 1 : 0);
 		memcpy(lastScissor, r, sizeof(r));
 		anyDraw = true;
+		force = false;
+	}
+	/* PopState: a new command only if the restored rect differs from the last draw command's (vg.cpp:3950-3966) */
+	void notePop(const float* sc)
+	{
+		const uint16_t r[4] = {(uint16_t)sc[0], (uint16_t)sc[1], (uint16_t)sc[2], (uint16_t)sc[3]};
+		if (anyDraw && memcmp(r, lastScissor, sizeof(r)) != 0) force = true;
 	}
 };
 
@@ -195,8 +205,8 @@ int runList(Run& R, const void* buffer, uint32_t size, uint32_t listFlags)
 				break;
 			}
 			vgb_batch_set_path_xform(b, s->mtx); /* transformPath: the state transform at the path's FIRST draw, vg.cpp:4957-4975 */
-			rc = vgb_batch_convex_fill(b, col, (flags & 0x04u) != 0);
 			R.noteDraw(s->scissor);
+			rc = vgb_batch_convex_fill(b, col, (flags & 0x04u) != 0);
 			++st.draws;
 		} break;
 		case CL_StrokePathColor: {
@@ -225,8 +235,8 @@ int runList(Run& R, const void* buffer, uint32_t size, uint32_t listFlags)
 			const bool aa = (flags & 0x10u) != 0;
 			const uint32_t op = !aa ? VGB_OP_STROKE : (thin ? VGB_OP_STROKE_AA_THIN : VGB_OP_STROKE_AA);
 			vgb_batch_set_path_xform(b, s->mtx);
-			rc = vgb_batch_stroke(b, op, col, thin ? fringe : scaled, (flags >> 2) & 3u, flags & 3u);
 			R.noteDraw(s->scissor);
+			rc = vgb_batch_stroke(b, op, col, thin ? fringe : scaled, (flags >> 2) & 3u, flags & 3u);
 			++st.draws;
 		} break;
 		case CL_FillPathGradient: case CL_FillPathImagePattern: case CL_StrokePathGradient: case CL_StrokePathImagePattern:
@@ -257,12 +267,14 @@ int runList(Run& R, const void* buffer, uint32_t size, uint32_t listFlags)
 		case CL_PopState: /* vg.cpp:3946-3969, 4560-4567 */
 			if (stack.size() <= 1) { rc = fail(VGB_ERR_INVALID, "state stack underflow"); break; }
 			stack.pop_back();
+			R.notePop(stack.back().scissor);
 			if (cullCmds) skipCmds = stack.back().scissor[2] < 1.0f || stack.back().scissor[3] < 1.0f;
 			break;
 		case CL_ResetScissor: /* vg.cpp:3971-3979 */
 			s->scissor[0] = s->scissor[1] = 0.0f;
 			s->scissor[2] = ctx->canvas_width;
 			s->scissor[3] = ctx->canvas_height;
+			R.force = true;
 			skipCmds = false;
 			break;
 		case CL_SetScissor: { /* vg.cpp:3981-4003 */
@@ -273,6 +285,7 @@ int runList(Run& R, const void* buffer, uint32_t size, uint32_t listFlags)
 			const float minx = clampf(px, 0.0f, ctx->canvas_width), miny = clampf(py, 0.0f, ctx->canvas_height);
 			const float maxx = clampf(px + sx, 0.0f, ctx->canvas_width), maxy = clampf(py + sy, 0.0f, ctx->canvas_height);
 			s->scissor[0] = minx; s->scissor[1] = miny; s->scissor[2] = maxx - minx; s->scissor[3] = maxy - miny;
+			R.force = true;
 			if (cullCmds) skipCmds = s->scissor[2] < 1.0f || s->scissor[3] < 1.0f;
 		} break;
 		case CL_IntersectScissor: { /* vg.cpp:4005-4033 */
@@ -284,6 +297,7 @@ int runList(Run& R, const void* buffer, uint32_t size, uint32_t listFlags)
 			const float maxx = minf(px + sx, s->scissor[0] + s->scissor[2]), maxy = minf(py + sy, s->scissor[1] + s->scissor[3]);
 			const float w = maxf(0.0f, maxx - minx), h = maxf(0.0f, maxy - miny);
 			s->scissor[0] = minx; s->scissor[1] = miny; s->scissor[2] = w; s->scissor[3] = h;
+			R.force = true;
 			if (cullCmds) skipCmds = !(w >= 1.0f && h >= 1.0f);
 		} break;
 		case CL_TransformIdentity: /* vg.cpp:4035-4045 */

@@ -23,6 +23,8 @@
  *   k_fill_job_sizes, k_fill_emit   pure convex-AA-fill batches: closed-form sizes and addresses
  *   k_seg_next/_double/_cmds/_mesh_base, k_fill_u32   final layout: greedy vertex-buffer
  *                      segmentation by pointer doubling, draw-command table, per-mesh index bases, uv stream
+ *   k_split_marks/_pos/_flags/_cmds/_fin   the same table when scissor commands force draw commands inside a
+ *                      vertex buffer (m_ForceNewDrawCommand): two scans over per-mesh flags
  *   k_replay_vertices, k_replay_indices   instance replay: cached meshes x n transforms
  *
  * Build: nvcc -gencode arch=compute_100a,code=sm_100a -fmad=false (see Makefile).  -fmad=false
@@ -939,7 +941,8 @@ __global__ void k_seg_double(const uint32_t* __restrict__ Jin, uint32_t* __restr
 }
 
 __global__ void k_seg_cmds(const uint32_t* __restrict__ starts, uint32_t numStarts, const ulonglong2* __restrict__ meshOff, uint32_t M, uint32_t ibCount,
-                           FinalHdr* __restrict__ hdr, vgb_draw_cmd* __restrict__ cmds)
+                           const uint32_t* __restrict__ jobDraw, const uint32_t* __restrict__ drawScissor, FinalHdr* __restrict__ hdr,
+                           vgb_draw_cmd* __restrict__ cmds)
 {
 	const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
 	if (j >= numStarts) return;
@@ -955,7 +958,7 @@ __global__ void k_seg_cmds(const uint32_t* __restrict__ starts, uint32_t numStar
 	c.num_indices = (uint32_t)(b.y - a.y);
 	c.first_mesh = s;
 	c.num_meshes = e - s;
-	c.reserved = 0;
+	c.scissor_id = drawScissor != nullptr ? drawScissor[jobDraw[s]] & 0x7fffffffu : 0u;
 	c.stream_vertex = a.x - o.x;
 	c.stream_index = a.y - o.y;
 	cmds[j] = c;
@@ -975,6 +978,93 @@ __global__ void k_seg_mesh_base(const uint32_t* __restrict__ starts, uint32_t nu
 		else hi = mid - 1;
 	}
 	meshBase[m] = (uint32_t)(meshOff[m].x - meshOff[starts[lo]].x) + (lo == 0 ? hdr->cmdV0 : 0u);
+}
+
+/* ---- scissor breaks inside a vertex buffer (m_ForceNewDrawCommand, vg.cpp:3946-4033 + 5368-5402) ----
+ * A draw recorded after a scissor change carries a mark; the flag stays up until a mesh with vertices consumes it
+ * (allocDrawCommand is only reached with vertices), and that mesh opens a new draw command in the SAME vertex
+ * buffer.  With  X[m] = (marks before m, non-empty meshes before m)  a non-empty mesh m opens a command iff there
+ * is a mark at or before it and no non-empty mesh between the latest such mark and m.  Draw commands are then the
+ * union of the vertex-buffer starts (the chain above) and those meshes; two more scans number them. */
+__global__ void k_split_marks(const ulonglong2* __restrict__ meshOff, uint32_t M, const uint32_t* __restrict__ jobDraw,
+                              const uint32_t* __restrict__ drawScissor, uint2* __restrict__ in)
+{
+	const uint32_t m = blockIdx.x * blockDim.x + threadIdx.x;
+	if (m >= M) return;
+	const uint32_t d = jobDraw[m];
+	const uint32_t mark = (drawScissor[d] >> 31) && (m == 0 || jobDraw[m - 1] != d) ? 1u : 0u; /* first mesh of a marked draw */
+	in[m] = make_uint2(mark, meshOff[m + 1].x > meshOff[m].x ? 1u : 0u);
+}
+
+__global__ void k_split_pos(const uint2* __restrict__ in, const ulonglong2* __restrict__ X, uint32_t M, uint32_t* __restrict__ markPos)
+{
+	const uint32_t m = blockIdx.x * blockDim.x + threadIdx.x;
+	if (m < M && in[m].x) markPos[X[m].x] = m;
+}
+
+/* flags[m] = (m starts a vertex buffer, m starts a draw command); overwrites the (mark, non-empty) pairs in place */
+__global__ void k_split_flags(uint2* __restrict__ io, const ulonglong2* __restrict__ X, uint32_t M, const uint32_t* __restrict__ markPos,
+                              const uint32_t* __restrict__ starts, uint32_t numStarts)
+{
+	const uint32_t m = blockIdx.x * blockDim.x + threadIdx.x;
+	if (m >= M) return;
+	const uint2 f = io[m];
+	uint32_t lo = 0, hi = numStarts - 1; /* last j with starts[j] <= m */
+	while (lo < hi) {
+		const uint32_t mid = lo + (hi - lo + 1) / 2;
+		if (starts[mid] <= m) lo = mid;
+		else hi = mid - 1;
+	}
+	const uint32_t vb = starts[lo] == m ? 1u : 0u;
+	uint32_t sc = 0;
+	const uint64_t k = X[m].x + f.x; /* marks at or before m */
+	if (f.y && k > 0) sc = X[m].y == X[markPos[k - 1]].y ? 1u : 0u;
+	io[m] = make_uint2(vb, vb | sc);
+}
+
+__global__ void k_split_cmds(const uint2* __restrict__ flags, const ulonglong2* __restrict__ Y, uint32_t M, const uint32_t* __restrict__ starts,
+                             const ulonglong2* __restrict__ meshOff, uint32_t ibCount, const uint32_t* __restrict__ jobDraw,
+                             const uint32_t* __restrict__ drawScissor, FinalHdr* __restrict__ hdr, vgb_draw_cmd* __restrict__ cmds,
+                             uint32_t* __restrict__ cmdMesh)
+{
+	const uint32_t m = blockIdx.x * blockDim.x + threadIdx.x;
+	if (m == 0) hdr->numCmds = (uint32_t)Y[M].y;
+	if (m >= M || !flags[m].y) return;
+	const uint32_t c = (uint32_t)Y[m].y;
+	const uint32_t j = (uint32_t)(Y[m].x + flags[m].x) - 1u; /* vertex buffer (= chain segment) of m */
+	const ulonglong2 a = meshOff[m], o = meshOff[0];
+	vgb_draw_cmd r;
+	r.vb_id = hdr->vbId0 + j;
+	r.first_vertex = (uint32_t)(a.x - meshOff[starts[j]].x) + (j == 0 ? hdr->first0 : 0u);
+	r.first_index = ibCount + (uint32_t)(a.y - o.y);
+	r.num_vertices = 0;
+	r.num_indices = 0;
+	r.first_mesh = m;
+	r.num_meshes = 0;
+	r.scissor_id = drawScissor[jobDraw[m]] & 0x7fffffffu;
+	r.stream_vertex = a.x - o.x;
+	r.stream_index = a.y - o.y;
+	cmds[c] = r;
+	cmdMesh[c] = m;
+}
+
+/* sizes of every command (up to the next command's first mesh) and the index base of every mesh */
+__global__ void k_split_fin(const uint2* __restrict__ flags, const ulonglong2* __restrict__ Y, uint32_t M, const ulonglong2* __restrict__ meshOff,
+                            const FinalHdr* __restrict__ hdr, const uint32_t* __restrict__ cmdMesh, vgb_draw_cmd* __restrict__ cmds,
+                            uint32_t* __restrict__ meshBase)
+{
+	const uint32_t m = blockIdx.x * blockDim.x + threadIdx.x;
+	const uint32_t numCmds = (uint32_t)Y[M].y;
+	if (m < numCmds) {
+		const uint32_t s = cmdMesh[m], e = m + 1 < numCmds ? cmdMesh[m + 1] : M;
+		cmds[m].num_vertices = (uint32_t)(meshOff[e].x - meshOff[s].x);
+		cmds[m].num_indices = (uint32_t)(meshOff[e].y - meshOff[s].y);
+		cmds[m].num_meshes = e - s;
+	}
+	if (m >= M) return;
+	const uint32_t c = (uint32_t)(Y[m].y + flags[m].y) - 1u; /* mesh 0 always starts a command */
+	/* command 0 continues the context's open command (cmdV0 vertices in it) unless mesh 0 itself was forced */
+	meshBase[m] = (uint32_t)(meshOff[m].x - meshOff[cmdMesh[c]].x) + (c == 0 ? hdr->cmdV0 : 0u);
 }
 
 /* the uv stream: every vertex of a colour mesh samples the white pixel (vg.cpp:5220-5227) */
@@ -1518,6 +1608,9 @@ public:
 	vgb_final_cfg fcfg{};
 	uint32_t finalCmdCap = 0;
 	DevBuf dSegNext[2], dSegStarts, dSegHdr, dSegCmds, dMeshBase, dUV;
+	DevBuf dDrawScissor, dSplitIn, dSplitX, dSplitY, dMarkPos, dCmdMesh; /* scissor breaks in the final layout */
+	bool haveScissor = false;
+	uint32_t numScissorBreaks = 0;
 	/* instance replay */
 	DevBuf dRXf, dRPos, dRCol, dRIdx;
 	uint32_t replayN = 0;
@@ -1539,7 +1632,7 @@ public:
 		DevBuf* all[] = {&dSubRec, &dCmd, &dData, &dScale, &dTol, &dXform, &dDraws, &dJobSub, &dJobDraw, &dSubNum, &dSubFirst,
 		                 &dSubClosed, &dPts, &dDD, &dJobPieces, &dPieceStart, &dJobRec, &dPieceJob, &dBlockTotals, &dBlockBase,
 		                 &dMeshTotals, &dMeshOff, &dScanTmp, &dBlockTail, &dSlotFirst, &dCounters, &dDenseFirst, &dDensePts, &dBulkErr, &dMeshSplit, &dTicket, &dRankTotals, &dRankBase, &dPos, &dCol, &dIdx,
-		                 &dCmdSub, &dCmdData, &dCmdCount, &dCmdOff, &dCmdOk, &dSubMode, &dSegNext[0], &dSegNext[1], &dSegStarts, &dSegHdr, &dSegCmds, &dMeshBase, &dUV, &dRXf, &dRPos, &dRCol, &dRIdx};
+		                 &dCmdSub, &dCmdData, &dCmdCount, &dCmdOff, &dCmdOk, &dSubMode, &dSegNext[0], &dSegNext[1], &dSegStarts, &dSegHdr, &dSegCmds, &dMeshBase, &dUV, &dDrawScissor, &dSplitIn, &dSplitX, &dSplitY, &dMarkPos, &dCmdMesh, &dRXf, &dRPos, &dRCol, &dRIdx};
 		for (DevBuf* b : all) b->release();
 		for (auto& e : ev) if (e) cudaEventDestroy(e);
 		for (auto& e : userEv) if (e) cudaEventDestroy(e);
@@ -1649,6 +1742,9 @@ public:
 		}
 		if (opsMask == 0 || (opsMask & (opsMask - 1))) opsMask = OPS_ALL; /* mixed batches use the general kernel */
 		rc |= up(dDraws, t.draws, t.numDraws, err);
+		haveScissor = t.drawScissor != nullptr;
+		numScissorBreaks = haveScissor ? t.numScissorBreaks : 0u;
+		if (haveScissor) rc |= up(dDrawScissor, t.drawScissor, t.numDraws, err);
 		if (!bulkMode) {
 			rc |= up(dJobSub, t.jobSub, t.numJobs, err);
 			rc |= up(dJobDraw, t.jobDraw, t.numJobs, err);
@@ -1944,10 +2040,11 @@ public:
 			uint32_t K = 0;
 			while (((uint64_t)1 << K) < segBound) ++K;
 			const uint32_t numStarts = 1u << K;
-			finalCmdCap = numStarts;
+			const bool split = numScissorBreaks > 0;
+			finalCmdCap = numStarts + numScissorBreaks;
 			if (dSegNext[0].ensure((size_t)(numJobs + 1) * 4, err) || dSegNext[1].ensure((size_t)(numJobs + 1) * 4, err) ||
 			    dSegStarts.ensure((size_t)numStarts * 4, err) || dSegHdr.ensure(sizeof(FinalHdr), err) ||
-			    dSegCmds.ensure((size_t)numStarts * sizeof(vgb_draw_cmd), err) || dMeshBase.ensure((size_t)numJobs * 4, err))
+			    dSegCmds.ensure((size_t)finalCmdCap * sizeof(vgb_draw_cmd), err) || dMeshBase.ensure((size_t)numJobs * 4, err))
 				return VGB_ERR_CUDA;
 			VGB_CUDA(cudaMemsetAsync(dSegHdr.p, 0, sizeof(FinalHdr), st));
 			const uint32_t jb = (numJobs + 1 + 255) / 256;
@@ -1961,11 +2058,34 @@ public:
 				                                 last ? 0u : 1u);
 				++launches;
 			}
-			k_seg_cmds<<<(numStarts + 255) / 256, 256, 0, st>>>(dSegStarts.as<uint32_t>(), numStarts, dMeshOff.as<ulonglong2>(), numJobs, fcfg.ib_count,
-			                                                     dSegHdr.as<FinalHdr>(), dSegCmds.as<vgb_draw_cmd>());
-			k_seg_mesh_base<<<(numJobs + 255) / 256, 256, 0, st>>>(dSegStarts.as<uint32_t>(), numStarts, dMeshOff.as<ulonglong2>(), numJobs,
-			                                                        dSegHdr.as<FinalHdr>(), dMeshBase.as<uint32_t>());
-			launches += 2;
+			if (!split) {
+				k_seg_cmds<<<(numStarts + 255) / 256, 256, 0, st>>>(dSegStarts.as<uint32_t>(), numStarts, dMeshOff.as<ulonglong2>(), numJobs, fcfg.ib_count,
+				                                                     dJobDraw.as<uint32_t>(), haveScissor ? dDrawScissor.as<uint32_t>() : nullptr,
+				                                                     dSegHdr.as<FinalHdr>(), dSegCmds.as<vgb_draw_cmd>());
+				k_seg_mesh_base<<<(numJobs + 255) / 256, 256, 0, st>>>(dSegStarts.as<uint32_t>(), numStarts, dMeshOff.as<ulonglong2>(), numJobs,
+				                                                        dSegHdr.as<FinalHdr>(), dMeshBase.as<uint32_t>());
+				launches += 2;
+			} else {
+				/* scissor changes open draw commands inside a vertex buffer */
+				if (dSplitIn.ensure((size_t)numJobs * 8, err) || dSplitX.ensure((size_t)(numJobs + 1) * 16, err) ||
+				    dSplitY.ensure((size_t)(numJobs + 1) * 16, err) || dMarkPos.ensure((size_t)(numScissorBreaks + 1) * 4, err) ||
+				    dCmdMesh.ensure((size_t)(finalCmdCap + 1) * 4, err))
+					return VGB_ERR_CUDA;
+				const uint32_t mb = (numJobs + 255) / 256;
+				k_split_marks<<<mb, 256, 0, st>>>(dMeshOff.as<ulonglong2>(), numJobs, dJobDraw.as<uint32_t>(), dDrawScissor.as<uint32_t>(), dSplitIn.as<uint2>());
+				if (scan<ScanOps<uint2>>(dSplitIn.as<uint2>(), numJobs, dSplitX.as<ulonglong2>(), err)) return VGB_ERR_CUDA;
+				k_split_pos<<<mb, 256, 0, st>>>(dSplitIn.as<uint2>(), dSplitX.as<ulonglong2>(), numJobs, dMarkPos.as<uint32_t>());
+				k_split_flags<<<mb, 256, 0, st>>>(dSplitIn.as<uint2>(), dSplitX.as<ulonglong2>(), numJobs, dMarkPos.as<uint32_t>(), dSegStarts.as<uint32_t>(),
+				                                   numStarts);
+				if (scan<ScanOps<uint2>>(dSplitIn.as<uint2>(), numJobs, dSplitY.as<ulonglong2>(), err)) return VGB_ERR_CUDA;
+				k_split_cmds<<<mb, 256, 0, st>>>(dSplitIn.as<uint2>(), dSplitY.as<ulonglong2>(), numJobs, dSegStarts.as<uint32_t>(), dMeshOff.as<ulonglong2>(),
+				                                  fcfg.ib_count, dJobDraw.as<uint32_t>(), dDrawScissor.as<uint32_t>(), dSegHdr.as<FinalHdr>(),
+				                                  dSegCmds.as<vgb_draw_cmd>(), dCmdMesh.as<uint32_t>());
+				const uint32_t fb = ((numJobs > finalCmdCap ? numJobs : finalCmdCap) + 255) / 256;
+				k_split_fin<<<fb, 256, 0, st>>>(dSplitIn.as<uint2>(), dSplitY.as<ulonglong2>(), numJobs, dMeshOff.as<ulonglong2>(), dSegHdr.as<FinalHdr>(),
+				                                 dCmdMesh.as<uint32_t>(), dSegCmds.as<vgb_draw_cmd>(), dMeshBase.as<uint32_t>());
+				launches += 5;
+			}
 			VGB_CUDA(cudaGetLastError());
 			pa.meshBase = dMeshBase.as<uint32_t>();
 			finalRan = true;

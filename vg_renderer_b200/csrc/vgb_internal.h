@@ -73,6 +73,9 @@ struct HostTables
 	/* draws and jobs */
 	const DrawRec* draws = nullptr;
 	uint32_t numDraws = 0;
+	/* per draw: scissor id | force-new-draw-command << 31 (nullptr: one scissor, no forced commands) */
+	const uint32_t* drawScissor = nullptr;
+	uint32_t numScissorBreaks = 0; /* draws carrying the force flag (bounds the draw-command table) */
 	const uint32_t* jobSub = nullptr;
 	const uint32_t* jobDraw = nullptr;
 	uint32_t numJobs = 0;
