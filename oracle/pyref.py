@@ -206,10 +206,18 @@ class CtxLib:
         if not os.path.exists(p):
             raise FileNotFoundError(f"{p} missing: run `make -C oracle ref` (needs /root/reference)")
         self.lib = C.CDLL(p)
-        self.lib.vgctx_run.restype = C.c_int
+        self.lib.vgctx_run_instances.restype = C.c_int
 
-    def run(self, script, list_flags=0, canvas=(1280, 720), max_vb_vertices=65536, vcap=1 << 22, icap=1 << 24):
+    def run(self, script, list_flags=0, canvas=(1280, 720), max_vb_vertices=65536, vcap=1 << 22, icap=1 << 24, xforms=None, children=()):
+        """xforms [n,6]: submit the list n times, each inside pushState / transformMult(row, Pre) / popState (with
+        list_flags = 1, Cacheable, the later submissions are the shape cache's replays); adds inv0 to the result"""
         script = np.frombuffer(bytes(script), np.uint8)
+        xf = None if xforms is None else np.ascontiguousarray(xforms, np.float32).reshape(-1, 6)
+        inv0 = np.zeros(6, np.float32)
+        # children: [(bytes, flags)] -> the context's lists 0 .. n-1, which SubmitCommandList records may name
+        kb = np.frombuffer(b"".join(bytes(c[0]) for c in children) + b"\0", np.uint8)
+        ks = np.asarray([len(bytes(c[0])) for c in children] + [0], np.uint32)
+        kf = np.asarray([c[1] for c in children] + [0], np.uint32)
         cl = np.zeros(len(script) + 4096, np.uint8)
         cl_size, ndraws, nvbs, nidx = C.c_uint32(), C.c_uint32(), C.c_uint32(), C.c_uint64()
         draws = np.zeros(1 << 16, CTX_DRAW_DTYPE)
@@ -218,8 +226,9 @@ class CtxLib:
         col = np.zeros(vcap, np.uint32)
         vbc = np.zeros(4096, np.uint32)
         idx = np.zeros(icap, np.uint16)
-        rc = self.lib.vgctx_run(_p(script, C.c_uint8), C.c_uint32(len(script)), C.c_uint32(list_flags), C.c_uint32(canvas[0]), C.c_uint32(canvas[1]),
-                                C.c_uint32(max_vb_vertices), _p(cl, C.c_uint8), C.c_uint32(len(cl)), C.byref(cl_size),
+        rc = self.lib.vgctx_run_instances(_p(script, C.c_uint8), C.c_uint32(len(script)), C.c_uint32(list_flags), C.c_uint32(canvas[0]), C.c_uint32(canvas[1]),
+                                C.c_uint32(max_vb_vertices), None if xf is None else _p(xf, C.c_float), C.c_uint32(0 if xf is None else len(xf)),
+                                _p(inv0, C.c_float), _p(kb, C.c_uint8), _p(ks, C.c_uint32), _p(kf, C.c_uint32), C.c_uint32(len(children)), _p(cl, C.c_uint8), C.c_uint32(len(cl)), C.byref(cl_size),
                                 draws.ctypes.data_as(C.c_void_p), C.c_uint32(len(draws)), C.byref(ndraws),
                                 _p(pos, C.c_float), _p(uv, C.c_int16), _p(col, C.c_uint32), C.c_uint64(vcap), _p(vbc, C.c_uint32), C.c_uint32(len(vbc)),
                                 C.byref(nvbs), _p(idx, C.c_uint16), C.c_uint64(icap), C.byref(nidx))
@@ -228,4 +237,4 @@ class CtxLib:
         counts = vbc[: nvbs.value].copy()
         nv = int(counts.sum())
         return dict(cl_bytes=cl[: cl_size.value].tobytes(), draws=draws[: ndraws.value].copy(), vb_counts=counts, pos=pos[:nv].copy(),
-                    uv=uv[:nv].copy(), color=col[:nv].copy(), index=idx[: nidx.value].copy())
+                    uv=uv[:nv].copy(), color=col[:nv].copy(), index=idx[: nidx.value].copy(), inv0=inv0)

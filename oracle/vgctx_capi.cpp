@@ -58,18 +58,9 @@ struct vgctx_draw
  * given comes back: per vertex buffer its pos / uv / colour streams (concatenated, vbCounts[i] vertices each), the
  * uint16 index buffer, and one record per bgfx::submit.
  */
-int vgctx_run(const uint8_t* script, uint32_t size, uint32_t listFlags, uint32_t canvasW, uint32_t canvasH, uint32_t maxVBVertices,
-              uint8_t* clBytes, uint32_t clCap, uint32_t* clSize,
-              vgctx_draw* draws, uint32_t drawCap, uint32_t* numDraws,
-              float* pos, int16_t* uv, uint32_t* col, uint64_t vcap, uint32_t* vbCounts, uint32_t vbCap, uint32_t* numVBs,
-              uint16_t* idx, uint64_t icap, uint64_t* numIdx)
+/* replay the records of a script through the public recording API into list cl */
+static int record(vg::Context* ctx, vg::CommandListHandle cl, const uint8_t* script, uint32_t size)
 {
-	vg::ContextConfig cfg = {64, 64, 8, 32, 16, 256, maxVBVertices ? maxVBVertices : 65536u, vg::ImageFlags::Filter_Bilinear, 16, true};
-	bgfx::recorder() = bgfx::Recorder();
-	bgfx::recorder().resetDraw();
-	vg::Context* ctx = vg::createContext(&s_ctxAlloc, &cfg);
-	if (!ctx) return -1;
-	vg::CommandListHandle cl = vg::createCommandList(ctx, listFlags);
 	int rc = 0;
 	const uint8_t* cmd = script;
 	const uint8_t* end = script + size;
@@ -131,10 +122,47 @@ int vgctx_run(const uint8_t* script, uint32_t size, uint32_t listFlags, uint32_t
 		} break;
 		case vg::CommandType::SetViewBox: vg::clSetViewBox(ctx, cl, f[0], f[1], f[2], f[3]); break;
 		case vg::CommandType::SetGlobalAlpha: vg::clSetGlobalAlpha(ctx, cl, f[0]); break;
+		case vg::CommandType::SubmitCommandList: {
+			const vg::CommandListHandle child = {r.get<uint16_t>()};
+			vg::clSubmitCommandList(ctx, cl, child);
+		} break;
 		default: rc = -2; break; /* outside the oracle's script vocabulary */
 		}
 		cmd = cmd + 16 + dataSize;
 	}
+	return rc;
+}
+
+/* xforms (numXforms x 6, may be null): instead of one submission under the identity, the list is submitted once per row
+ * inside  vg::pushState / vg::transformMult(row, Pre) / ... / vg::popState  -- with CommandListFlags::Cacheable in listFlags
+ * this is the shape cache's life cycle: the first submission tessellates and caches (addCachedCommand, vg.cpp:5803-5841),
+ * every later one whose average scale equals the cached one replays (clCacheRender -> submitCachedMesh, vg.cpp:6137-6166).
+ * inv0 (6 floats, may be null) receives vgutil::invertMatrix3 of the first row: the matrix beginCachedCommand stores
+ * (vg.cpp:5788) for a list without transforms of its own. */
+int vgctx_run_instances(const uint8_t* script, uint32_t size, uint32_t listFlags, uint32_t canvasW, uint32_t canvasH, uint32_t maxVBVertices,
+                        const float* xforms, uint32_t numXforms, float* inv0,
+                        const uint8_t* childBytes, const uint32_t* childSizes, const uint32_t* childFlags, uint32_t numChildren,
+                        uint8_t* clBytes, uint32_t clCap, uint32_t* clSize,
+                        vgctx_draw* draws, uint32_t drawCap, uint32_t* numDraws,
+                        float* pos, int16_t* uv, uint32_t* col, uint64_t vcap, uint32_t* vbCounts, uint32_t vbCap, uint32_t* numVBs,
+                        uint16_t* idx, uint64_t icap, uint64_t* numIdx)
+{
+	vg::ContextConfig cfg = {64, 64, 8, 32, 16, 256, maxVBVertices ? maxVBVertices : 65536u, vg::ImageFlags::Filter_Bilinear, 16, true};
+	bgfx::recorder() = bgfx::Recorder();
+	bgfx::recorder().resetDraw();
+	vg::Context* ctx = vg::createContext(&s_ctxAlloc, &cfg);
+	if (!ctx) return -1;
+	/* the lists a SubmitCommandList record may name: handles 0 .. numChildren-1 (the allocator hands them out in order),
+	 * all created before any is recorded so that they can name each other -- or themselves */
+	int rc = 0;
+	std::vector<vg::CommandListHandle> kids;
+	for (uint32_t i = 0; i < numChildren; ++i) {
+		kids.push_back(vg::createCommandList(ctx, childFlags[i]));
+		if (kids.back().idx != i) rc = -3;
+	}
+	for (uint32_t i = 0, off = 0; i < numChildren && rc == 0; off += childSizes[i], ++i) rc = record(ctx, kids[i], childBytes + off, childSizes[i]);
+	vg::CommandListHandle cl = vg::createCommandList(ctx, listFlags);
+	if (rc == 0) rc = record(ctx, cl, script, size);
 	if (rc == 0) {
 		/* the list as the reference recorded it */
 		const vg::CommandList* l = &ctx->m_CmdLists[cl.idx];
@@ -144,7 +172,17 @@ int vgctx_run(const uint8_t* script, uint32_t size, uint32_t listFlags, uint32_t
 	}
 	if (rc == 0) {
 		vg::begin(ctx, 0, (uint16_t)canvasW, (uint16_t)canvasH, 1.0f);
-		vg::submitCommandList(ctx, cl);
+		if (xforms == nullptr) {
+			vg::submitCommandList(ctx, cl);
+		} else {
+			if (inv0 && numXforms) vgutil::invertMatrix3(xforms, inv0);
+			for (uint32_t k = 0; k < numXforms; ++k) {
+				vg::pushState(ctx);
+				vg::transformMult(ctx, xforms + 6 * (size_t)k, vg::TransformOrder::Pre);
+				vg::submitCommandList(ctx, cl);
+				vg::popState(ctx);
+			}
+		}
 		vg::end(ctx);
 		const bgfx::Recorder& R = bgfx::recorder();
 		/* vertex buffers: vg.cpp creates (pos, uv, colour) handles per VertexBuffer, in that order (vg.cpp:1106-1114) */
@@ -179,8 +217,19 @@ int vgctx_run(const uint8_t* script, uint32_t size, uint32_t listFlags, uint32_t
 		vg::frame(ctx);
 	}
 	vg::destroyCommandList(ctx, cl);
+	for (size_t i = 0; i < kids.size(); ++i) vg::destroyCommandList(ctx, kids[i]);
 	vg::destroyContext(ctx);
 	return rc;
+}
+
+int vgctx_run(const uint8_t* script, uint32_t size, uint32_t listFlags, uint32_t canvasW, uint32_t canvasH, uint32_t maxVBVertices,
+              uint8_t* clBytes, uint32_t clCap, uint32_t* clSize,
+              vgctx_draw* draws, uint32_t drawCap, uint32_t* numDraws,
+              float* pos, int16_t* uv, uint32_t* col, uint64_t vcap, uint32_t* vbCounts, uint32_t vbCap, uint32_t* numVBs,
+              uint16_t* idx, uint64_t icap, uint64_t* numIdx)
+{
+	return vgctx_run_instances(script, size, listFlags, canvasW, canvasH, maxVBVertices, nullptr, 0, nullptr, nullptr, nullptr, nullptr, 0, clBytes, clCap, clSize, draws, drawCap,
+	                           numDraws, pos, uv, col, vcap, vbCounts, vbCap, numVBs, idx, icap, numIdx);
 }
 
 } /* extern "C" */

@@ -73,7 +73,7 @@ def records(buf):
     while i < len(buf):
         t, n = np.frombuffer(buf[i:i + 8], np.uint32)
         p = buf[i + 16:i + 16 + int(n)]
-        m = 4 + 8 * int(np.frombuffer(p[:4], np.uint32)[0]) if t == CL.POLYLINE else _PAYLOAD[int(t)]
+        m = 4 + 8 * int(np.frombuffer(p[:4], np.uint32)[0]) if t == CL.POLYLINE else 2 if t == CL.SUBMIT_LIST else _PAYLOAD[int(t)]
         out.append((int(t), int(n), bytes(p[:m])))
         i += 16 + int(n)
     assert i == len(buf)
@@ -280,3 +280,90 @@ def test_culling_scissor_and_matrix_commands_against_the_real_context(cull):
     np.testing.assert_array_equal(real["pos"], exp["pos"])
     np.testing.assert_array_equal(real["color"], exp["color"])
     assert int(real["draws"]["num_indices"].sum()) == exp["num_indices"]
+
+
+def plain_scene(seed=21, shapes=24):
+    """paths, fills and strokes with no transform or state commands of their own: one matrix for the whole list"""
+    rng = np.random.default_rng(seed)
+    w = CL.Writer()
+    for k in range(shapes):
+        x, y = [float(np.float32(v)) for v in rng.uniform(-150, 150, 2)]
+        w.begin_path()
+        if k % 4 == 0:
+            w.rounded_rect(x, y, 80, 45, 11.0)
+        elif k % 4 == 1:
+            w.circle(x, y, float(np.float32(rng.uniform(4, 40))))
+        elif k % 4 == 2:
+            w.move_to(x, y).cubic_to(x + 30, y - 50, x + 70, y + 60, x + 120, y).quadratic_to(x + 140, y + 50, x + 60, y + 55).close_path()
+        else:
+            w.move_to(x, y).line_to(x + 40, y + 10).arc_to(x + 90, y + 10, x + 90, y + 60, 15).line_to(x + 20, y + 70)
+        if k % 4 != 3:
+            w.fill(0xFF000000 | int(rng.integers(0, 1 << 24)), CL.fill_flags(aa=bool(k % 3)))
+        w.stroke(0xE0000000 | int(rng.integers(0, 1 << 24)), float(np.float32(rng.uniform(0.6, 5.0))), CL.stroke_flags(int(rng.integers(0, 3)), int(rng.integers(0, 3)), True))
+    return w
+
+
+def test_shape_cache_replay_is_the_restated_instance_replay():
+    """SURVEY 8 f3 against the reference's own shape cache: a Cacheable list submitted under n matrices of equal average
+    scale.  Submission 0 tessellates (= the decoder's recording under that matrix through the compiled hot path) and
+    caches Tinv(mesh) (addCachedCommand, vg.cpp:5803-5841); submissions 1.. are submitCachedMesh (vg.cpp:6137-6166):
+    pos = T_k(Tinv(pos_0)) by vgutil::batchTransformPositions, colours and local indices copied -- the contract
+    vgb_batch_replay implements (its GPU output is checked against the same two reference functions in
+    tests/test_gpu_parity.py::test_replay_matches_reference_transform)."""
+    s = 1.5
+    xf = np.asarray([[s, 0, 0, s, 400.25, 300.5], [0, s, -s, 0, 900.0, 120.0], [-s, 0, 0, -s, 1000.5, 650.0], [s, 0, 0, s, 77.0, 500.125],
+                     [0, -s, s, 0, 333.0, 444.0]], np.float32)
+    w = plain_scene()
+    real = CtxLib().run(w.bytes(), list_flags=1, canvas=(1280, 720), xforms=xf)
+    got = vgb.Batch(-1)
+    st = got.submit_command_list(w.bytes(), vgb.make_cl_context(xform=[float(v) for v in xf[0]], canvas=(1280.0, 720.0)))
+    assert st.unsupported == 0
+    ref = RefLib("scalar")
+    exp = ref.run_batch(tables_from_recorded(got.recorded_streams()))
+    V, I, n = exp["num_vertices"], exp["num_indices"], len(xf)
+    assert len(real["pos"]) == n * V and len(real["index"]) == n * I
+    np.testing.assert_array_equal(real["pos"][:V], exp["pos"])
+    cached = ref.transform_positions(exp["pos"], real["inv0"])
+    for k in range(1, n):
+        np.testing.assert_array_equal(real["pos"][k * V:(k + 1) * V], ref.transform_positions(cached, xf[k]), err_msg=f"instance {k}")
+        np.testing.assert_array_equal(real["color"][k * V:(k + 1) * V], exp["color"])
+    # the index buffer: every instance's local indices, rebased by the merge step like any other mesh
+    mvo = np.concatenate([exp["mesh_vtx_off"][:-1] + k * V for k in range(n)] + [[n * V]]).astype(np.uint64)
+    mio = np.concatenate([exp["mesh_idx_off"][:-1] + k * I for k in range(n)] + [[n * I]]).astype(np.uint64)
+    idx, _, cmds = ref.final_layout(mvo, mio, np.tile(exp["index"], n), vgb.make_final_cfg(65536))
+    np.testing.assert_array_equal(real["index"], idx)
+    assert len(cmds) == len(real["draws"])
+    # a matrix of another average scale invalidates the cache (vg.cpp:4289-4299): that submission is a fresh tessellation
+    xf2 = np.vstack([xf[:2], [[2.0, 0, 0, 2.0, 50.0, 60.0]]]).astype(np.float32)
+    real2 = CtxLib().run(w.bytes(), list_flags=1, canvas=(1280, 720), xforms=xf2)
+    got2 = vgb.Batch(-1)
+    got2.submit_command_list(w.bytes(), vgb.make_cl_context(xform=[float(v) for v in xf2[2]], canvas=(1280.0, 720.0)))
+    exp2 = ref.run_batch(tables_from_recorded(got2.recorded_streams()))
+    np.testing.assert_array_equal(real2["pos"][2 * V:], exp2["pos"])
+
+
+def test_nested_command_lists_against_the_real_context():
+    """SubmitCommandList inside lists (vg.cpp:4611-4618): state left behind by a child (VG_CONFIG_COMMAND_LIST_PRESERVE_STATE
+    is 0), a child submitted under different matrices, a handle that is not a list (skipped), a list that submits itself
+    until ContextConfig::m_MaxCommandListDepth (16, vg.cpp:4278-4283) stops it, a child with AllowCommandCulling."""
+    icon = CL.Writer().push_state().scale(0.5, 0.5).begin_path().rounded_rect(0, 0, 40, 40, 6).fill(0xFF336699, CL.fill_flags())
+    icon.stroke(0xFF000000, 2.0, CL.stroke_flags(1, 1, True)).pop_state().translate(50, 0)      # leaves a translation behind
+    row = CL.Writer().submit(0).submit(0).submit(9).rotate(0.2).submit(0)                         # 9: not a list -> skipped
+    deep = CL.Writer().translate(7, 5).begin_path().circle(20, 20, 6).fill(0xFFFFFFFF, CL.fill_flags(aa=False)).submit(2)  # submits itself
+    culled = CL.Writer().set_scissor(0, 0, 0.2, 0.2).begin_path().rect(0, 0, 5, 5).fill(0xFF00FF00, CL.fill_flags())
+    kids = [(icon, 0), (row, 0), (deep, 0), (culled, 2)]
+    top = CL.Writer().translate(100, 200).submit(1).push_state().scale(2, 2).submit(1).pop_state().submit(2).submit(3)
+    top.reset_scissor().begin_path().rect(1, 1, 90, 90).fill(0xFFABCDEF, CL.fill_flags())
+    real = CtxLib().run(top.bytes(), canvas=(1280, 720), children=[(w.bytes(), fl) for w, fl in kids])
+    assert records(real["cl_bytes"]) == records(top.bytes())
+    got = vgb.Batch(-1)
+    ctx = vgb.make_cl_context(canvas=(1280.0, 720.0), lists={k: (w.bytes(), fl) for k, (w, fl) in enumerate(kids)})
+    st = got.submit_command_list(top.bytes(), ctx)
+    assert st.nested == 2 + 6 + 16 + 1 and st.culled == 1 and st.draws == 2 * 6 + 15 + 1
+    ref = RefLib("scalar")
+    exp = ref.run_batch(tables_from_recorded(got.recorded_streams()))
+    np.testing.assert_array_equal(real["pos"], exp["pos"])
+    np.testing.assert_array_equal(real["color"], exp["color"])
+    idx, uv, cmds = ref.final_layout(exp["mesh_vtx_off"], exp["mesh_idx_off"], exp["index"], vgb.make_final_cfg(65536), mesh_scissor=got.recorded_mesh_scissor())
+    np.testing.assert_array_equal(real["index"], idx)
+    assert_cmds_equal_real(real, cmds, got.scissor_rects())
