@@ -16,6 +16,7 @@
 #include <string.h>
 #include <new>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 using namespace vgb;
@@ -63,6 +64,7 @@ struct vgb_batch
 	/* scissor state (vgb_batch_set_scissor): table of distinct uint16 rects, id of the current one, pending force flag */
 	std::vector<uint16_t> scissors = std::vector<uint16_t>(4, 0);
 	std::vector<uint32_t> drawScissor;
+	std::unordered_map<uint64_t, uint32_t> scissorIds;
 	uint32_t curScissor = 0, scissorBreaks = 0;
 	bool forceNewCmd = false, anyScissor = false;
 	/* current path */
@@ -90,7 +92,7 @@ struct vgb_batch
 		pathScale.clear(); pathTol.clear(); pathXform.clear();
 		anyXform = false;
 		draws.clear(); jobSub.clear(); jobDraw.clear();
-		scissors.assign(4, 0); drawScissor.clear();
+		scissors.assign(4, 0); drawScissor.clear(); scissorIds.clear();
 		curScissor = 0; scissorBreaks = 0; forceNewCmd = false; anyScissor = false;
 		inPath = subOpen = drawn = false;
 		rawMode = false;
@@ -366,14 +368,16 @@ int vgb_batch_set_scissor(vgb_batch* b, const float rect[4], int forceNewCommand
 	if (!b || !rect) return fail(VGB_ERR_INVALID, "null argument");
 	if (!finite_all(rect, 4)) return fail(VGB_ERR_NONFINITE, "non-finite scissor rect");
 	const uint16_t r[4] = {(uint16_t)rect[0], (uint16_t)rect[1], (uint16_t)rect[2], (uint16_t)rect[3]}; /* vg.cpp:5392-5395 */
-	uint32_t id = 0;
-	const uint32_t n = (uint32_t)(b->scissors.size() / 4);
-	for (id = 1; id < n; ++id) { /* id 0 is the "no scissor set" entry: never matched */
-		if (memcmp(&b->scissors[4 * (size_t)id], r, sizeof(r)) == 0) break;
-	}
-	if (id >= n) {
-		id = n;
+	/* one table entry per distinct rect; id 0 is the "no scissor set" entry and is never handed out */
+	const uint64_t key = (uint64_t)r[0] | (uint64_t)r[1] << 16 | (uint64_t)r[2] << 32 | (uint64_t)r[3] << 48;
+	const auto it = b->scissorIds.find(key);
+	uint32_t id;
+	if (it != b->scissorIds.end()) {
+		id = it->second;
+	} else {
+		id = (uint32_t)(b->scissors.size() / 4);
 		b->scissors.insert(b->scissors.end(), r, r + 4);
+		b->scissorIds.emplace(key, id);
 	}
 	b->curScissor = id;
 	b->forceNewCmd = b->forceNewCmd || forceNewCommand != 0;
