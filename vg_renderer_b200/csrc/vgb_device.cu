@@ -58,6 +58,9 @@ namespace vgb
 #ifndef VGB_EMIT_PREFETCH
 #define VGB_EMIT_PREFETCH 1
 #endif
+#ifndef VGB_SINGLE_PASS_DEFAULT
+#define VGB_SINGLE_PASS_DEFAULT 0 /* k_group_emit_sp instead of count + scans + k_group_emit when the output buffers exist */
+#endif
 #ifndef VGB_EMIT_MIN_BLOCKS_SPEC
 #define VGB_EMIT_MIN_BLOCKS_SPEC 8
 #endif
@@ -660,6 +663,13 @@ struct PieceArgs
 	const uint32_t* meshBase; /* final layout: per-mesh index base (nullptr otherwise) */
 	uint32_t* ticket;         /* emit: dynamic group tickets (zeroed by k_mesh_off) */
 	uint32_t chunkShift;      /* emit: a ticket is worth 1 << chunkShift consecutive groups */
+	/* single-pass emit (k_group_emit_sp): group descriptors of the chained scan, output capacity, mesh table */
+	uint4* spA;                /* per group: totals word  (see k_group_emit_sp) */
+	uint4* spP;                /* per group: prefix word */
+	uint32_t* spFlags;         /* bit 0: output capacity exceeded, bit 1: the look-back gave up (never expected) */
+	uint64_t capV, capI;
+	const uint32_t* pieceStart; /* numJobs + 1 */
+	ulonglong2* meshOffW;       /* numJobs + 1, written by the groups that hold a job's first piece */
 	/* emit outputs */
 	float2* pos;
 	uint32_t* col;
@@ -1486,6 +1496,312 @@ __global__ void __launch_bounds__(128, (OPS == OPS_STROKE_AA && JT < 3) ? VGB_EM
 	}
 }
 
+/* ---- single-pass emit: classification, offsets and output in ONE kernel ---------------------------
+ * (experimental: VGB_SINGLE_PASS=1; results are bit-identical to the two-pass pipeline, see profiles/README.md for
+ * where it stands on speed)
+ * k_group_count + the two scans + k_mesh_off compute, for every group of 32 pieces, exactly what k_group_emit
+ * computes again right before it writes: the pieces' sizes.  This variant classifies once.  A group's output
+ * offset is the sum of the sizes of all groups before it, which a chained scan with decoupled look-back
+ * (Merrill & Garland) delivers inside the kernel: every group publishes its totals as soon as its pieces are
+ * classified (descriptor word A), then sums its predecessors' descriptors backwards until it meets one that
+ * already knows its own inclusive prefix (word P), and publishes P itself -- before it emits anything.
+ * Two more things used to come from the count pass and travel through the descriptors as well:
+ *   - the hand-over word of the previous group's last piece (lane 0's `prev` vertices),
+ *   - F, the number of vertices the lane's mesh already holds: for a job that began in an earlier group this is
+ *     the job's share of the group it began in plus the whole of every group in between (`spans`), i.e. a second,
+ *     segmented sum over the same descriptors.
+ * The mesh table is written by the lanes that hold a job's first piece.  The output buffers must exist before the
+ * sizes are known: the kernel is given their capacity, a group that would not fit writes nothing and raises a
+ * flag (the host grows the buffers to the totals the scan produced anyway, and runs the kernel again).
+ * Waiting is bounded: a look-back that polls one descriptor SP_POLL_LIMIT times gives up, raises a flag that stops
+ * every other look-back, and the host runs the batch through the two-pass pipeline. */
+/* A descriptor is TWO self-validating 16-byte words, each written with one aligned 128-bit store and read with one
+ * 128-bit load (what cub::ScanTileState does for its status + value words): no fence on either side, a reader either
+ * sees a whole word or the zeros the host left there.
+ *   word A (totals known):   x = vertices | 0x5 << 28, y = indices, z = last piece's hand-over word,
+ *                            w = the last job's vertices inside the group | spans << 31
+ *   word P (prefix known):   x = prefix vertices (low 32), y = high 16 of both prefixes, z = prefix indices (low 32),
+ *                            w = the last job's vertices up to the end of the group | 0xA << 28 */
+__device__ __forceinline__ void spStore(uint4* p, uint4 v)
+{
+	asm volatile("st.relaxed.gpu.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ uint4 spLoad(const uint4* p)
+{
+	uint4 v;
+	asm volatile("ld.relaxed.gpu.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+	return v;
+}
+__device__ __forceinline__ uint4 spWordA(uint32_t totV, uint32_t totI, uint32_t tail, uint32_t lastLocal, uint32_t spans)
+{
+	return make_uint4((totV & 0x0FFFFFFFu) | 0x50000000u, totI, tail, (lastLocal & 0x7FFFFFFFu) | (spans << 31));
+}
+__device__ __forceinline__ uint4 spWordP(uint64_t pv, uint64_t pi, uint32_t carry)
+{
+	return make_uint4((uint32_t)pv, (uint32_t)((pv >> 32) & 0xFFFFu) | ((uint32_t)((pi >> 32) & 0xFFFFu) << 16), (uint32_t)pi,
+	                  (carry & 0x0FFFFFFFu) | 0xA0000000u);
+}
+__device__ __forceinline__ uint64_t warpSum64(uint64_t v)
+{
+#pragma unroll
+	for (int d = 16; d > 0; d >>= 1) {
+		v += __shfl_xor_sync(0xffffffffu, v, d);
+	}
+	return v;
+}
+
+static constexpr uint32_t SP_POLL_LIMIT = 1u << 22; /* polls of one descriptor before the look-back gives up */
+
+struct SpLook
+{
+	uint64_t exV, exI; /* exclusive prefix of the group */
+	uint32_t carry;    /* vertices lane 0's job holds before this group (if that job began earlier) */
+	uint32_t tail;     /* hand-over word of the previous group's last piece */
+	bool dead;
+};
+
+/* all 32 lanes; w > 0.  Lane l looks at group base - l; the window moves back 32 groups at a time. */
+__device__ __forceinline__ SpLook spLookBack(const PieceArgs& a, uint32_t w, uint32_t lane)
+{
+	SpLook r;
+	r.exV = r.exI = 0;
+	r.carry = r.tail = 0;
+	r.dead = false;
+	bool carryDone = false, first = true;
+	int64_t base = (int64_t)w - 1;
+	for (;;) {
+		const int64_t u = base - (int64_t)lane;
+		/* before group 0 everything is zero and known */
+		uint4 wa = make_uint4(0x50000000u, 0u, 0u, 0u), wp = make_uint4(0u, 0u, 0u, 0xA0000000u);
+		bool gaveUp = false;
+		if (u >= 0) {
+			uint32_t polls = 0;
+			for (;;) {
+				wa = spLoad(a.spA + u);
+				if ((wa.x >> 28) == 0x5u) break;
+				__nanosleep(40);
+				if (++polls >= SP_POLL_LIMIT || ((polls & 1023u) == 0 && (*(volatile uint32_t*)a.spFlags & 2u))) {
+					gaveUp = true;
+					break;
+				}
+			}
+			wp = spLoad(a.spP + u);
+		}
+		if (__any_sync(0xffffffffu, gaveUp)) {
+			if (lane == 0) atomicOr(a.spFlags, 2u);
+			r.dead = true;
+			return r;
+		}
+		const bool res = (wp.w >> 28) == 0xAu;
+		const unsigned pm = __ballot_sync(0xffffffffu, res);
+		const uint32_t np = pm ? (uint32_t)__ffs(pm) - 1u : 32u; /* nearest resolved predecessor of this window */
+		uint64_t cv = 0, ci = 0;
+		if (lane < np) {
+			cv = wa.x & 0x0FFFFFFFu;
+			ci = wa.y;
+		} else if (lane == np) {
+			cv = (uint64_t)wp.x | ((uint64_t)(wp.y & 0xFFFFu) << 32);
+			ci = (uint64_t)wp.z | ((uint64_t)(wp.y >> 16) << 32);
+		}
+		r.exV += warpSum64(cv);
+		r.exI += warpSum64(ci);
+		if (!carryDone) {
+			/* the walk over the job that reaches into this group ends at the first group it does not span */
+			const bool stop = res || !(wa.w >> 31);
+			const unsigned sm = __ballot_sync(0xffffffffu, stop);
+			const uint32_t k = sm ? (uint32_t)__ffs(sm) - 1u : 32u;
+			uint32_t c = 0;
+			if (lane < k) c = wa.w & 0x7FFFFFFFu;
+			else if (lane == k) c = res ? (wp.w & 0x0FFFFFFFu) : (wa.w & 0x7FFFFFFFu);
+			r.carry += __reduce_add_sync(0xffffffffu, c);
+			carryDone = k < 32u;
+		}
+		if (first) {
+			r.tail = __shfl_sync(0xffffffffu, wa.z, 0);
+			first = false;
+		}
+		if (np < 32u) break;
+		base -= 32;
+	}
+	return r;
+}
+
+template<class IDX, uint32_t OPS, int JT, int CT, bool BIGI>
+__global__ void __launch_bounds__(128, (OPS == OPS_STROKE_AA && JT < 3) ? VGB_EMIT_MIN_BLOCKS_SPEC : VGB_EMIT_MIN_BLOCKS) k_group_emit_sp(PieceArgs a)
+{
+	constexpr uint32_t CIW = (sizeof(IDX) == 2 || BIGI) ? CIW_COUNT : CIW_COUNT / 2;
+	constexpr uint32_t KI = 16 / sizeof(IDX);
+	constexpr uint32_t POS_BYTES = (CVW + 2) * 8, COL_BYTES = (CVW + 4) * 4, IDX_BYTES = (CIW + KI) * sizeof(IDX);
+	constexpr uint32_t WBYTES = POS_BYTES + COL_BYTES + IDX_BYTES;
+	static_assert(POS_BYTES % 16 == 0 && COL_BYTES % 16 == 0 && IDX_BYTES % 16 == 0, "16-byte aligned staging streams");
+	__shared__ __align__(16) uint8_t sStage[4 * WBYTES];
+
+	const uint32_t lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+	const uint32_t numGroups = (a.numPieces + 31) >> 5;
+	/* group order: a warp's first group is its index in the grid, every later one a ticket drawn ONE group ahead (at the
+	 * top of the group before it).  What keeps the look-back decoupled is that every group publishes its totals a
+	 * roughly fixed time after its id became known to be taken: immediately for the first groups, one group later for
+	 * ticketed ones.  (Handing a warp several consecutive groups at once breaks exactly that: see launchEmitSp.) */
+	const uint32_t W = gridDim.x * 4;
+	uint32_t w = blockIdx.x * 4 + wib;
+	if (w >= numGroups) {
+		return;
+	}
+	uint8_t* stage = sStage + wib * WBYTES;
+	float2* sPos = reinterpret_cast<float2*>(stage);
+	uint32_t* sCol = reinterpret_cast<uint32_t*>(stage + POS_BYTES);
+	IDX* sIdx = reinterpret_cast<IDX*>(stage + POS_BYTES + COL_BYTES);
+	bool copyPending = false;
+	uint2 rec = make_uint2(0u, 0u);
+	if (w * 32 + lane < a.numPieces) rec = a.pieceRec[w * 32 + lane];
+	for (;;) {
+	const uint32_t g = w * 32 + lane;
+	const bool valid = g < a.numPieces;
+	const uint32_t j = rec.x;
+	uint32_t ticketNext = 0;
+	if (lane == 0) ticketNext = atomicAdd(a.ticket, 1u); /* consumed after the totals are published */
+	JobCtx J;
+	Piece P;
+	uint32_t q = 0, ps = 0;
+	if (OPS == OPS_STROKE_AA) {
+		const float2 p = a.pts[rec.y];
+		const float2 edge = loadEdge(a.pts, rec.y, p, lane);
+		J = loadJob(a, j, &ps);
+		q = g - ps;
+		P = classifyWarpAA<JT, CT>(a.pts, J, j, q, valid, p, edge, lane);
+		if (!valid) {
+			P.kind = PK_NONE;
+			P.vcount = P.icount = 0;
+			P.flags = 0;
+		}
+	} else {
+		P.kind = PK_NONE;
+		P.vcount = P.icount = 0;
+		P.flags = 0;
+		if (valid) {
+			J = loadJob(a, j, &ps);
+			q = g - ps;
+			P = classify<OPS, JT, CT>(J, q, a.pts);
+		}
+	}
+	const uint32_t myTail = valid ? packTail(P) : 0u;
+	const uint2 inc = warpInclusive(make_uint2(P.vcount, P.icount), lane);
+	const uint32_t vl = inc.x - P.vcount, il = inc.y - P.icount;
+	const uint32_t totV = __shfl_sync(0xffffffffu, inc.x, 31), totI = __shfl_sync(0xffffffffu, inc.y, 31);
+	/* where the lane's job begins: a lane of this group (>= 0) or an earlier group (-1) */
+	const uint32_t g0 = w * 32;
+	const bool inside = valid && ps >= g0;
+	const uint32_t vlAtStart = __shfl_sync(0xffffffffu, vl, inside ? (int)(ps - g0) : 0);
+	const uint32_t ownV = inc.x - (inside ? vlAtStart : 0u); /* the job's vertices in this group up to and including the lane */
+	/* descriptor fields: the last piece's hand-over word; the last job's share of this group; does it span the group */
+	const uint32_t tail31 = __shfl_sync(0xffffffffu, myTail, 31);
+	const uint32_t lastLocal = __shfl_sync(0xffffffffu, valid ? ownV : 0u, 31);
+	const uint32_t spans = __shfl_sync(0xffffffffu, (valid && !inside) ? 1u : 0u, 31);
+	/* totals known: publish them, then fetch the next group's id and piece records while the look-back runs */
+	if (lane == 0) {
+		spStore(a.spA + w, spWordA(totV, totI, tail31, lastLocal, spans));
+	}
+	const uint32_t wn = W + __shfl_sync(0xffffffffu, ticketNext, 0);
+	uint2 recN = make_uint2(0u, 0u);
+	if (wn < numGroups && wn * 32 + lane < a.numPieces) recN = a.pieceRec[wn * 32 + lane];
+	uint64_t exV = 0, exI = 0;
+	uint32_t carryIn = 0, tw0 = 0;
+	if (w > 0) {
+		const SpLook lb = spLookBack(a, w, lane);
+		if (lb.dead) {
+			break;
+		}
+		exV = lb.exV;
+		exI = lb.exI;
+		carryIn = lb.carry;
+		tw0 = lb.tail;
+	}
+	const uint64_t runV = exV + totV, runI = exI + totI;
+	if (lane == 0) {
+		spStore(a.spP + w, spWordP(runV, runI, spans ? carryIn + totV : lastLocal));
+	}
+#if VGB_EMIT_PREFETCH
+	if (wn < numGroups && wn * 32 + lane < a.numPieces) {
+		asm volatile("prefetch.global.L2 [%0];" ::"l"(a.pts + recN.y));
+		asm volatile("prefetch.global.L2 [%0];" ::"l"(a.jobRec + recN.x));
+	}
+#endif
+	uint32_t tw = __shfl_up_sync(0xffffffffu, myTail, 1);
+	if (lane == 0) {
+		tw = tw0;
+	}
+	const ulonglong2 bb = make_ulonglong2(exV, exI);
+	uint32_t F = 0;
+	uint64_t mox = 0;
+	uint4 prev = make_uint4(0, 0, 0, 0);
+	if (valid) {
+		F = inside ? vl - vlAtStart : carryIn + vl;
+		mox = bb.x + vl - F; /* first vertex of the lane's mesh */
+		if (P.flags & PF_HAS_PREV) {
+			prev = ((OPS & OPS_OTHER) && J.op != VGB_OP_STROKE_AA) ? ribbonOutFromTail(J, tw, F)
+			                                                        : out4FromTail(CT < 3 ? (uint32_t)CT : J.cap, JT < 3 ? (uint32_t)JT : J.join, tw, F);
+		}
+		/* the mesh table: a job's first piece knows where the mesh starts; empty jobs start where the next piece does */
+		if (g == ps) {
+			const ulonglong2 o = make_ulonglong2(bb.x + vl, bb.y + il);
+			a.meshOffW[j] = o;
+			for (uint32_t jj = j; jj-- > 0 && a.pieceStart[jj] == g;) {
+				a.meshOffW[jj] = o;
+			}
+		}
+		if (g + 1 == a.numPieces) {
+			const ulonglong2 o = make_ulonglong2(runV, runI);
+			for (uint32_t jj = j + 1; jj <= a.numJobs; ++jj) {
+				a.meshOffW[jj] = o;
+			}
+		}
+	}
+	const uint32_t idxBase = sizeof(IDX) == 2 ? 0u : (uint32_t)(mox + a.vertexBase);
+	const bool room = runV <= a.capV && runI <= a.capI; /* warp-uniform; prefixes grow, so later groups agree */
+	const bool fits = totV <= CVW && totI <= CIW;        /* warp-uniform */
+	if (!room) {
+		if (lane == 0) atomicOr(a.spFlags, 1u);
+	} else if (fits) {
+		if (copyPending) {
+			if (lane == 0 || lane == 2 || lane == 8) {
+				bulkWaitRead();
+			}
+			__syncwarp();
+		}
+		SinkS<IDX, !(OPS & OPS_OTHER)> S;
+		S.base = idxBase;
+		S.pos = sPos + (uint32_t)(bb.x & 1) + vl;
+		S.col = sCol + (uint32_t)(bb.x & 3) + vl;
+		S.idx = sIdx + (uint32_t)(bb.y & (KI - 1)) + il;
+		S.par = ((uint32_t)bb.y + il) & 1u;
+		if (valid) {
+			emitAny<OPS, JT, CT>(a.pts, J, P, F, prev, S);
+		}
+		fenceProxyAsync();
+		__syncwarp();
+		copyOutWarp3<IDX>(a.pos, a.col, reinterpret_cast<IDX*>(a.idx), bb.x, bb.y, totV, totI, sPos, sCol, sIdx, lane);
+		copyPending = true;
+	} else if (valid) {
+		Sink<IDX, !(OPS & OPS_OTHER)> S;
+		S.base = idxBase;
+		S.par = 0;
+		S.pos = a.pos + bb.x + vl;
+		S.col = a.col + bb.x + vl;
+		S.idx = reinterpret_cast<IDX*>(a.idx) + bb.y + il;
+		emitAnyCold<OPS, JT, CT>(a.pts, J, P, F, prev, S);
+	}
+	/* next group */
+	w = wn;
+	rec = recN;
+	if (w >= numGroups) {
+		break;
+	}
+	} /* groups of this warp */
+	if (copyPending && (lane == 0 || lane == 2 || lane == 8)) {
+		bulkWaitRead();
+	}
+}
+
 /* =========================================================================================
  * pure convex-AA-fill batches (BASELINE configs[3]): sizes are closed-form (V = 2N, I = 9N - 6,
  * stroker.cpp:726-730), so there is no count pass at all, and every output of a polygon vertex has
@@ -1609,6 +1925,9 @@ public:
 	uint32_t finalCmdCap = 0;
 	DevBuf dSegNext[2], dSegStarts, dSegHdr, dSegCmds, dMeshBase, dUV;
 	DevBuf dDrawScissor, dSplitIn, dSplitX, dSplitY, dMarkPos, dCmdMesh; /* scissor breaks in the final layout */
+	DevBuf dSpDesc; /* single-pass emit: group descriptors (two 16-byte words per group) */
+	int spMode = -1;                /* -1: read VGB_SINGLE_PASS on first use */
+	bool spUnchecked = false;       /* a single-pass run of known sizes whose flags have not been looked at yet */
 	bool haveScissor = false;
 	uint32_t numScissorBreaks = 0;
 	/* instance replay */
@@ -1632,7 +1951,7 @@ public:
 		DevBuf* all[] = {&dSubRec, &dCmd, &dData, &dScale, &dTol, &dXform, &dDraws, &dJobSub, &dJobDraw, &dSubNum, &dSubFirst,
 		                 &dSubClosed, &dPts, &dDD, &dJobPieces, &dPieceStart, &dJobRec, &dPieceJob, &dBlockTotals, &dBlockBase,
 		                 &dMeshTotals, &dMeshOff, &dScanTmp, &dBlockTail, &dSlotFirst, &dCounters, &dDenseFirst, &dDensePts, &dBulkErr, &dMeshSplit, &dTicket, &dRankTotals, &dRankBase, &dPos, &dCol, &dIdx,
-		                 &dCmdSub, &dCmdData, &dCmdCount, &dCmdOff, &dCmdOk, &dSubMode, &dSegNext[0], &dSegNext[1], &dSegStarts, &dSegHdr, &dSegCmds, &dMeshBase, &dUV, &dDrawScissor, &dSplitIn, &dSplitX, &dSplitY, &dMarkPos, &dCmdMesh, &dRXf, &dRPos, &dRCol, &dRIdx};
+		                 &dCmdSub, &dCmdData, &dCmdCount, &dCmdOff, &dCmdOk, &dSubMode, &dSegNext[0], &dSegNext[1], &dSegStarts, &dSegHdr, &dSegCmds, &dMeshBase, &dUV, &dDrawScissor, &dSplitIn, &dSplitX, &dSplitY, &dMarkPos, &dCmdMesh, &dSpDesc, &dRXf, &dRPos, &dRCol, &dRIdx};
 		for (DevBuf* b : all) b->release();
 		for (auto& e : ev) if (e) cudaEventDestroy(e);
 		for (auto& e : userEv) if (e) cudaEventDestroy(e);
@@ -1817,6 +2136,36 @@ public:
 		k_group_emit<IDX, OPS, JT, CT, BIGI><<<need < cap ? need : cap, PPB, 0, st>>>(q);
 	}
 
+	template<class IDX, uint32_t OPS, int JT, int CT, bool BIGI>
+	void launchEmitSp(const PieceArgs& pa, uint32_t gridBlocks)
+	{
+		static int perSM = 0;
+		if (perSM == 0) {
+			cudaFuncSetAttribute(k_group_emit_sp<IDX, OPS, JT, CT, BIGI>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
+			if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_group_emit_sp<IDX, OPS, JT, CT, BIGI>, (int)PPB, 0) != cudaSuccess || perSM < 1) perSM = 8;
+			const char* f = getenv("VGB_EMIT_PER_SM");
+			if (f && atoi(f) > 0) perSM = atoi(f);
+		}
+		if (numSMs == 0) {
+			if (cudaDeviceGetAttribute(&numSMs, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || numSMs < 1) numSMs = 148;
+		}
+		const uint32_t cap = (uint32_t)perSM * (uint32_t)numSMs;
+		/* one group per ticket: a decoupled look-back only stays decoupled if every group publishes its totals a
+		 * (roughly) fixed time after its ticket was drawn.  A warp walking the 4 consecutive groups of one ticket
+		 * publishes the 4th three groups later than the 1st, every later ticket waits for it, and the waits chain
+		 * up over the whole launch (measured: 2.9 s instead of 1 ms on the headline workload) */
+		PieceArgs q = pa;
+		static int spChunk = -1;
+		if (spChunk < 0) {
+			const char* e = getenv("VGB_SP_CHUNK_SHIFT"); /* diagnosis only */
+			spChunk = e ? atoi(e) : 0;
+		}
+		q.chunkShift = (uint32_t)spChunk;
+		const uint32_t need = (gridBlocks + (1u << q.chunkShift) - 1) >> q.chunkShift;
+		if (getenv("VGB_DEBUG")) fprintf(stderr, "[vgb] single-pass emit grid: perSM %d blocks %u of %u\n", perSM, need < cap ? need : cap, gridBlocks);
+		k_group_emit_sp<IDX, OPS, JT, CT, BIGI><<<need < cap ? need : cap, PPB, 0, st>>>(q);
+	}
+
 	int run(uint32_t flags, uint64_t vertexBase, std::string* err, const MergeHook* merge = nullptr) override
 	{
 		if (!uploaded) {
@@ -1971,6 +2320,7 @@ public:
 			numPts = kNumPts;
 			sz.num_points = numPts;
 		}
+		bool useSp = false;
 		const uint32_t numBlocks = (numPieces + GRP - 1) / GRP;          /* offset groups (warps or blocks) */
 		const uint32_t gridBlocks = (numPieces + PPB - 1) / PPB;         /* 128-thread launch blocks      */
 		uint64_t totals[2] = {0, 0};
@@ -1999,7 +2349,18 @@ public:
 			pa.vertexBase = vertexBase;
 			if (dTicket.ensure(16, err)) return VGB_ERR_CUDA;
 			pa.ticket = dTicket.as<uint32_t>();
-			if (fillOnly) {
+			/* single-pass emit (k_group_emit_sp): no count pass; needs output buffers before the sizes are known, so it
+			 * runs when a previous run left buffers behind (or the sizes of this upload are known), and never with the
+			 * final layout or a merged run, whose tables need the totals before the first vertex is written */
+			if (spMode < 0) {
+				const char* e = getenv("VGB_SINGLE_PASS");
+				spMode = e ? atoi(e) : VGB_SINGLE_PASS_DEFAULT;
+			}
+			useSp = spMode > 0 && !fillOnly && !finalOn && merge == nullptr &&
+			        (sizesKnown || (dPos.cap > 64 && dCol.cap > 64 && dIdx.cap > 64));
+			if (useSp) {
+				/* nothing to do here: classification happens in the emit kernel */
+			} else if (fillOnly) {
 				/* closed-form sizes: the mesh table is a plain scan of (2N, 9N-6); no count kernel */
 				if (scan<ScanOps<uint2>>(dMeshTotals.as<uint2>(), numJobs, dMeshOff.as<ulonglong2>(), err)) return VGB_ERR_CUDA;
 			} else {
@@ -2020,7 +2381,7 @@ public:
 			if (sizesKnown) {
 				totals[0] = kTotals[0];
 				totals[1] = kTotals[1];
-			} else if (readback(totals, dMeshOff.as<ulonglong2>() + numJobs, 16, err)) {
+			} else if (!useSp && readback(totals, dMeshOff.as<ulonglong2>() + numJobs, 16, err)) {
 				return VGB_ERR_CUDA;
 			}
 		} else {
@@ -2105,7 +2466,75 @@ public:
 		VGB_CUDA(cudaEventRecord(ev[2], st));
 
 		/* ---- emit ---- */
-		if (numPieces) {
+		if (numPieces && useSp) {
+			if (dSpDesc.ensure((size_t)numBlocks * 32, err)) return VGB_ERR_CUDA;
+			pa.spA = dSpDesc.as<uint4>();
+			pa.spP = dSpDesc.as<uint4>() + numBlocks;
+			pa.spFlags = dTicket.as<uint32_t>() + 1;
+			pa.pieceStart = dPieceStart.as<uint32_t>();
+			pa.meshOffW = dMeshOff.as<ulonglong2>();
+			const bool bigI = idxBytes == 4 && sizesKnown && numBlocks > 0 && totals[1] / numBlocks > (uint64_t)(CIW_COUNT / 2) * 3 / 4;
+			for (int attempt = 0;; ++attempt) {
+				if (sizesKnown || attempt > 0) {
+					if (dPos.ensure(totals[0] * 8 + 32, err) || dCol.ensure(totals[0] * 4 + 32, err) || dIdx.ensure(totals[1] * idxBytes + 32, err))
+						return VGB_ERR_CUDA;
+				}
+				pa.pos = dPos.as<float2>();
+				pa.col = dCol.as<uint32_t>();
+				pa.idx = dIdx.p;
+				const uint64_t cv0 = (dPos.cap - 32) / 8, cv1 = (dCol.cap - 32) / 4;
+				pa.capV = cv0 < cv1 ? cv0 : cv1;
+				pa.capI = (dIdx.cap - 32) / idxBytes;
+				VGB_CUDA(cudaMemsetAsync(dSpDesc.p, 0, (size_t)numBlocks * 32, st));
+				VGB_CUDA(cudaMemsetAsync(dTicket.p, 0, 16, st));
+#define VGB_EMIT_K(T, O, J, C)                                                   \
+	do {                                                                         \
+		if (bigI) launchEmitSp<T, O, J, C, true>(pa, gridBlocks);                 \
+		else launchEmitSp<T, O, J, C, false>(pa, gridBlocks);                     \
+	} while (0)
+#define VGB_LAUNCH_EMIT(T)                                                                                  \
+	do {                                                                                                    \
+		if (opsMask == OPS_STROKE_AA && uniJoin == VGB_JOIN_ROUND && uniCap == VGB_CAP_ROUND) VGB_EMIT_K(T, OPS_STROKE_AA, 1, 1); \
+		else if (opsMask == OPS_STROKE_AA && uniJoin == VGB_JOIN_MITER && uniCap == VGB_CAP_BUTT) VGB_EMIT_K(T, OPS_STROKE_AA, 0, 0); \
+		else if (opsMask == OPS_STROKE_AA) VGB_EMIT_K(T, OPS_STROKE_AA, 3, 3); \
+		else if (opsMask == OPS_FILL_AA) VGB_EMIT_K(T, OPS_FILL_AA, 3, 3); \
+		else VGB_EMIT_K(T, OPS_ALL, 3, 3);                                 \
+	} while (0)
+				if (idxBytes == 2) {
+					if (bigI) return VGB_ERR_STATE; /* uint16 + BIGI is the final layout: never single-pass */
+					VGB_LAUNCH_EMIT(uint16_t);
+				} else {
+					VGB_LAUNCH_EMIT(uint32_t);
+				}
+#undef VGB_LAUNCH_EMIT
+#undef VGB_EMIT_K
+				++launches;
+				VGB_CUDA(cudaGetLastError());
+				if (sizesKnown) {
+					/* the buffers hold exactly this upload's output: nothing can overflow, and the flags are looked at
+					 * where the stream is drained anyway (sync / download) instead of draining it here */
+					spUnchecked = true;
+					break;
+				}
+				/* a new upload: the totals the scan produced, and whether everything fitted */
+				uint64_t* h = reinterpret_cast<uint64_t*>(hPinned);
+				VGB_CUDA(cudaMemcpyAsync(h, dMeshOff.as<ulonglong2>() + numJobs, 16, cudaMemcpyDeviceToHost, st));
+				VGB_CUDA(cudaMemcpyAsync(h + 2, dTicket.as<uint32_t>() + 1, 4, cudaMemcpyDeviceToHost, st));
+				VGB_CUDA(cudaStreamSynchronize(st));
+				const uint32_t spf = *reinterpret_cast<uint32_t*>(h + 2);
+				if ((spf & 2u) || attempt > 1) {
+					/* the look-back gave up (never expected): this batch object goes back to the two-pass pipeline */
+					spMode = 0;
+					return run(flags, vertexBase, err, merge);
+				}
+				totals[0] = h[0];
+				totals[1] = h[1];
+				if (!(spf & 1u)) break;
+				/* some groups did not fit: grow to the totals (now known) and emit again */
+			}
+			sz.num_vertices = totals[0];
+			sz.num_indices = totals[1];
+		} else if (numPieces) {
 			if (dPos.ensure(totals[0] * 8 + 32, err) || dCol.ensure(totals[0] * 4 + 32, err) || dIdx.ensure(totals[1] * idxBytes + 32, err))
 				return VGB_ERR_CUDA;
 			pa.pos = dPos.as<float2>();
@@ -2172,10 +2601,27 @@ public:
 		return 0;
 	}
 
+	/* single-pass runs of known sizes: did the kernel raise a flag (never expected)? */
+	int checkSp(std::string* err)
+	{
+		if (!spUnchecked) return 0;
+		spUnchecked = false;
+		uint32_t f = 0;
+		if (readback(&f, dTicket.as<uint32_t>() + 1, 4, err)) return VGB_ERR_CUDA;
+		if (f) {
+			spMode = 0; /* this batch object goes back to the two-pass pipeline */
+			ran = false;
+			if (err) *err = "single-pass emit did not complete (flags " + std::to_string(f) + "): run again";
+			return VGB_ERR_CUDA;
+		}
+		return 0;
+	}
+
 	int sync(std::string* err) override
 	{
 		VGB_CUDA(cudaSetDevice(dev));
 		VGB_CUDA(cudaStreamSynchronize(st));
+		if (const int rc = checkSp(err)) return rc;
 		if (ran) {
 			cudaEventElapsedTime(&rt.total, ev[0], ev[3]);
 			cudaEventElapsedTime(&rt.flatten, ev[0], ev[1]);
@@ -2370,6 +2816,7 @@ public:
 			return VGB_ERR_STATE;
 		}
 		VGB_CUDA(cudaSetDevice(dev));
+		if (const int rc = checkSp(err)) return rc;
 		if ((pos || color) && vcap < sz.num_vertices) {
 			if (err) *err = "vertex capacity too small";
 			return VGB_ERR_CAPACITY;
