@@ -1579,7 +1579,7 @@ __device__ __forceinline__ SpLook spLookBack(const PieceArgs& a, uint32_t w, uin
 			for (;;) {
 				wa = spLoad(a.spA + u);
 				if ((wa.x >> 28) == 0x5u) break;
-				__nanosleep(40);
+				__nanosleep(20);
 				if (++polls >= SP_POLL_LIMIT || ((polls & 1023u) == 0 && (*(volatile uint32_t*)a.spFlags & 2u))) {
 					gaveUp = true;
 					break;
@@ -1658,8 +1658,11 @@ __global__ void __launch_bounds__(128, (OPS == OPS_STROKE_AA && JT < 3) ? VGB_EM
 	const uint32_t g = w * 32 + lane;
 	const bool valid = g < a.numPieces;
 	const uint32_t j = rec.x;
+	/* chunkShift doubles as the ticket policy here: 0 = drawn one group ahead (its piece records are prefetched, but the
+	 * id is taken a whole group time before its totals appear), 1 = drawn when the group starts (nothing prefetched) */
+	const bool lateTicket = a.chunkShift != 0;
 	uint32_t ticketNext = 0;
-	if (lane == 0) ticketNext = atomicAdd(a.ticket, 1u); /* consumed after the totals are published */
+	if (!lateTicket && lane == 0) ticketNext = atomicAdd(a.ticket, 1u); /* consumed after the totals are published */
 	JobCtx J;
 	Piece P;
 	uint32_t q = 0, ps = 0;
@@ -1701,9 +1704,9 @@ __global__ void __launch_bounds__(128, (OPS == OPS_STROKE_AA && JT < 3) ? VGB_EM
 	if (lane == 0) {
 		spStore(a.spA + w, spWordA(totV, totI, tail31, lastLocal, spans));
 	}
-	const uint32_t wn = W + __shfl_sync(0xffffffffu, ticketNext, 0);
+	uint32_t wn = W + __shfl_sync(0xffffffffu, ticketNext, 0);
 	uint2 recN = make_uint2(0u, 0u);
-	if (wn < numGroups && wn * 32 + lane < a.numPieces) recN = a.pieceRec[wn * 32 + lane];
+	if (!lateTicket && wn < numGroups && wn * 32 + lane < a.numPieces) recN = a.pieceRec[wn * 32 + lane];
 	uint64_t exV = 0, exI = 0;
 	uint32_t carryIn = 0, tw0 = 0;
 	if (w > 0) {
@@ -1721,7 +1724,7 @@ __global__ void __launch_bounds__(128, (OPS == OPS_STROKE_AA && JT < 3) ? VGB_EM
 		spStore(a.spP + w, spWordP(runV, runI, spans ? carryIn + totV : lastLocal));
 	}
 #if VGB_EMIT_PREFETCH
-	if (wn < numGroups && wn * 32 + lane < a.numPieces) {
+	if (!lateTicket && wn < numGroups && wn * 32 + lane < a.numPieces) {
 		asm volatile("prefetch.global.L2 [%0];" ::"l"(a.pts + recN.y));
 		asm volatile("prefetch.global.L2 [%0];" ::"l"(a.jobRec + recN.x));
 	}
@@ -1791,6 +1794,13 @@ __global__ void __launch_bounds__(128, (OPS == OPS_STROKE_AA && JT < 3) ? VGB_EM
 		emitAnyCold<OPS, JT, CT>(a.pts, J, P, F, prev, S);
 	}
 	/* next group */
+	if (lateTicket) {
+		uint32_t t = 0;
+		if (lane == 0) t = atomicAdd(a.ticket, 1u);
+		wn = W + __shfl_sync(0xffffffffu, t, 0);
+		recN = make_uint2(0u, 0u);
+		if (wn < numGroups && wn * 32 + lane < a.numPieces) recN = a.pieceRec[wn * 32 + lane];
+	}
 	w = wn;
 	rec = recN;
 	if (w >= numGroups) {
@@ -2155,13 +2165,13 @@ public:
 		 * publishes the 4th three groups later than the 1st, every later ticket waits for it, and the waits chain
 		 * up over the whole launch (measured: 2.9 s instead of 1 ms on the headline workload) */
 		PieceArgs q = pa;
-		static int spChunk = -1;
-		if (spChunk < 0) {
-			const char* e = getenv("VGB_SP_CHUNK_SHIFT"); /* diagnosis only */
-			spChunk = e ? atoi(e) : 0;
+		static int spLate = -1;
+		if (spLate < 0) {
+			const char* e = getenv("VGB_SP_LATE_TICKET"); /* 1: draw a group's ticket when the group starts */
+			spLate = e ? atoi(e) : 0;
 		}
-		q.chunkShift = (uint32_t)spChunk;
-		const uint32_t need = (gridBlocks + (1u << q.chunkShift) - 1) >> q.chunkShift;
+		q.chunkShift = spLate ? 1u : 0u; /* the single-pass kernel reads it as the ticket policy */
+		const uint32_t need = gridBlocks;
 		if (getenv("VGB_DEBUG")) fprintf(stderr, "[vgb] single-pass emit grid: perSM %d blocks %u of %u\n", perSM, need < cap ? need : cap, gridBlocks);
 		k_group_emit_sp<IDX, OPS, JT, CT, BIGI><<<need < cap ? need : cap, PPB, 0, st>>>(q);
 	}
