@@ -111,7 +111,7 @@ def test_decoded_list_meshes_match_reference(sincos, gpu_batch, ref):
         np.testing.assert_array_equal(out[k], exp[k], err_msg=k)
 
 
-def _random_list(seed, n_ops=400):
+def _random_list(seed, n_ops=400, concave=True):
     """random but well-formed command stream: every path command sits inside a BeginPath, pops never underflow"""
     rng = np.random.default_rng(seed)
     w = CL.Writer()
@@ -156,7 +156,7 @@ def _random_list(seed, n_ops=400):
                      CL.stroke_flags(int(rng.integers(0, 3)), int(rng.integers(0, 3)), bool(rng.integers(0, 2)), bool(rng.random() < 0.2)))
         elif u < 0.74:
             drawn = True
-            w.fill(int(rng.integers(0, 1 << 32)), CL.fill_flags(concave=bool(rng.random() < 0.15), aa=bool(rng.integers(0, 2))))
+            w.fill(int(rng.integers(0, 1 << 32)), CL.fill_flags(concave=bool(rng.random() < 0.15) and concave, aa=bool(rng.integers(0, 2))))
         elif u < 0.80:
             if depth < 20:
                 w.push_state()
