@@ -293,7 +293,9 @@ typedef struct vgb_cl_stats {
 	uint32_t nested;      /* SubmitCommandList commands executed                     */
 	uint32_t scissor_changes; /* recorded draws before which vg.cpp forces a new DrawCommand because of the scissor
 	                       * (m_ForceNewDrawCommand: every Set/Intersect/ResetScissor, and PopState when the restored rect
-	                       * differs from the last draw's; vg.cpp:3946-4033, 5359-5405).  The batch carries them
+	                       * differs from the last draw's; vg.cpp:3946-4033, 5359-5405) -- or before which this decoder
+	                       * skipped a draw it does not handle (paints, text, clips, concave fills: the caller's own
+	                       * geometry belongs between the two draw commands).  The batch carries the marks
 	                       * (vgb_batch_set_scissor): the final layout starts a new draw command there */
 } vgb_cl_stats;
 

@@ -248,3 +248,22 @@ def test_collapsed_transform_does_not_abort_the_list():
     a, b = got.recorded_streams(), expect.recorded_streams()
     for k in ("cmd", "data", "draw_op", "draw_color", "draw_width", "path_scale"):
         np.testing.assert_array_equal(a[k], b[k], err_msg=k)
+
+
+def test_skipped_draws_leave_an_ordering_marker():
+    """a draw the decoder does not handle (gradient fill, concave fill, text ...) sits between two colour draws: the batch
+    must not let them share a draw command -- the caller's own geometry for the skipped draw goes in between.  The mark is
+    the one a scissor change leaves (vgb_batch_recorded_draw_scissor bit 31)."""
+    import struct
+    w = CL.Writer()
+    w.begin_path().rect(10, 10, 50, 40).fill(0xFF778899, CL.fill_flags())
+    w.begin_path().circle(100, 100, 30).fill(0xFF112233, CL.fill_flags())                       # merges with the first
+    w.begin_path().rect(0, 0, 20, 20).raw(CL.FILL_GRADIENT, struct.pack("<IHH", 4, 0, 0))       # skipped: another draw type
+    w.begin_path().circle(200, 100, 30).fill(0xFF445566, CL.fill_flags())                       # new command
+    w.begin_path().move_to(0, 0).line_to(50, 0).line_to(25, 40).line_to(60, 60).close_path().fill(0xFF000000, CL.fill_flags(concave=True))  # skipped
+    w.stroke(0xFFFFFFFF, 2.0, CL.stroke_flags(1, 1, True))                                      # new command
+    w.begin_path().rect(5, 5, 9, 9).stroke(0xFF00FF00, 1.5, CL.stroke_flags(0, 0, True))        # merges
+    got = vgb.Batch(-1)
+    st = got.submit_command_list(w.bytes(), vgb.make_cl_context())
+    assert st.unsupported == 2 and st.draws == 5 and st.scissor_changes == 2
+    np.testing.assert_array_equal(got.recorded_draw_scissor() >> 31, [0, 0, 1, 1, 0])

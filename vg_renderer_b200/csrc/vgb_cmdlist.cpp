@@ -195,6 +195,7 @@ int runList(Run& R, const void* buffer, uint32_t size, uint32_t listFlags)
 			const uint32_t color = rd<uint32_t>(p);
 			if (inClip || (flags & 0x01u) != 0) { /* clip geometry / PathType::Concave (libtess2): not on this path */
 				++st.unsupported;
+				R.force = true; /* an ordering marker: the caller's own geometry goes between two draw commands */
 				break;
 			}
 			/* ctxFillPathColor, vg.cpp:3071-3076 */
@@ -216,6 +217,7 @@ int runList(Run& R, const void* buffer, uint32_t size, uint32_t listFlags)
 			const uint32_t color = rd<uint32_t>(p);
 			if (inClip) {
 				++st.unsupported;
+				R.force = true;
 				break;
 			}
 			/* ctxStrokePathColor, vg.cpp:3411-3437 */
@@ -240,8 +242,13 @@ int runList(Run& R, const void* buffer, uint32_t size, uint32_t listFlags)
 			++st.draws;
 		} break;
 		case CL_FillPathGradient: case CL_FillPathImagePattern: case CL_StrokePathGradient: case CL_StrokePathImagePattern:
-		case CL_IndexedTriList: case CL_CreateLinearGradient: case CL_CreateBoxGradient: case CL_CreateRadialGradient:
-		case CL_CreateImagePattern: case CL_Text: case CL_TextBox: case CL_ResetClip:
+		case CL_IndexedTriList: case CL_Text: case CL_TextBox: case CL_ResetClip:
+			/* draws of another DrawCommand type (or clip state) in the reference: what the batch records around them
+			 * must not share a draw command, so the caller can put its own geometry in between */
+			++st.unsupported;
+			R.force = true;
+			break;
+		case CL_CreateLinearGradient: case CL_CreateBoxGradient: case CL_CreateRadialGradient: case CL_CreateImagePattern:
 			++st.unsupported;
 			break;
 		case CL_SubmitCommandList: { /* vg.cpp:4620-4626 */
@@ -258,8 +265,8 @@ int runList(Run& R, const void* buffer, uint32_t size, uint32_t listFlags)
 			rc = runList(R, ctx->lists[id].commands, ctx->lists[id].size, ctx->lists[id].flags);
 			s = &stack.back(); /* the nested list may have pushed / popped states */
 		} break;
-		case CL_BeginClip: inClip = true; ++st.unsupported; break;
-		case CL_EndClip: inClip = false; break;
+		case CL_BeginClip: inClip = true; ++st.unsupported; R.force = true; break;
+		case CL_EndClip: inClip = false; R.force = true; break;
 		case CL_PushState: /* vg.cpp:3934-3944 */
 			if (stack.size() >= kMaxStates) { rc = fail(VGB_ERR_INVALID, "state stack overflow"); break; }
 			stack.push_back(stack.back());
