@@ -146,3 +146,37 @@ def test_bulk_zero_copy_recorded_counts():
         b.add_cubic_strokes(p8)
     b.reset(1.0)
     b.begin_path().move_to(0, 0)
+
+
+def test_scissor_table_and_marks():
+    """vgb_batch_set_scissor: one table entry per distinct uint16-truncated rect (id 0 = never set), the force flag waits
+    for a draw that has meshes, is dropped before the first draw, and reset() forgets everything"""
+    b = vgb.Batch(-1)
+    assert b.scissor_rects().tolist() == [[0, 0, 0, 0]]
+
+    def draw(with_path=True):
+        b.begin_path(1.0, 0.25)
+        if with_path:
+            b.move_to(0, 0)
+            b.line_to(10, 0)
+            b.line_to(10, 10)
+        b.stroke(vgb.OP_STROKE_AA, 0xFFFFFFFF, 2.0, 0, 0)
+
+    b.set_scissor([1.9, 2.2, 300.7, 200.0], True)      # before the first draw: nothing to break
+    draw()
+    b.set_scissor([1.1, 2.9, 300.2, 200.9], True)      # the same rect after truncation: same id, but the flag is up
+    draw(with_path=False)                              # no sub-path, no mesh: the flag waits
+    draw()
+    b.set_scissor([5, 6, 7, 8], False)                 # another rect, no forced command (a caller that knows better)
+    draw()
+    b.set_scissor([1, 2, 300, 200], True)
+    draw()
+    ds = b.recorded_draw_scissor()
+    np.testing.assert_array_equal(ds >> 31, [0, 0, 1, 0, 1])
+    np.testing.assert_array_equal(ds & 0x7FFFFFFF, [1, 1, 1, 2, 1])
+    assert b.scissor_rects().tolist() == [[0, 0, 0, 0], [1, 2, 300, 200], [5, 6, 7, 8]]
+    np.testing.assert_array_equal(b.recorded_mesh_scissor() >> 31, [0, 1, 0, 1])   # one mesh per draw that has a sub-path
+    with pytest.raises(vgb.VgbError):
+        b.set_scissor([0, 0, float("nan"), 1], True)
+    b.reset(1.0)
+    assert b.scissor_rects().tolist() == [[0, 0, 0, 0]] and len(b.recorded_draw_scissor()) == 0
