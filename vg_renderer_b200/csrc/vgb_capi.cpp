@@ -367,7 +367,10 @@ int vgb_batch_set_scissor(vgb_batch* b, const float rect[4], int forceNewCommand
 {
 	if (!b || !rect) return fail(VGB_ERR_INVALID, "null argument");
 	if (!finite_all(rect, 4)) return fail(VGB_ERR_NONFINITE, "non-finite scissor rect");
-	const uint16_t r[4] = {(uint16_t)rect[0], (uint16_t)rect[1], (uint16_t)rect[2], (uint16_t)rect[3]}; /* vg.cpp:5392-5395 */
+	/* (uint16_t)scissor[k], vg.cpp:5392-5395.  Negative sizes happen (ctxSetScissor under a mirrored transform); the
+	 * reference's x86 build stores them modulo 2^16: spelled out so that it is defined behaviour and the same everywhere */
+	uint16_t r[4];
+	for (int k = 0; k < 4; ++k) r[k] = (rect[k] > -2147483520.0f && rect[k] < 2147483520.0f) ? (uint16_t)(int32_t)rect[k] : (uint16_t)0;
 	/* one table entry per distinct rect; id 0 is the "no scissor set" entry and is never handed out */
 	const uint64_t key = (uint64_t)r[0] | (uint64_t)r[1] << 16 | (uint64_t)r[2] << 32 | (uint64_t)r[3] << 48;
 	const auto it = b->scissorIds.find(key);

@@ -79,6 +79,14 @@ int fail(int code, const char* msg)
 
 namespace
 {
+/* (uint16_t)scissor[k] as vg.cpp:5392-5395 stores it.  A mirrored transform gives ctxSetScissor a negative size
+ * (vg.cpp:3991-4005), and the reference's x86 build turns that into the value modulo 2^16 (cvttss2si, then the low half):
+ * spelled out here so that it is defined behaviour and the same everywhere (the batch does the same) */
+static inline uint16_t u16sat(float v)
+{
+	return (v > -2147483520.0f && v < 2147483520.0f) ? (uint16_t)(int32_t)v : (uint16_t)0;
+}
+
 struct Run /* what one top-level submit shares with the lists it nests */
 {
 	vgb_batch* b;
@@ -96,7 +104,7 @@ struct Run /* what one top-level submit shares with the lists it nests */
 	/* before a draw is recorded: hand the state's scissor to the batch (vg.cpp stamps it on the DrawCommand) */
 	void noteDraw(const float* sc)
 	{
-		const uint16_t r[4] = {(uint16_t)sc[0], (uint16_t)sc[1], (uint16_t)sc[2], (uint16_t)sc[3]};
+		const uint16_t r[4] = {u16sat(sc[0]), u16sat(sc[1]), u16sat(sc[2]), u16sat(sc[3])};
 		if (anyDraw && force) ++st.scissor_changes;
 		vgb_batch_set_scissor(b, sc, force ? 1 : 0);
 		memcpy(lastScissor, r, sizeof(r));
@@ -106,7 +114,7 @@ struct Run /* what one top-level submit shares with the lists it nests */
 	/* PopState: a new command only if the restored rect differs from the last draw command's (vg.cpp:3950-3966) */
 	void notePop(const float* sc)
 	{
-		const uint16_t r[4] = {(uint16_t)sc[0], (uint16_t)sc[1], (uint16_t)sc[2], (uint16_t)sc[3]};
+		const uint16_t r[4] = {u16sat(sc[0]), u16sat(sc[1]), u16sat(sc[2]), u16sat(sc[3])};
 		if (anyDraw && memcmp(r, lastScissor, sizeof(r)) != 0) force = true;
 	}
 };
