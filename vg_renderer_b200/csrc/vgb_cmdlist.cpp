@@ -82,7 +82,7 @@ namespace
 /* (uint16_t)scissor[k] as vg.cpp:5392-5395 stores it.  A mirrored transform gives ctxSetScissor a negative size
  * (vg.cpp:3991-4005), and the reference's x86 build turns that into the value modulo 2^16 (cvttss2si, then the low half):
  * spelled out here so that it is defined behaviour and the same everywhere (the batch does the same) */
-static inline uint16_t u16sat(float v)
+static inline uint16_t u16trunc(float v)
 {
 	return (v > -2147483520.0f && v < 2147483520.0f) ? (uint16_t)(int32_t)v : (uint16_t)0;
 }
@@ -104,17 +104,19 @@ struct Run /* what one top-level submit shares with the lists it nests */
 	/* before a draw is recorded: hand the state's scissor to the batch (vg.cpp stamps it on the DrawCommand) */
 	void noteDraw(const float* sc)
 	{
-		const uint16_t r[4] = {u16sat(sc[0]), u16sat(sc[1]), u16sat(sc[2]), u16sat(sc[3])};
+		const uint16_t r[4] = {u16trunc(sc[0]), u16trunc(sc[1]), u16trunc(sc[2]), u16trunc(sc[3])};
 		if (anyDraw && force) ++st.scissor_changes;
-		vgb_batch_set_scissor(b, sc, force ? 1 : 0);
+		/* a non-finite rect (NaN operands in the list) is refused by the batch: the draw then runs under the previous
+		 * rect and the mark stays up for the next one */
+		const bool ok = vgb_batch_set_scissor(b, sc, force ? 1 : 0) == 0;
 		memcpy(lastScissor, r, sizeof(r));
 		anyDraw = true;
-		force = false;
+		if (ok) force = false;
 	}
 	/* PopState: a new command only if the restored rect differs from the last draw command's (vg.cpp:3950-3966) */
 	void notePop(const float* sc)
 	{
-		const uint16_t r[4] = {u16sat(sc[0]), u16sat(sc[1]), u16sat(sc[2]), u16sat(sc[3])};
+		const uint16_t r[4] = {u16trunc(sc[0]), u16trunc(sc[1]), u16trunc(sc[2]), u16trunc(sc[3])};
 		if (anyDraw && memcmp(r, lastScissor, sizeof(r)) != 0) force = true;
 	}
 };
