@@ -392,3 +392,38 @@ def test_random_lists_against_the_real_context(seed):
     idx, uv, cmds = ref.final_layout(exp["mesh_vtx_off"], exp["mesh_idx_off"], exp["index"], vgb.make_final_cfg(65536), mesh_scissor=got.recorded_mesh_scissor())
     np.testing.assert_array_equal(real["index"], idx)
     assert_cmds_equal_real(real, cmds, got.scissor_rects())
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_random_nested_lists_against_the_real_context(seed):
+    """three fuzz lists as children (one with AllowCommandCulling, later ones submitting earlier ones), a top list that
+    submits them under changing state, an id that is no list: decoder recording + compiled hot path + restated merge step
+    against the real context (400 more seeds of this generator were run once offline: no difference)"""
+    from test_cmdlist import _random_list
+    rng = np.random.default_rng(seed)
+    kids = [(_random_list(seed * 7 + k, n_ops=int(rng.integers(20, 120)), concave=False), int(rng.choice([0, 0, 2]))) for k in range(3)]
+    for w, _ in kids:  # balanced state stacks: the reference does not check overflow in release builds (VG_CHECK, vg.cpp:3936)
+        depth = sum(1 for t, _ in w.ops if t == CL.PUSH_STATE) - sum(1 for t, _ in w.ops if t == CL.POP_STATE)
+        for _ in range(max(depth, 0)):
+            w.pop_state()
+    for k in (1, 2):
+        if rng.random() < 0.6:
+            kids[k][0].submit(int(rng.integers(0, k)))
+    top = CL.Writer().translate(float(np.float32(rng.uniform(0, 50))), 3.0)
+    for _ in range(int(rng.integers(2, 7))):
+        top.submit(int(rng.choice([0, 1, 2, 9])))  # 9: not a list (3 would be the top list itself)
+        if rng.random() < 0.5:
+            top.begin_path().circle(float(np.float32(rng.uniform(50, 400))), 100.0, 20.0).fill(0xFF336699, CL.fill_flags())
+        if rng.random() < 0.3:
+            top.push_state().scale(1.5, 0.75).submit(int(rng.integers(0, 3))).pop_state()
+    cull = 2 if seed % 2 else 0
+    got = vgb.Batch(-1)
+    got.submit_command_list(top.bytes(), vgb.make_cl_context(canvas=(1280.0, 720.0), flags=cull, lists={k: (w.bytes(), fl) for k, (w, fl) in enumerate(kids)}))
+    ref = RefLib("scalar")
+    exp = ref.run_batch(tables_from_recorded(got.recorded_streams()))
+    real = CtxLib().run(top.bytes(), list_flags=cull, canvas=(1280, 720), children=[(w.bytes(), fl) for w, fl in kids])
+    np.testing.assert_array_equal(real["pos"], exp["pos"])
+    np.testing.assert_array_equal(real["color"], exp["color"])
+    idx, uv, cmds = ref.final_layout(exp["mesh_vtx_off"], exp["mesh_idx_off"], exp["index"], vgb.make_final_cfg(65536), mesh_scissor=got.recorded_mesh_scissor())
+    np.testing.assert_array_equal(real["index"], idx)
+    assert_cmds_equal_real(real, cmds, got.scissor_rects())
