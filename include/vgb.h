@@ -372,7 +372,15 @@ VGB_API int vgb_batch_download_final(vgb_batch* b, int16_t* uv, uint64_t vtx_cap
  *                                          cache stores it; inv_xform = NULL skips Tinv
  *     colour copied, uint16 indices copied (per-mesh local) / uint32 merged indices + k * V,
  * V = vertices of the cached run.  The index type is the last run's; not available after a
- * final-layout run.  Mesh (k, m) starts at k*V + mesh_vtx_off[m] / k*I + mesh_idx_off[m]. */
+ * final-layout run.  Mesh (k, m) starts at k*V + mesh_vtx_off[m] / k*I + mesh_idx_off[m].
+ * Scope: ONE matrix per instance for all meshes.  That is bit-for-bit the reference's cache replay for lists that run
+ * under their entry state throughout (checked against vg.cpp's real shape cache, tests/test_vgctx.py).  The reference
+ * keeps an inverse matrix per cached COMMAND (vg.cpp:5788) and re-executes the list's state commands on replay
+ * (clCacheRender): a list with relative transforms inside (translate / scale / rotate / mult) then agrees with the
+ * one-matrix form to rounding only (<= 2.5e-4 at coordinates ~1000, measured), one that resets the transform
+ * (TransformIdentity, SetViewBox) or changes global alpha inside does not -- replay such lists from one batch per group
+ * of commands that share a state.  While RECORDING a cache vg.cpp also tessellates draws whose alpha is zero; a plain run
+ * (this library's decoder included) skips them. */
 VGB_API int vgb_batch_replay(vgb_batch* b, const float* xforms /* n x 6 */, uint32_t n, const float* inv_xform /* 6 or NULL */);
 /* sizes of the replay (num_vertices = n*V, num_indices = n*I, num_meshes = n*M), device pointers, host copy */
 VGB_API int vgb_batch_replay_sizes(vgb_batch* b, vgb_sizes* out);
